@@ -1,0 +1,48 @@
+"""Shared helpers for parity tests (tolerances are stated here once)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import synth
+from oracle.ref_ops import fold_weight_norm
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# north_star: "outputs match the reference PyTorch forward ... to <= 1e-3 rel fp32"
+REL_TOL = 1e-3
+# oracle-vs-reference on the same CPU ATen ops: only summation-order noise is allowed
+ORACLE_TOL = 2e-5
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).double().reshape(-1)
+    b = torch.as_tensor(b).double().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_abs_over_peak(a, b):
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    arrays = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    return meta, arrays
+
+
+def golden_weights(meta):
+    """Regenerate the synthetic checkpoint of a fixture (raw, with weight_g/weight_v)
+    and verify the checksum recorded when the reference produced the golden output."""
+    sd = synth.synth_state_dict([(k, tuple(s)) for k, s in meta["spec"]], meta["seed"], meta["gain"])
+    cs = synth.checksum(sd)
+    assert abs(cs - meta["checksum"]) <= 1e-9 * abs(meta["checksum"]), "synthetic weights drifted from the fixture"
+    return sd
+
+
+def golden_effective_weights(meta):
+    return fold_weight_norm(golden_weights(meta))
