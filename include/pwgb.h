@@ -1,0 +1,111 @@
+/*
+ * pwgb.h -- C ABI of the B200-native vocoder hot path (libpwgb.so).
+ *
+ * The reference (kan-bayashi/ParallelWaveGAN) has no FFI of its own: its seam is
+ * the torch.nn.Module surface.  Each entry point below replaces
+ * the ATen call sequence of one reference forward (cited per function,
+ * file:line relative to /root/reference).  INTEGRATION.md shows the ctypes
+ * stubs a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer to fp32
+ *    data owned by the caller (inputs, outputs, workspaces).  The library never
+ *    allocates, frees or retains device memory and keeps no global state.
+ *  - tensors are (B, C, T) channel-major, time contiguous, like the reference.
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued, never synced.
+ *  - return value: 0 = PWGB_OK, negative = error (see pwgb_status); the message
+ *    is available from pwgb_last_error() (thread local).
+ *  - PWGB_UNSUPPORTED means "this configuration has no kernel"; callers must
+ *    raise, there is no CPU fallback anywhere in the product.
+ */
+#ifndef PWGB_H_
+#define PWGB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PWGB_API __attribute__((visibility("default")))
+#else
+#define PWGB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pwgb_status {
+  PWGB_OK = 0,
+  PWGB_INVALID = -1,     /* bad descriptor / null pointer / size mismatch */
+  PWGB_UNSUPPORTED = -2, /* valid but no kernel for this configuration    */
+  PWGB_CUDA_ERROR = -3   /* launch failed; message holds cudaGetErrorString */
+} pwgb_status;
+
+enum { PWGB_PAD_ZERO = 0, PWGB_PAD_REFLECT = 1, PWGB_PAD_REPLICATE = 2 };
+enum { PWGB_ACT_NONE = 0, PWGB_ACT_TANH = 1, PWGB_ACT_LRELU = 2 };
+
+PWGB_API const char* pwgb_last_error(void);
+/* library version and the SM architecture the kernels were compiled for (100) */
+PWGB_API int pwgb_version(void);
+PWGB_API int pwgb_compiled_arch(void);
+/* number of kernels launched by this thread since the last reset (bench.py's gpu_launches) */
+PWGB_API long long pwgb_launch_count(void);
+PWGB_API void pwgb_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Fused 1-D convolution:  y = [y +] out_scale * ( act( conv(pre(x)) + bias ) + residual )
+ *
+ * Replaces the ATen chains  LeakyReLU -> [Reflection|Zero pad] -> Conv1d -> [act] -> [+x]
+ * of layers/residual_block.py:243-258 (HiFi-GAN ResBlock), layers/residual_stack.py:75-85
+ * (MelGAN), models/hifigan.py:586-601, 354-381 (MSD/MPD towers; the MPD Conv2d (k,1)
+ * over the (B,C,T/P,P) view is `period` = P), models/melgan.py:364-379,
+ * models/parallel_wavegan.py:337-349.
+ * ---------------------------------------------------------------------- */
+typedef struct pwgb_conv1d_desc {
+  int32_t batch;
+  int32_t cin, cout;    /* total channels (all groups)                               */
+  int32_t t_in;         /* logical input rows (per period column)                    */
+  int32_t t_out;        /* output rows                                               */
+  int32_t kernel, stride, dilation, groups;
+  int32_t pad_left;     /* rows of padding on the left (right is implied by t_out)   */
+  int32_t pad_mode;     /* PWGB_PAD_*; reflect/replicate need period == 1            */
+  int32_t period;       /* 1 = plain Conv1d; P>1 = Conv2d (k,1) on the (T/P, P) view */
+  int32_t t_valid;      /* flat source length (<= t_in*period); flat indices beyond
+                           it are reflected (hifigan.py:365-369 F.pad(..,"reflect")) */
+  float pre_slope;      /* LeakyReLU slope applied to x on load (1 = identity)       */
+  int32_t pre_gate;     /* 1: x has 2*cin channels; in = tanh(x[c]) * sigmoid(x[c+cin]) */
+  int32_t post_act;     /* PWGB_ACT_* applied to conv+bias                           */
+  float post_slope;
+  float out_scale;
+  int32_t accumulate;   /* 1: y += result                                            */
+  int32_t shuffle;      /* >1: pixel-shuffle epilogue used by conv_transpose (internal) */
+  int32_t shuffle_pad;
+  int32_t shuffle_tout; /* final output length when shuffle > 1                       */
+  int64_t x_batch_stride; /* elements; 0 = contiguous                                 */
+  int64_t y_batch_stride;
+  int64_t r_batch_stride;
+} pwgb_conv1d_desc;
+
+/* w: (cout, cin/groups, kernel); bias: (cout) or NULL; residual: like y or NULL. */
+PWGB_API int pwgb_conv1d_forward(const pwgb_conv1d_desc* d, const float* x, const float* w, const float* bias,
+                        const float* residual, float* y, void* stream);
+
+/* ------------------------------------------------------------------------
+ * ConvTranspose1d(k, stride s, padding p, output_padding op) with fused pre-LeakyReLU,
+ * poly-phase (no zero stuffing).  models/hifigan.py:94-107, models/melgan.py:86-101.
+ * w: (cin, cout, kernel) -- the reference layout.  ws: workspace of
+ * pwgb_conv_transpose1d_workspace() bytes.  t_out = (t_in-1)*s - 2p + k + op.
+ * ---------------------------------------------------------------------- */
+typedef struct pwgb_convtr1d_desc {
+  int32_t batch, cin, cout, t_in, t_out;
+  int32_t kernel, stride, padding;
+  float pre_slope;
+} pwgb_convtr1d_desc;
+PWGB_API size_t pwgb_conv_transpose1d_workspace(const pwgb_convtr1d_desc* d);
+PWGB_API int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const float* x, const float* w, const float* bias,
+                                  float* y, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PWGB_H_ */

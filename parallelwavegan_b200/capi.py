@@ -1,0 +1,82 @@
+"""ctypes binding of include/pwgb.h (libpwgb.so).  Fails loudly if the library is absent."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libpwgb.so")
+
+PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
+ACT_NONE, ACT_TANH, ACT_LRELU = 0, 1, 2
+
+
+class PwgbError(RuntimeError):
+    pass
+
+
+class Conv1dDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("t_in", C.c_int32), ("t_out", C.c_int32),
+        ("kernel", C.c_int32), ("stride", C.c_int32), ("dilation", C.c_int32), ("groups", C.c_int32),
+        ("pad_left", C.c_int32), ("pad_mode", C.c_int32), ("period", C.c_int32), ("t_valid", C.c_int32),
+        ("pre_slope", C.c_float), ("pre_gate", C.c_int32), ("post_act", C.c_int32), ("post_slope", C.c_float),
+        ("out_scale", C.c_float), ("accumulate", C.c_int32), ("shuffle", C.c_int32), ("shuffle_pad", C.c_int32),
+        ("shuffle_tout", C.c_int32),
+        ("x_batch_stride", C.c_int64), ("y_batch_stride", C.c_int64), ("r_batch_stride", C.c_int64),
+    ]
+
+
+class ConvTr1dDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("t_in", C.c_int32), ("t_out", C.c_int32),
+        ("kernel", C.c_int32), ("stride", C.c_int32), ("padding", C.c_int32), ("pre_slope", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libpwgb.so once.  No fallback: a missing library is a hard error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PwgbError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (needs nvcc). parallelwavegan_b200 has no CPU/PyTorch fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.pwgb_last_error.restype = C.c_char_p
+    L.pwgb_version.restype = C.c_int
+    L.pwgb_compiled_arch.restype = C.c_int
+    L.pwgb_launch_count.restype = C.c_longlong
+    L.pwgb_reset_launch_count.restype = None
+    L.pwgb_conv1d_forward.restype = C.c_int
+    L.pwgb_conv1d_forward.argtypes = [C.POINTER(Conv1dDesc), vp, vp, vp, vp, vp, vp]
+    L.pwgb_conv_transpose1d_workspace.restype = C.c_size_t
+    L.pwgb_conv_transpose1d_workspace.argtypes = [C.POINTER(ConvTr1dDesc)]
+    L.pwgb_conv_transpose1d_forward.restype = C.c_int
+    L.pwgb_conv_transpose1d_forward.argtypes = [C.POINTER(ConvTr1dDesc), vp, vp, vp, vp, vp, C.c_size_t, vp]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().pwgb_last_error().decode("utf-8", "replace")
+        raise PwgbError(f"{what} failed (status {rc}): {msg}")
+
+
+def launch_count():
+    return int(lib().pwgb_launch_count())
+
+
+def reset_launch_count():
+    lib().pwgb_reset_launch_count()
+
+
+EXPORTED_SYMBOLS = [
+    "pwgb_last_error", "pwgb_version", "pwgb_compiled_arch", "pwgb_launch_count", "pwgb_reset_launch_count",
+    "pwgb_conv1d_forward", "pwgb_conv_transpose1d_workspace", "pwgb_conv_transpose1d_forward",
+]

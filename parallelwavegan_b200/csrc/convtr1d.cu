@@ -1,0 +1,78 @@
+// ConvTranspose1d as a poly-phase convolution: a stride-s transposed conv with K taps is
+// s interleaved ordinary convs with ceil(K/s) taps each (no zero stuffing).  The weight is
+// re-laid out on device to the virtual conv  (cout*s, cin, M)  and the generic conv kernel
+// writes through a pixel-shuffle epilogue  o = i*s + phase - padding.
+#include "common.cuh"
+
+namespace pwgb {
+
+int conv1d_forward_simt(const pwgb_conv1d_desc* d, const float* x, const float* w, const float* bias,
+                        const float* residual, float* y, cudaStream_t st);
+
+// w: (cin, cout, K) -> wv: (cout*s, cin, M), wv[co*s+ph][ci][m'] = w[ci][co][ph + (M-1-m')*s]
+__global__ void convtr_weight_kernel(const float* __restrict__ w, float* __restrict__ wv, int cin, int cout, int K,
+                                     int s, int M) {
+  const long long n = (long long)cout * s * cin * M;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int m = (int)(i % M);
+    long long t = i / M;
+    int ci = (int)(t % cin);
+    int cv = (int)(t / cin);
+    int co = cv / s, ph = cv - co * s;
+    int k = ph + (M - 1 - m) * s;
+    wv[i] = k < K ? w[((long long)ci * cout + co) * K + k] : 0.f;
+  }
+}
+
+}  // namespace pwgb
+
+using namespace pwgb;
+
+extern "C" size_t pwgb_conv_transpose1d_workspace(const pwgb_convtr1d_desc* d) {
+  if (!d || d->stride <= 0) return 0;
+  const int M = ceil_div(d->kernel, d->stride);
+  return (size_t)d->cout * d->stride * d->cin * M * sizeof(float);
+}
+
+extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const float* x, const float* w,
+                                             const float* bias, float* y, void* ws, size_t ws_bytes, void* stream) {
+  PWGB_CHECK_ARG(d && x && w && y, "conv_transpose1d: null argument");
+  PWGB_CHECK_ARG(d->batch >= 0 && d->cin > 0 && d->cout > 0 && d->t_in > 0 && d->kernel > 0 && d->stride > 0 &&
+                     d->padding >= 0,
+                 "conv_transpose1d: bad descriptor");
+  const int s = d->stride, K = d->kernel, M = ceil_div(K, s);
+  const int op = d->t_out - ((d->t_in - 1) * s - 2 * d->padding + K);
+  PWGB_CHECK_ARG(op >= 0 && op < s, "conv_transpose1d: t_out=%d inconsistent with t_in=%d k=%d s=%d p=%d", d->t_out,
+                 d->t_in, K, s, d->padding);
+  const size_t need = pwgb_conv_transpose1d_workspace(d);
+  PWGB_CHECK_ARG(ws && ws_bytes >= need, "conv_transpose1d: workspace too small (%zu < %zu)", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* wv = (float*)ws;
+  const long long n = (long long)d->cout * s * d->cin * M;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  convtr_weight_kernel<<<blocks, 256, 0, st>>>(w, wv, d->cin, d->cout, K, s, M);
+  int rc = check_launch("convtr_weight_kernel");
+  if (rc) return rc;
+  pwgb_conv1d_desc c = {};
+  c.batch = d->batch;
+  c.cin = d->cin;
+  c.cout = d->cout * s;
+  c.t_in = d->t_in;
+  c.t_out = (d->t_out - 1 + d->padding) / s + 1;
+  c.kernel = M;
+  c.stride = 1;
+  c.dilation = 1;
+  c.groups = 1;
+  c.pad_left = M - 1;
+  c.pad_mode = PWGB_PAD_ZERO;
+  c.period = 1;
+  c.t_valid = d->t_in;
+  c.pre_slope = d->pre_slope;
+  c.post_act = PWGB_ACT_NONE;
+  c.out_scale = 1.f;
+  c.shuffle = s;
+  c.shuffle_pad = d->padding;
+  c.shuffle_tout = d->t_out;
+  return conv1d_forward_simt(&c, x, wv, bias, nullptr, y, st);
+}

@@ -1,0 +1,228 @@
+"""Host-side mirror of ``parallel_wavegan.layers`` (names, ctor kwargs, state-dict keys).
+
+The ``torch.nn`` modules below are *parameter containers*: they give the same
+``state_dict()`` layout as the reference (including ``weight_g``/``weight_v`` under
+weight norm) but no torch arithmetic runs in ``forward`` -- every forward is a
+sequence of ``libpwgb.so`` kernel calls (``ops``).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .capi import PwgbError
+
+
+def effective_weight(m):
+    """Weight a conv container currently represents.
+
+    * plain parameter (after ``remove_weight_norm``): ``m.weight``
+    * weight norm (``weight_g``, ``weight_v``): ``g * v / ||v||`` -- the same
+      ``torch._weight_norm`` primitive ``torch.nn.utils.weight_norm`` calls in its
+      pre-forward hook (which never runs here because the container is not called)
+    * spectral norm (``weight_orig``, ``weight_u``): one power iteration in training
+      mode, as ``torch.nn.utils.spectral_norm`` does (hifigan.py:613-621).
+    """
+    if hasattr(m, "weight_g"):
+        return torch._weight_norm(m.weight_v, m.weight_g, 0)
+    if hasattr(m, "weight_orig"):
+        w = m.weight_orig
+        w_mat = w.reshape(w.shape[0], -1)
+        u, v = m.weight_u, m.weight_v
+        if m.training:
+            with torch.no_grad():
+                v = torch.nn.functional.normalize(torch.mv(w_mat.t(), u), dim=0, eps=1e-12, out=v)
+                u = torch.nn.functional.normalize(torch.mv(w_mat, v), dim=0, eps=1e-12, out=u)
+                u = u.clone(memory_format=torch.contiguous_format)
+                v = v.clone(memory_format=torch.contiguous_format)
+        sigma = torch.dot(u, torch.mv(w_mat, v))
+        return w / sigma
+    return m.weight
+
+
+def activation_slope(name, params):
+    """Map the reference's (nonlinear_activation, params) to a LeakyReLU slope."""
+    if name == "LeakyReLU":
+        return float((params or {}).get("negative_slope", 0.01))
+    if name == "ReLU":
+        return 0.0
+    raise PwgbError(f"nonlinear_activation={name!r} has no sm_100a kernel (supported: LeakyReLU, ReLU)")
+
+
+class Conv1d(torch.nn.Conv1d):
+    """Conv1d with kaiming init (layers/residual_block.py:19-30)."""
+
+    def reset_parameters(self):
+        torch.nn.init.kaiming_normal_(self.weight, nonlinearity="relu")
+        if self.bias is not None:
+            torch.nn.init.constant_(self.bias, 0.0)
+
+
+class Conv1d1x1(Conv1d):
+    """1x1 Conv1d (layers/residual_block.py:33-40)."""
+
+    def __init__(self, in_channels, out_channels, bias):
+        super().__init__(in_channels, out_channels, kernel_size=1, padding=0, dilation=1, bias=bias)
+
+
+class HiFiGANResidualBlock(torch.nn.Module):
+    """layers/residual_block.py:143-258: 3 x [LReLU -> conv(k, d) -> LReLU -> conv(k, 1)] + x."""
+
+    def __init__(
+        self,
+        kernel_size=3,
+        channels=512,
+        dilations=(1, 3, 5),
+        bias=True,
+        use_additional_convs=True,
+        nonlinear_activation="LeakyReLU",
+        nonlinear_activation_params={"negative_slope": 0.1},
+        use_causal_conv=False,
+    ):
+        super().__init__()
+        if use_causal_conv:
+            raise PwgbError("use_causal_conv=True has no sm_100a kernel yet")
+        assert kernel_size % 2 == 1, "Kernel size must be odd number."
+        self.kernel_size = kernel_size
+        self.dilations = tuple(dilations)
+        self.use_additional_convs = use_additional_convs
+        self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
+        act = getattr(torch.nn, nonlinear_activation)
+        self.convs1 = torch.nn.ModuleList()
+        if use_additional_convs:
+            self.convs2 = torch.nn.ModuleList()
+        for d in dilations:
+            self.convs1 += [
+                torch.nn.Sequential(
+                    act(**nonlinear_activation_params),
+                    torch.nn.Conv1d(channels, channels, kernel_size, 1, dilation=d, bias=bias, padding=(kernel_size - 1) // 2 * d),
+                )
+            ]
+            if use_additional_convs:
+                self.convs2 += [
+                    torch.nn.Sequential(
+                        act(**nonlinear_activation_params),
+                        torch.nn.Conv1d(channels, channels, kernel_size, dilation=1, bias=bias, padding=(kernel_size - 1) // 2),
+                    )
+                ]
+
+    def forward(self, x, out=None, accumulate=False, out_scale=1.0):
+        """Returns block(x); optionally ``out (+)= out_scale * block(x)`` fused into the last conv."""
+        k = self.kernel_size
+        n = len(self.dilations)
+        for idx, d in enumerate(self.dilations):
+            last = idx == n - 1
+            c1 = self.convs1[idx][1]
+            tail = dict(out=out, accumulate=accumulate, out_scale=out_scale) if last else {}
+            if self.use_additional_convs:
+                xt = ops.conv1d(x, effective_weight(c1), c1.bias, dilation=d, padding=(k - 1) // 2 * d, pre_slope=self.slope)
+                c2 = self.convs2[idx][1]
+                x = ops.conv1d(xt, effective_weight(c2), c2.bias, padding=(k - 1) // 2, pre_slope=self.slope, residual=x, **tail)
+            else:
+                x = ops.conv1d(x, effective_weight(c1), c1.bias, dilation=d, padding=(k - 1) // 2 * d, pre_slope=self.slope, residual=x, **tail)
+        return x
+
+
+class ResidualStack(torch.nn.Module):
+    """layers/residual_stack.py:13-85 (MelGAN): LReLU->ReflPad(d)->conv k3 dil d->LReLU->1x1, + 1x1 skip."""
+
+    def __init__(
+        self,
+        kernel_size=3,
+        channels=32,
+        dilation=1,
+        bias=True,
+        nonlinear_activation="LeakyReLU",
+        nonlinear_activation_params={"negative_slope": 0.2},
+        pad="ReflectionPad1d",
+        pad_params={},
+        use_causal_conv=False,
+    ):
+        super().__init__()
+        if use_causal_conv:
+            raise PwgbError("use_causal_conv=True has no sm_100a kernel yet")
+        assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
+        self.pad_mode = pad_mode_of(pad, pad_params)
+        self.kernel_size = kernel_size
+        self.dilation = dilation
+        self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
+        act = getattr(torch.nn, nonlinear_activation)
+        self.stack = torch.nn.Sequential(
+            act(**nonlinear_activation_params),
+            getattr(torch.nn, pad)((kernel_size - 1) // 2 * dilation, **pad_params),
+            torch.nn.Conv1d(channels, channels, kernel_size, dilation=dilation, bias=bias),
+            act(**nonlinear_activation_params),
+            torch.nn.Conv1d(channels, channels, 1, bias=bias),
+        )
+        self.skip_layer = torch.nn.Conv1d(channels, channels, 1, bias=bias)
+
+    def forward(self, c):
+        k, d = self.kernel_size, self.dilation
+        c1, c2, sk = self.stack[2], self.stack[4], self.skip_layer
+        h = ops.conv1d(c, effective_weight(c1), c1.bias, dilation=d, padding=(k - 1) // 2 * d, pad_mode=self.pad_mode, pre_slope=self.slope)
+        s = ops.conv1d(c, effective_weight(sk), sk.bias)
+        return ops.conv1d(h, effective_weight(c2), c2.bias, pre_slope=self.slope, residual=s)
+
+
+def pad_mode_of(pad, pad_params):
+    if pad == "ReflectionPad1d":
+        return "reflect"
+    if pad == "ReplicationPad1d":
+        return "replicate"
+    if pad == "ConstantPad1d" and float((pad_params or {}).get("value", 0.0)) == 0.0:
+        return "zero"
+    raise PwgbError(f"pad={pad!r} {pad_params!r} has no sm_100a kernel (supported: ReflectionPad1d, ReplicationPad1d, zero ConstantPad1d)")
+
+
+def design_prototype_filter(taps=62, cutoff_ratio=0.142, beta=9.0):
+    """Kaiser-window prototype low-pass for the PQMF bank (layers/pqmf.py:14-48); host-side
+    float64 numpy like the reference (``scipy.signal.kaiser`` == np.kaiser's definition)."""
+    assert taps % 2 == 0, "The number of taps mush be even number."
+    assert 0.0 < cutoff_ratio < 1.0, "Cutoff ratio must be > 0.0 and < 1.0."
+    omega_c = np.pi * cutoff_ratio
+    n = np.arange(taps + 1) - 0.5 * taps
+    with np.errstate(invalid="ignore", divide="ignore"):
+        h_i = np.sin(omega_c * n) / (np.pi * n)
+    h_i[taps // 2] = np.cos(0) * cutoff_ratio
+    M = taps + 1
+    alpha = (M - 1) / 2.0
+    w = np.i0(beta * np.sqrt(1 - ((np.arange(M) - alpha) / alpha) ** 2.0)) / np.i0(beta)
+    return h_i * w
+
+
+class PQMF(torch.nn.Module):
+    """Pseudo-QMF analysis / synthesis (layers/pqmf.py:51-149).
+
+    analysis  = one strided FIR launch (the reference's stride-N identity
+    ``updown_filter`` conv is the ``stride`` of the kernel -- an exact index op);
+    synthesis = one poly-phase transposed FIR launch (no zero-stuffed tensor)."""
+
+    def __init__(self, subbands=4, taps=62, cutoff_ratio=0.142, beta=9.0):
+        super().__init__()
+        h_proto = design_prototype_filter(taps, cutoff_ratio, beta)
+        h_analysis = np.zeros((subbands, len(h_proto)))
+        h_synthesis = np.zeros((subbands, len(h_proto)))
+        for k in range(subbands):
+            ph = (2 * k + 1) * (np.pi / (2 * subbands)) * (np.arange(taps + 1) - (taps / 2))
+            h_analysis[k] = 2 * h_proto * np.cos(ph + (-1) ** k * np.pi / 4)
+            h_synthesis[k] = 2 * h_proto * np.cos(ph - (-1) ** k * np.pi / 4)
+        self.register_buffer("analysis_filter", torch.from_numpy(h_analysis).float().unsqueeze(1))
+        self.register_buffer("synthesis_filter", torch.from_numpy(h_synthesis).float().unsqueeze(0))
+        updown_filter = torch.zeros((subbands, subbands, subbands)).float()
+        for k in range(subbands):
+            updown_filter[k, k, 0] = 1.0
+        self.register_buffer("updown_filter", updown_filter)
+        self.subbands = subbands
+        self.taps = taps
+
+    def analysis(self, x):
+        """(B, 1, T) -> (B, subbands, T // subbands)."""
+        return ops.conv1d(x, self.analysis_filter, None, stride=self.subbands, padding=self.taps // 2)
+
+    def synthesis(self, x):
+        """(B, subbands, T // subbands) -> (B, 1, T).  Transposed-FIR form of
+        ``conv1d(pad(zero_stuff(x) * N), synthesis_filter)``: w[b, 0, k'] = N * h[b, taps - k']."""
+        n = self.subbands
+        w = (self.synthesis_filter[0].flip(-1) * float(n)).unsqueeze(1).contiguous()  # (N, 1, taps+1)
+        return ops.conv_transpose1d(x, w, None, stride=n, padding=self.taps // 2, output_padding=n - 1)

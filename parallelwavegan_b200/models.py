@@ -1,0 +1,273 @@
+"""Host-side mirror of ``parallel_wavegan.models``: same class names, constructor
+kwargs, ``forward`` / ``inference`` signatures and ``state_dict()`` keys, so that
+``getattr(models, config["generator_type"])(**config["generator_params"])``
+(train.py:1364-1381, utils/utils.py:317-330) and reference checkpoints work
+unchanged.  Forward passes run only on CUDA through ``libpwgb.so``.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import ops
+from .capi import PwgbError
+from .layers import HiFiGANResidualBlock as ResidualBlock
+from .layers import ResidualStack, activation_slope, effective_weight, pad_mode_of
+
+
+def _read_stats(stats):
+    assert stats.endswith(".h5") or stats.endswith(".npy")
+    if stats.endswith(".h5"):
+        import h5py  # optional dependency, as in the reference (utils/utils.py:83-117)
+
+        with h5py.File(stats, "r") as f:
+            mean = f["mean"][()].reshape(-1)
+            scale = f["scale"][()].reshape(-1)
+    else:
+        mean = np.load(stats)[0].reshape(-1)
+        scale = np.load(stats)[1].reshape(-1)
+    return mean, scale
+
+
+class _GeneratorBase(torch.nn.Module):
+    def remove_weight_norm(self):
+        def _remove_weight_norm(m):
+            try:
+                torch.nn.utils.remove_weight_norm(m)
+            except ValueError:
+                return
+
+        self.apply(_remove_weight_norm)
+
+    def register_stats(self, stats):
+        mean, scale = _read_stats(stats)
+        self.register_buffer("mean", torch.from_numpy(mean).float())
+        self.register_buffer("scale", torch.from_numpy(scale).float())
+        logging.info("Successfully registered stats as buffer.")
+
+    def _prep_inference_input(self, c, normalize_before):
+        if not isinstance(c, torch.Tensor):
+            c = torch.tensor(c, dtype=torch.float).to(next(self.parameters()).device)
+        if normalize_before:
+            c = (c - self.mean) / self.scale
+        return c.transpose(1, 0).unsqueeze(0).contiguous()
+
+
+class HiFiGANGenerator(_GeneratorBase):
+    """models/hifigan.py:23-267."""
+
+    def __init__(
+        self,
+        in_channels=80,
+        out_channels=1,
+        channels=512,
+        kernel_size=7,
+        upsample_scales=(8, 8, 2, 2),
+        upsample_kernel_sizes=(16, 16, 4, 4),
+        resblock_kernel_sizes=(3, 7, 11),
+        resblock_dilations=[(1, 3, 5), (1, 3, 5), (1, 3, 5)],
+        use_additional_convs=True,
+        bias=True,
+        nonlinear_activation="LeakyReLU",
+        nonlinear_activation_params={"negative_slope": 0.1},
+        use_causal_conv=False,
+        use_weight_norm=True,
+    ):
+        super().__init__()
+        if use_causal_conv:
+            raise PwgbError("HiFiGANGenerator(use_causal_conv=True) has no sm_100a kernel yet")
+        assert kernel_size % 2 == 1, "Kernel size must be odd number."
+        assert len(upsample_scales) == len(upsample_kernel_sizes)
+        assert len(resblock_dilations) == len(resblock_kernel_sizes)
+        self.num_upsamples = len(upsample_kernel_sizes)
+        self.num_blocks = len(resblock_kernel_sizes)
+        self.use_causal_conv = use_causal_conv
+        self.kernel_size = kernel_size
+        self.upsample_scales = tuple(upsample_scales)
+        self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
+        act = getattr(torch.nn, nonlinear_activation)
+        self.input_conv = torch.nn.Conv1d(in_channels, channels, kernel_size, bias=bias, padding=(kernel_size - 1) // 2)
+        self.upsamples = torch.nn.ModuleList()
+        self.blocks = torch.nn.ModuleList()
+        for i in range(len(upsample_kernel_sizes)):
+            assert upsample_kernel_sizes[i] == 2 * upsample_scales[i]
+            s = upsample_scales[i]
+            self.upsamples += [
+                torch.nn.Sequential(
+                    act(**nonlinear_activation_params),
+                    torch.nn.ConvTranspose1d(
+                        channels // (2**i), channels // (2 ** (i + 1)), upsample_kernel_sizes[i], s,
+                        padding=s // 2 + s % 2, output_padding=s % 2, bias=bias,
+                    ),
+                )
+            ]
+            for j in range(len(resblock_kernel_sizes)):
+                self.blocks += [
+                    ResidualBlock(
+                        kernel_size=resblock_kernel_sizes[j],
+                        channels=channels // (2 ** (i + 1)),
+                        dilations=resblock_dilations[j],
+                        bias=bias,
+                        use_additional_convs=use_additional_convs,
+                        nonlinear_activation=nonlinear_activation,
+                        nonlinear_activation_params=nonlinear_activation_params,
+                        use_causal_conv=use_causal_conv,
+                    )
+                ]
+        self.output_conv = torch.nn.Sequential(
+            torch.nn.LeakyReLU(),  # default slope 0.01 (hifigan.py:139-142)
+            torch.nn.Conv1d(channels // (2 ** (i + 1)), out_channels, kernel_size, bias=bias, padding=(kernel_size - 1) // 2),
+            torch.nn.Tanh(),
+        )
+        if use_weight_norm:
+            self.apply_weight_norm()
+        self.reset_parameters()
+
+    def forward(self, c):
+        """(B, in_channels, T) -> (B, out_channels, T * prod(upsample_scales))  (hifigan.py:173-192)."""
+        pad = (self.kernel_size - 1) // 2
+        ic = self.input_conv
+        c = ops.conv1d(c, effective_weight(ic), ic.bias, padding=pad)
+        nb = self.num_blocks
+        for i in range(self.num_upsamples):
+            up = self.upsamples[i][1]
+            s = self.upsample_scales[i]
+            c = ops.conv_transpose1d(c, effective_weight(up), up.bias, stride=s, padding=s // 2 + s % 2,
+                                     output_padding=s % 2, pre_slope=self.slope)
+            cs = torch.empty_like(c)
+            for j in range(nb):  # cs = sum_j block_j(c) / nb, fused into each block's last conv
+                self.blocks[i * nb + j](c, out=cs, accumulate=j > 0, out_scale=1.0 / nb)
+            c = cs
+        oc = self.output_conv[1]
+        return ops.conv1d(c, effective_weight(oc), oc.bias, padding=pad, pre_slope=0.01, post_act="tanh")
+
+    def reset_parameters(self):
+        def _reset_parameters(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                m.weight.data.normal_(0.0, 0.01)
+
+        self.apply(_reset_parameters)
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+    def inference(self, c, normalize_before=False):
+        """(T, in_channels) -> (T * prod(upsample_scales), out_channels)  (hifigan.py:251-267)."""
+        c = self.forward(self._prep_inference_input(c, normalize_before))
+        return c.squeeze(0).transpose(1, 0)
+
+
+class MelGANGenerator(_GeneratorBase):
+    """models/melgan.py:17-257 (also the multi-band generator with out_channels=4)."""
+
+    def __init__(
+        self,
+        in_channels=80,
+        out_channels=1,
+        kernel_size=7,
+        channels=512,
+        bias=True,
+        upsample_scales=[8, 8, 2, 2],
+        stack_kernel_size=3,
+        stacks=3,
+        nonlinear_activation="LeakyReLU",
+        nonlinear_activation_params={"negative_slope": 0.2},
+        pad="ReflectionPad1d",
+        pad_params={},
+        use_final_nonlinear_activation=True,
+        use_weight_norm=True,
+        use_causal_conv=False,
+    ):
+        super().__init__()
+        if use_causal_conv:
+            raise PwgbError("MelGANGenerator(use_causal_conv=True) has no sm_100a kernel yet")
+        assert channels >= np.prod(upsample_scales)
+        assert channels % (2 ** len(upsample_scales)) == 0
+        assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
+        self.kernel_size = kernel_size
+        self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
+        self.pad_mode = pad_mode_of(pad, pad_params)
+        self.use_final_nonlinear_activation = use_final_nonlinear_activation
+        act = getattr(torch.nn, nonlinear_activation)
+        layers = [getattr(torch.nn, pad)((kernel_size - 1) // 2, **pad_params), torch.nn.Conv1d(in_channels, channels, kernel_size, bias=bias)]
+        for i, s in enumerate(upsample_scales):
+            layers += [act(**nonlinear_activation_params)]
+            layers += [
+                torch.nn.ConvTranspose1d(channels // (2**i), channels // (2 ** (i + 1)), s * 2, stride=s,
+                                         padding=s // 2 + s % 2, output_padding=s % 2, bias=bias)
+            ]
+            for j in range(stacks):
+                layers += [
+                    ResidualStack(
+                        kernel_size=stack_kernel_size,
+                        channels=channels // (2 ** (i + 1)),
+                        dilation=stack_kernel_size**j,
+                        bias=bias,
+                        nonlinear_activation=nonlinear_activation,
+                        nonlinear_activation_params=nonlinear_activation_params,
+                        pad=pad,
+                        pad_params=pad_params,
+                        use_causal_conv=use_causal_conv,
+                    )
+                ]
+        layers += [act(**nonlinear_activation_params)]
+        layers += [getattr(torch.nn, pad)((kernel_size - 1) // 2, **pad_params), torch.nn.Conv1d(channels // (2 ** (i + 1)), out_channels, kernel_size, bias=bias)]
+        if use_final_nonlinear_activation:
+            layers += [torch.nn.Tanh()]
+        self.melgan = torch.nn.Sequential(*layers)
+        if use_weight_norm:
+            self.apply_weight_norm()
+        self.reset_parameters()
+        self.pqmf = None
+
+    def forward(self, c):
+        """(B, in_channels, T) -> (B, out_channels, T * prod(upsample_scales))  (melgan.py:168-178)."""
+        pad = (self.kernel_size - 1) // 2
+        mods = list(self.melgan)
+        n = len(mods)
+        pre = 1.0  # slope of a pending activation, fused into the next conv's loader
+        idx = 0
+        while idx < n:
+            m = mods[idx]
+            if isinstance(m, torch.nn.ConvTranspose1d):
+                s = m.stride[0]
+                c = ops.conv_transpose1d(c, effective_weight(m), m.bias, stride=s, padding=m.padding[0],
+                                         output_padding=m.output_padding[0], pre_slope=pre)
+                pre = 1.0
+            elif isinstance(m, torch.nn.Conv1d):
+                final = idx >= n - 2
+                c = ops.conv1d(c, effective_weight(m), m.bias, padding=pad, pad_mode=self.pad_mode, pre_slope=pre,
+                               post_act="tanh" if (final and self.use_final_nonlinear_activation) else None)
+                pre = 1.0
+            elif isinstance(m, ResidualStack):
+                c = m(c)
+            elif isinstance(m, (torch.nn.LeakyReLU, torch.nn.ReLU)):
+                pre = self.slope
+            # padding modules and the final Tanh are fused into the neighbouring conv
+            idx += 1
+        return c
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+    def reset_parameters(self):
+        def _reset_parameters(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                m.weight.data.normal_(0.0, 0.02)
+
+        self.apply(_reset_parameters)
+
+    def inference(self, c, normalize_before=False):
+        """(T, in_channels) -> (T * prod(upsample_scales) [* subbands], 1)  (melgan.py:239-257)."""
+        c = self.forward(self._prep_inference_input(c, normalize_before))
+        if self.pqmf is not None:
+            c = self.pqmf.synthesis(c)
+        return c.squeeze(0).transpose(1, 0)

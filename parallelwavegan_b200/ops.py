@@ -1,0 +1,126 @@
+"""Tensor-level wrappers over the C ABI (include/pwgb.h).
+
+PyTorch is plumbing here: it owns device memory and the stream.  Every function
+checks that its tensors live on a CUDA device and raises otherwise -- there is no
+CPU path in this package.
+"""
+import ctypes as C
+
+import torch
+
+from . import capi
+from .capi import ACT_LRELU, ACT_NONE, ACT_TANH, PAD_REFLECT, PAD_REPLICATE, PAD_ZERO, PwgbError
+
+_PAD = {"zero": PAD_ZERO, "zeros": PAD_ZERO, "reflect": PAD_REFLECT, "replicate": PAD_REPLICATE}
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "tanh": ACT_TANH, "lrelu": ACT_LRELU}
+
+
+def _dev(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise PwgbError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise PwgbError(f"{name}: tensor is on {t.device}; parallelwavegan_b200 only runs on CUDA (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise PwgbError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def conv1d(
+    x,
+    w,
+    bias=None,
+    *,
+    stride=1,
+    padding=0,
+    dilation=1,
+    groups=1,
+    pad_mode="zero",
+    pre_slope=1.0,
+    pre_gate=False,
+    post_act=None,
+    post_slope=0.0,
+    residual=None,
+    out_scale=1.0,
+    out=None,
+    accumulate=False,
+    period=1,
+):
+    """y = [y +] out_scale * (act(conv(pre(x)) + bias) + residual)   -- pwgb_conv1d_forward.
+
+    ``padding``: int or (left, right) rows.  ``period`` > 1 treats x as the
+    (B, C, ceil(L/P), P) view of HiFiGANPeriodDiscriminator (reflect-extended to a
+    multiple of P, hifigan.py:365-369) and returns a 4-D tensor."""
+    x = _dev(x, "x")
+    w = _dev(w, "w")
+    if w.dim() == 4:  # Conv2d (k, 1) weights of the period discriminators
+        w = w.reshape(w.shape[0], w.shape[1], w.shape[2])
+    B, cin_x = x.shape[0], x.shape[1]
+    L = x.numel() // max(B * cin_x, 1)
+    cout, cin_g, K = w.shape
+    cin = cin_g * groups
+    if cin_x != cin * (2 if pre_gate else 1):
+        raise PwgbError(f"conv1d: x has {cin_x} channels, weight expects {cin}")
+    P = int(period)
+    t_in = (L + P - 1) // P
+    pl, pr = (padding, padding) if isinstance(padding, int) else padding
+    t_out = (t_in + pl + pr - dilation * (K - 1) - 1) // stride + 1
+    if t_out < 0:
+        raise PwgbError("conv1d: input shorter than the receptive field")
+    shape = (B, cout, t_out) if P == 1 else (B, cout, t_out, P)
+    if out is None:
+        if accumulate:
+            raise PwgbError("conv1d: accumulate needs `out`")
+        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    else:
+        out = _dev(out, "out")
+        if tuple(out.shape) != shape:
+            raise PwgbError(f"conv1d: out has shape {tuple(out.shape)}, expected {shape}")
+    if residual is not None:
+        residual = _dev(residual, "residual")
+        if residual.numel() != out.numel():
+            raise PwgbError("conv1d: residual shape mismatch")
+        if residual.data_ptr() == out.data_ptr():
+            raise PwgbError("conv1d: residual must not alias out")
+    if bias is not None:
+        bias = _dev(bias, "bias")
+    d = capi.Conv1dDesc(
+        batch=B, cin=cin, cout=cout, t_in=t_in, t_out=t_out, kernel=K, stride=stride, dilation=dilation,
+        groups=groups, pad_left=pl, pad_mode=_PAD[pad_mode], period=P, t_valid=L, pre_slope=float(pre_slope),
+        pre_gate=int(bool(pre_gate)), post_act=_ACT[post_act], post_slope=float(post_slope),
+        out_scale=float(out_scale), accumulate=int(bool(accumulate)), shuffle=0, shuffle_pad=0, shuffle_tout=0,
+        x_batch_stride=0, y_batch_stride=0, r_batch_stride=0,
+    )
+    rc = capi.lib().pwgb_conv1d_forward(C.byref(d), _p(x), _p(w), _p(bias), _p(residual), _p(out), _stream())
+    capi.check(rc, "pwgb_conv1d_forward")
+    return out
+
+
+def conv_transpose1d(x, w, bias=None, *, stride, padding=0, output_padding=0, pre_slope=1.0):
+    """ConvTranspose1d with fused pre-LeakyReLU -- pwgb_conv_transpose1d_forward.
+    w is the reference layout (cin, cout, k)."""
+    x = _dev(x, "x")
+    w = _dev(w, "w")
+    B, cin, t_in = x.shape
+    if w.shape[0] != cin:
+        raise PwgbError(f"conv_transpose1d: x has {cin} channels, weight expects {w.shape[0]}")
+    cout, K = w.shape[1], w.shape[2]
+    t_out = (t_in - 1) * stride - 2 * padding + K + output_padding
+    if bias is not None:
+        bias = _dev(bias, "bias")
+    d = capi.ConvTr1dDesc(batch=B, cin=cin, cout=cout, t_in=t_in, t_out=t_out, kernel=K, stride=stride,
+                          padding=padding, pre_slope=float(pre_slope))
+    L = capi.lib()
+    nbytes = L.pwgb_conv_transpose1d_workspace(C.byref(d))
+    ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+    y = torch.empty((B, cout, t_out), device=x.device, dtype=torch.float32)
+    rc = L.pwgb_conv_transpose1d_forward(C.byref(d), _p(x), _p(w), _p(bias), _p(y), _p(ws), C.c_size_t(nbytes), _stream())
+    capi.check(rc, "pwgb_conv_transpose1d_forward")
+    return y

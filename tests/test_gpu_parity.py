@@ -1,0 +1,200 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs golden vectors from the real reference
+and vs the CPU oracle on the same seeded inputs.  Tolerance: rel-L2 <= 1e-3 (north_star);
+the fp32 FFMA kernels are expected to sit near 1e-6."""
+import json
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import REL_TOL, golden_effective_weights, golden_weights, load_golden, max_abs_over_peak, rel_l2
+from oracle import ref_ops, synth
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 2e-5  # exact-arithmetic (FFMA) kernels: summation-order noise only
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import __graft_entry__
+
+    __graft_entry__.build()
+    return torch.device("cuda:0")
+
+
+def test_conv_golden_cases(dev):
+    from parallelwavegan_b200 import ops
+
+    meta, g = load_golden("conv_cases")
+    for case in meta["cases"]:
+        i = case["idx"]
+        x = synth.randn((2, case["cin"], case["T"]), 200 + i).to(dev)
+        b = synth.randn((case["cout"],), 400 + i, 0.1).to(dev)
+        if case["op"] == "conv1d":
+            w = synth.randn((case["cout"], case["cin"] // case["groups"], case["k"]), 300 + i, 0.3).to(dev)
+            y = ops.conv1d(x, w, b, stride=case["stride"], padding=case["padding"], dilation=case["dilation"], groups=case["groups"])
+        else:
+            s = case["stride"]
+            w = synth.randn((case["cin"], case["cout"], case["k"]), 300 + i, 0.3).to(dev)
+            y = ops.conv_transpose1d(x, w, b, stride=s, padding=s // 2 + s % 2, output_padding=s % 2)
+        assert tuple(y.shape) == tuple(g[f"y{i}"].shape), case
+        assert rel_l2(y.cpu(), g[f"y{i}"]) < FP32_TOL, case
+
+
+@pytest.mark.parametrize(
+    "cin,cout,k,stride,dil,groups,pad,mode,T,B",
+    [
+        (64, 64, 3, 1, 1, 1, (1, 1), "zero", 1000, 3),
+        (32, 32, 11, 1, 5, 1, (25, 25), "zero", 777, 2),
+        (48, 48, 3, 1, 9, 1, (9, 9), "reflect", 300, 2),
+        (16, 24, 5, 1, 2, 1, (8, 0), "replicate", 129, 2),
+        (128, 128, 41, 4, 1, 4, (20, 20), "zero", 2048, 2),
+        (128, 256, 41, 4, 1, 16, (20, 20), "zero", 513, 2),
+        (1, 128, 15, 1, 1, 1, (7, 7), "zero", 4096, 2),
+        (64, 1, 7, 1, 1, 1, (3, 3), "zero", 5000, 2),
+        (20, 4, 7, 1, 1, 1, (3, 3), "reflect", 260, 2),
+        (80, 80, 5, 1, 1, 1, (0, 0), "zero", 104, 2),
+        (3, 5, 1, 1, 1, 1, (0, 0), "zero", 1, 1),
+    ],
+)
+def test_conv1d_fused_options(dev, cin, cout, k, stride, dil, groups, pad, mode, T, B):
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((B, cin, T), 1)
+    w = synth.randn((cout, cin // groups, k), 2, 1.0 / (cin // groups * k) ** 0.5)
+    b = synth.randn((cout,), 3, 0.1)
+    xa = F.leaky_relu(x, 0.1)
+    if mode == "zero":
+        xp = F.pad(xa, pad)
+    else:
+        xp = F.pad(xa, pad, mode=mode)
+    conv = F.conv1d(xp, w, b, stride=stride, dilation=dil, groups=groups)
+    res = synth.randn(conv.shape, 4)
+    prev = synth.randn(conv.shape, 5)
+    ref = prev + 0.5 * (torch.tanh(conv) + res)
+    out = prev.clone().to(dev)
+    y = ops.conv1d(x.to(dev), w.to(dev), b.to(dev), stride=stride, padding=pad, dilation=dil, groups=groups,
+                   pad_mode=mode, pre_slope=0.1, post_act="tanh", residual=res.to(dev), out_scale=0.5, out=out, accumulate=True)
+    assert y.data_ptr() == out.data_ptr()
+    assert rel_l2(y.cpu(), ref) < FP32_TOL
+    # plain form
+    y2 = ops.conv1d(x.to(dev), w.to(dev), None, stride=stride, padding=pad, dilation=dil, groups=groups, pad_mode=mode)
+    xp2 = F.pad(x, pad) if mode == "zero" else F.pad(x, pad, mode=mode)
+    assert rel_l2(y2.cpu(), F.conv1d(xp2, w, None, stride=stride, dilation=dil, groups=groups)) < FP32_TOL
+
+
+@pytest.mark.parametrize("period", [2, 3, 5, 7, 11])
+def test_conv1d_period_view(dev, period):
+    """MPD layer semantics (hifigan.py:354-381): reflect-extend to a multiple of P, view (B,C,T/P,P),
+    Conv2d (5,1) stride (3,1) pad (2,0); then a second layer on the 4-D result."""
+    from parallelwavegan_b200 import ops
+
+    B, T = 2, 1000 + period - 3
+    x = synth.randn((B, 1, T), 11)
+    w1 = synth.randn((32, 1, 5, 1), 12, 0.4)
+    b1 = synth.randn((32,), 13, 0.1)
+    w2 = synth.randn((64, 32, 5, 1), 14, 0.08)
+    xr = x
+    if T % period:
+        xr = F.pad(x, (0, period - T % period), "reflect")
+    xv = xr.view(B, 1, -1, period)
+    r1 = F.leaky_relu(F.conv2d(xv, w1, b1, stride=(3, 1), padding=(2, 0)), 0.1)
+    r2 = F.conv2d(r1, w2, None, stride=(3, 1), padding=(2, 0))
+    y1 = ops.conv1d(x.to(dev), w1.to(dev), b1.to(dev), stride=3, padding=2, period=period, post_act="lrelu", post_slope=0.1)
+    assert tuple(y1.shape) == tuple(r1.shape)
+    assert rel_l2(y1.cpu(), r1) < FP32_TOL
+    y2 = ops.conv1d(y1, w2.to(dev), None, stride=3, padding=2, period=period)
+    assert rel_l2(y2.cpu(), r2) < FP32_TOL
+
+
+def _load_mirror(name, dev):
+    from parallelwavegan_b200 import models
+
+    meta, g = load_golden(name)
+    cls = {"hifigan_generator": models.HiFiGANGenerator, "melgan_generator": models.MelGANGenerator,
+           "pwg_generator": getattr(models, "ParallelWaveGANGenerator", None)}[meta["kind"]]
+    if cls is None:
+        pytest.skip("not built yet")
+    m = cls(**json.loads(json.dumps(meta["kwargs"])))
+    m.load_state_dict(golden_weights(meta), strict=True)
+    return meta, g, m.eval().to(dev)
+
+
+@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd"])
+@pytest.mark.parametrize("weight_norm", [True, False])
+def test_hifigan_generator_vs_reference(dev, name, weight_norm):
+    meta, g, m = _load_mirror(name, dev)
+    if not weight_norm:
+        m.remove_weight_norm()
+    c = synth.randn(meta["c_shape"], meta["c_seed"]).to(dev)
+    with torch.no_grad():
+        y = m(c)
+        y_inf = m.inference(c[0].t())
+    assert tuple(y.shape) == tuple(g["y"].shape)
+    assert rel_l2(y.cpu(), g["y"]) < REL_TOL and max_abs_over_peak(y.cpu(), g["y"]) < REL_TOL
+    assert rel_l2(y_inf.cpu(), g["y_inf"]) < REL_TOL
+    # and against the travelling oracle, same weights
+    kw = meta["kwargs"]
+    ref = ref_ops.hifigan_generator(golden_effective_weights(meta), c.cpu(), dict(kw, negative_slope=kw["nonlinear_activation_params"]["negative_slope"]))
+    assert rel_l2(y.cpu(), ref) < REL_TOL
+
+
+@pytest.mark.parametrize("name", ["mb_melgan_v2", "melgan_small"])
+def test_melgan_generator_vs_reference(dev, name):
+    from parallelwavegan_b200.layers import PQMF
+
+    meta, g, m = _load_mirror(name, dev)
+    c = synth.randn(meta["c_shape"], meta["c_seed"]).to(dev)
+    with torch.no_grad():
+        y = m(c)
+    assert rel_l2(y.cpu(), g["y"]) < REL_TOL and max_abs_over_peak(y.cpu(), g["y"]) < REL_TOL
+    if meta.get("pqmf_subbands"):
+        pq = PQMF(meta["pqmf_subbands"]).to(dev)
+        with torch.no_grad():
+            yp = pq.synthesis(y)
+            m.pqmf = pq
+            y_inf = m.inference(c[0].t())
+        assert rel_l2(yp.cpu(), g["y_pqmf"]) < REL_TOL
+        assert rel_l2(y_inf.cpu(), g["y_inf"]) < REL_TOL
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 8])
+def test_pqmf_vs_reference(dev, n):
+    from parallelwavegan_b200.layers import PQMF
+
+    meta, g = load_golden(f"pqmf_{n}")
+    pq = PQMF(n).to(dev)
+    assert torch.equal(pq.analysis_filter.cpu(), g["analysis_filter"])
+    assert torch.equal(pq.synthesis_filter.cpu(), g["synthesis_filter"])
+    x = synth.randn(meta["x_shape"], meta["x_seed"]).to(dev)
+    a = pq.analysis(x)
+    assert tuple(a.shape) == tuple(g["analysis"].shape)
+    assert rel_l2(a.cpu(), g["analysis"]) < FP32_TOL
+    s = pq.synthesis(g["analysis"].to(dev))
+    assert tuple(s.shape) == tuple(g["synthesis"].shape)
+    assert rel_l2(s.cpu(), g["synthesis"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_pqmf_band_interleave_bit_exact(dev, n):
+    """north_star: "bit-exact for PQMF integer banding".  With small-integer signals and
+    filters every partial sum is exact in fp32, so the poly-phase kernels must reproduce the
+    reference's zero-stuff / stride-N index arithmetic (pqmf.py:130-131, 146-149) bit for bit."""
+    from parallelwavegan_b200.layers import PQMF
+
+    pq = PQMF(n).to(dev)
+    gen = torch.Generator().manual_seed(n)
+    an = torch.randint(-3, 4, (n, 1, 63), generator=gen).float()
+    sy = torch.randint(-3, 4, (1, n, 63), generator=gen).float()
+    pq.analysis_filter.copy_(an)
+    pq.synthesis_filter.copy_(sy)
+    x = torch.randint(-8, 9, (3, 1, 40 * n + 0), generator=gen).float()
+    a_ref = ref_ops.pqmf_analysis(x, an)
+    a = pq.analysis(x.to(dev))
+    assert torch.equal(a.cpu(), a_ref)
+    sub = torch.randint(-8, 9, (3, n, 50), generator=gen).float()
+    s_ref = ref_ops.pqmf_synthesis(sub, sy)
+    s = pq.synthesis(sub.to(dev))
+    assert torch.equal(s.cpu(), s_ref)
