@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: HiFi-GAN v1 (22.05 kHz) generator inference,
+BASELINE.json configs[1]: batch 16 x 80 x 400 synthetic mels -> 16 x 1 x 102400 samples.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one generator forward over one batch.  Multi-GPU (torchrun, one rank per
+GPU): independent utterance batches per rank, no data-path collective ("weak" scaling);
+time = max over ranks (device events), value = total samples / that time.
+
+Output: ONE JSON line on rank 0 (see the driver contract in the task statement) with the
+extra objects `roofline`, `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FS = 22050
+CFG = dict(in_channels=80, out_channels=1, channels=512, kernel_size=7, upsample_scales=[8, 8, 2, 2],
+           upsample_kernel_sizes=[16, 16, 4, 4], resblock_kernel_sizes=[3, 7, 11],
+           resblock_dilations=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], use_additional_convs=True, bias=True,
+           nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1})
+BATCH, FRAMES, HOP = 16, 400, 256
+METRIC = "audio_samples_per_sec"
+UNIT = "samples/s"
+WORKLOAD = "HiFi-GAN v1 generator inference (ljspeech hifigan.v1.yaml), 16x80x400 mels -> 16x1x102400 samples, fp32 weights, weight-norm folded"
+
+
+def synth_weights(seed=1234):
+    """Random-init weights of the HiFi-GAN v1 architecture (no checkpoints offline): synthetic
+    state dict in the reference layout, folded (remove_weight_norm) like decode.py:147."""
+    from oracle import synth  # test infrastructure: only used to draw reproducible weights
+    from parallelwavegan_b200 import models
+
+    m = models.HiFiGANGenerator(**CFG)
+    spec = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    sd = synth.synth_state_dict(spec, seed, 1.15)
+    m.load_state_dict(sd)
+    m.remove_weight_norm()
+    return m.eval(), sd
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_forward(weights, c):
+    """The reference's CPU implementation of the path, restated (oracle port): same ATen CPU ops."""
+    from oracle import ref_ops
+
+    with torch.no_grad():
+        return ref_ops.hifigan_generator(weights, c, dict(CFG, negative_slope=0.1))
+
+
+def time_cpu(weights, batch, frames, reps):
+    c = torch.randn(batch, 80, frames)
+    cpu_reference_forward(weights, torch.randn(1, 80, 16))  # warm-up (thread pool, oneDNN primitives)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        y = cpu_reference_forward(weights, c)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return y.numel() / best, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path (oracle port; /root/reference does not exist
+    on the GPU box) on all host cores, one bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle.ref_ops import fold_weight_norm
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, sd = synth_weights()
+    w = fold_weight_norm(sd)
+    sb, sf = 2, FRAMES  # bounded sample: 2 of the 16 utterances per step
+    c = torch.randn(sb, 80, sf)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_forward(w, c[:, :, :64])
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        y = cpu_reference_forward(w, c)
+        n += y.numel()
+    dt = time.perf_counter() - t0
+    val = n / dt
+    sample = f"{sb}x80x{sf} mels per step (1/8 of the 16x80x400 batch), {args.steps} steps, torch CPU fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rtf": FS / val,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import __graft_entry__
+
+    __graft_entry__.build()
+    from parallelwavegan_b200 import capi, ops
+
+    assert torch.cuda.is_available(), "bench.py (--impl ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, sd = synth_weights()
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    mel_host = torch.randn(BATCH, 80, FRAMES, generator=g).pin_memory()
+    mel_dev = mel_host.to(dev)
+    out_host = torch.empty(BATCH, 1, FRAMES * HOP).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(mel_dev)
+        torch.cuda.synchronize()
+
+        # ---- device-resident timing: K steps, per-step events, L2 flushed between steps
+        sampler = ClockSampler(local_rank)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        sampler.start()
+        capi.reset_launch_count()
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record()
+            y = model(mel_dev)
+            e1.record()
+        barrier()
+        launches = capi.launch_count()
+        clocks = sampler.stop()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+
+        # ---- end to end through the public API: pinned host mels in, host audio out, every step
+        for _ in range(2):
+            out_host.copy_(model(mel_host.to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            flush.zero_()
+            y = model(mel_host.to(dev, non_blocking=True))
+            out_host.copy_(y, non_blocking=True)
+        e1.record()
+        barrier()
+        ms_e2e_total = e0.elapsed_time(e1)
+        # subtract nothing: the flush is part of the region here (it is ~0.1 ms of a multi-ms step)
+
+        # ---- per-kernel-class timing for the roofline (separate instrumented pass)
+        ops.PROFILE = []
+        for _ in range(3):
+            flush.zero_()
+            model(mel_dev)
+        torch.cuda.synchronize()
+        prof = ops.PROFILE
+        ops.PROFILE = None
+
+    t = torch.tensor([ms, ms_e2e_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e_total = float(t[0]), float(t[1])
+    samples_per_step = BATCH * FRAMES * HOP * world
+    value = samples_per_step * args.steps / (ms * 1e-3)
+    e2e_value = samples_per_step * args.steps / (ms_e2e_total * 1e-3)
+
+    # roofline of the dominant kernel class
+    agg = {}
+    for name, fl, by, a, b in prof:
+        d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+        d[0] += fl
+        d[1] += by
+        d[2] += a.elapsed_time(b)
+        d[3] += 1
+    dom = max(agg, key=lambda k: agg[k][2])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    fl, by, tms, cnt = agg[dom]
+    achieved = fl / (tms * 1e-3) / 1e12
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": cnt / 3, "avg_launch_ms": tms / cnt, "share_of_step": tms / sum(v[2] for v in agg.values()),
+                "algorithmic_flops_per_step": fl / 3,
+                "note": "achieved = algorithmic conv FLOPs (2*MAC, fp32 semantics) / summed CUDA-event durations of the class"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle.ref_ops import fold_weight_norm
+
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sb = 4
+            v, dt = time_cpu(fold_weight_norm(sd), sb, FRAMES, 2)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{sb}x80x{FRAMES} mels (1/4 of the batch), best of 2, {dt:.2f} s, oracle port (torch CPU fp32 ATen ops)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "frames": FRAMES, "l2": "flushed between timed steps (256 MiB write); activations (>=210 MB per stage tensor) exceed L2 anyway",
+                       "parallelism": f"utterance-sharded x{world}"},
+            "rtf": FS / (value / world) , "x_realtime_per_gpu": (value / world) / FS,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4 * world,
+                    "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": ms_e2e_total / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "kernel_classes": {k: {"ms_per_step": v[2] / 3, "launches_per_step": v[3] / 3, "tflops": v[0] / (v[2] * 1e-3) / 1e12,
+                                   "alg_GBps": v[1] / (v[2] * 1e-3) / 1e9} for k, v in agg.items()},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,29 @@ import torch
 from . import capi
 from .capi import ACT_LRELU, ACT_NONE, ACT_TANH, PAD_REFLECT, PAD_REPLICATE, PAD_ZERO, PwgbError
 
+# Optional per-launch instrumentation used by bench.py / profiling (None = off).  When set
+# to a list, every wrapper appends (kernel_class, algorithmic_flops, algorithmic_bytes,
+# start_event, end_event) recorded on the launching stream.
+PROFILE = None
+
+
+class _Prof:
+    __slots__ = ("name", "flops", "bytes", "e0")
+
+    def __init__(self, name, flops, nbytes):
+        self.name, self.flops, self.bytes = name, flops, nbytes
+        self.e0 = None
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def done(self):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+
+
 _PAD = {"zero": PAD_ZERO, "zeros": PAD_ZERO, "reflect": PAD_REFLECT, "replicate": PAD_REPLICATE}
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "tanh": ACT_TANH, "lrelu": ACT_LRELU}
 
@@ -98,8 +121,11 @@ def conv1d(
         out_scale=float(out_scale), accumulate=int(bool(accumulate)), shuffle=0, shuffle_pad=0, shuffle_tout=0,
         x_batch_stride=0, y_batch_stride=0, r_batch_stride=0,
     )
+    prof = _Prof("conv1d", 2.0 * B * cout * t_out * P * cin_g * K,
+                 4.0 * (x.numel() + out.numel() * (2 if accumulate else 1) + (residual.numel() if residual is not None else 0)))
     rc = capi.lib().pwgb_conv1d_forward(C.byref(d), _p(x), _p(w), _p(bias), _p(residual), _p(out), _stream())
     capi.check(rc, "pwgb_conv1d_forward")
+    prof.done()
     return out
 
 
@@ -121,6 +147,8 @@ def conv_transpose1d(x, w, bias=None, *, stride, padding=0, output_padding=0, pr
     nbytes = L.pwgb_conv_transpose1d_workspace(C.byref(d))
     ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
     y = torch.empty((B, cout, t_out), device=x.device, dtype=torch.float32)
+    prof = _Prof("conv_transpose1d", 2.0 * B * cout * t_out * cin * ((K + stride - 1) // stride), 4.0 * (x.numel() + y.numel()))
     rc = L.pwgb_conv_transpose1d_forward(C.byref(d), _p(x), _p(w), _p(bias), _p(y), _p(ws), C.c_size_t(nbytes), _stream())
     capi.check(rc, "pwgb_conv_transpose1d_forward")
+    prof.done()
     return y
