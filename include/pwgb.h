@@ -105,6 +105,23 @@ PWGB_API size_t pwgb_conv_transpose1d_workspace(const pwgb_convtr1d_desc* d);
 PWGB_API int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const float* x, const float* w, const float* bias,
                                   float* y, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * tcgen05 (5th-gen tensor core) path for the wide stride-1 convolutions: same descriptor
+ * and semantics as pwgb_conv1d_forward, fp32-accurate through a bf16x3 operand split with
+ * fp32 TMEM accumulation.  Weights are re-laid out once per weight update by
+ * pwgb_conv1d_tc_pack_weight into a caller-owned buffer of
+ * pwgb_conv1d_tc_packed_weight_bytes().  pwgb_conv1d_tc_supported() returns 1 when the
+ * configuration can run here (stride 1, groups 1, cin % 32 == 0, cout % 16 == 0, cout <= 256,
+ * halo fits shared memory); everything else stays on pwgb_conv1d_forward.
+ * ---------------------------------------------------------------------- */
+/* bring-up aid (not part of the product contract): key 1 = tcgen05 descriptor variant */
+PWGB_API void pwgb_debug_set(int key, int value);
+PWGB_API size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kernel);
+PWGB_API int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream);
+PWGB_API int pwgb_conv1d_tc_supported(const pwgb_conv1d_desc* d);
+PWGB_API int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x, const void* packed_w, const float* bias,
+                           const float* residual, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,14 @@ def lib():
     L.pwgb_conv_transpose1d_workspace.argtypes = [C.POINTER(ConvTr1dDesc)]
     L.pwgb_conv_transpose1d_forward.restype = C.c_int
     L.pwgb_conv_transpose1d_forward.argtypes = [C.POINTER(ConvTr1dDesc), vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.pwgb_conv1d_tc_packed_weight_bytes.restype = C.c_size_t
+    L.pwgb_conv1d_tc_packed_weight_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.pwgb_conv1d_tc_pack_weight.restype = C.c_int
+    L.pwgb_conv1d_tc_pack_weight.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.pwgb_conv1d_tc_supported.restype = C.c_int
+    L.pwgb_conv1d_tc_supported.argtypes = [C.POINTER(Conv1dDesc)]
+    L.pwgb_conv1d_tc_forward.restype = C.c_int
+    L.pwgb_conv1d_tc_forward.argtypes = [C.POINTER(Conv1dDesc), vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -79,4 +87,6 @@ def reset_launch_count():
 EXPORTED_SYMBOLS = [
     "pwgb_last_error", "pwgb_version", "pwgb_compiled_arch", "pwgb_launch_count", "pwgb_reset_launch_count",
     "pwgb_conv1d_forward", "pwgb_conv_transpose1d_workspace", "pwgb_conv_transpose1d_forward",
+    "pwgb_conv1d_tc_packed_weight_bytes", "pwgb_conv1d_tc_pack_weight", "pwgb_conv1d_tc_supported",
+    "pwgb_conv1d_tc_forward", "pwgb_debug_set",
 ]

@@ -1,0 +1,454 @@
+// Stride-1 Conv1d on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-accurate via a bf16x3
+// operand split:  x = xh + xl, w = wh + wl (bf16 each),  x*w ~= xh*wh + xl*wh + xh*wl  with
+// fp32 accumulation in TMEM (dropped term xl*wl ~ 2^-16 relative).  One pass of plain
+// TF32/BF16 does not meet the 1e-3 parity bar end to end (SURVEY.md 7 "hard parts").
+//
+// Formulation (im2col is never materialised): TIME is the MMA M dimension.
+//   D[t, co] += sum_{ci in 16-chunk} A_k[t, ci] * B_k[co, ci]      for every tap k
+//   A_k = rows (t0 + t + k*dilation - pad) of the staged activation tile  -> a *row offset*
+//         into ONE shared-memory tile, expressed through the UMMA descriptor start address;
+//   B_k = W[:, :, k] pre-packed (hi/lo bf16) in global memory in the exact smem image.
+// Both operands are K-major, no-swizzle ("interleaved") core-matrix layouts:
+//   [ci/8][row][8 ci] bf16  -> 16 B per (row, 8 channels); 8-row core matrices are contiguous
+//   (SBO = 128 B) so any row offset is a legal 16 B-aligned descriptor start, and the K-adjacent
+//   core matrix sits LBO = rows*16 B away.
+// Warp roles (192 threads, 2 CTAs / SM):
+//   warps 0-3  A producers: coalesced fp32 loads along time, padding policy, LeakyReLU,
+//              hi/lo split, 16 B st.shared straight into the operand layout; afterwards the
+//              same warps are the epilogue (tcgen05.ld -> bias/act/residual/scale -> coalesced st).
+//   warp 4     B producer: one lane issues cp.async.bulk (TMA, 1-D) per (chunk, tap) weight stage.
+//   warp 5     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees stages.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace pwgb {
+
+constexpr int KC = 32;  // input channels per activation chunk / weight stage (2 UMMA K-steps)
+constexpr int TC_THREADS = 192;
+constexpr unsigned SPIN_LIMIT = 1u << 22;
+
+struct TcK {
+  int B, Cin, Cout, T_in, T_out, K, D, padL, pad_mode;
+  float pre_slope;
+  int post_act;
+  float post_slope;
+  float out_scale;
+  int accumulate;
+  int shuffle, shuffle_pad, shuffle_tout;
+  int MT, R, nchunks, tiles_per_seq, nb;
+  long long xbs, ybs, rbs;
+  unsigned idesc;
+  int tmem_cols;
+  int a_bytes, b_bytes;  // per buffer / per stage
+  int variant;           // debug: bit0 swaps LBO/SBO (bring-up aid, see pwgb_debug_set)
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned n = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++n > SPIN_LIMIT) {
+      printf("pwgb conv1d_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
+                                       unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4 (K-adjacent core matrix), [32,46) SBO>>4 (8-row group stride),
+// [46,48) version = 1 (Blackwell), [61,64) layout = 0 (SWIZZLE_NONE).
+__device__ __forceinline__ unsigned long long make_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+  return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo >> 4) & 0x3FFF) << 16) |
+         ((unsigned long long)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  unsigned h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    float2 hf = __bfloat1622float2(hh);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<unsigned*>(&hh);
+    l[i] = *reinterpret_cast<unsigned*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ------------------------------------------------------------------ weight packing
+// w (Cout, Cin, K) fp32 -> [chunk][tap][hi|lo][ci8][co][8] bf16 (the smem image of a stage).
+__global__ void tc_pack_weight_kernel(const float* __restrict__ w, uint4* __restrict__ packed, int Cin, int Cout,
+                                      int K) {
+  const int nchunks = Cin / KC;
+  const long long n = (long long)nchunks * K * (KC / 8) * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    long long t = i / Cout;
+    int g = (int)(t % (KC / 8));
+    t /= (KC / 8);
+    int k = (int)(t % K);
+    int c = (int)(t / K);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = w[((long long)co * Cin + c * KC + g * 8 + j) * K + k];
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const long long base = ((long long)(c * K + k) * 2) * (KC / 8) * Cout;
+    packed[base + (long long)g * Cout + co] = hi;
+    packed[base + (long long)(KC / 8) * Cout + (long long)g * Cout + co] = lo;
+  }
+}
+
+// ------------------------------------------------------------------ main kernel
+__global__ void __launch_bounds__(TC_THREADS, 2)
+    conv1d_tc_kernel(const TcK p, const float* __restrict__ x, const uint4* __restrict__ wpk,
+                     const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ y) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: A[2] | B[nb] | barriers | tmem ptr
+  unsigned char* a_buf = smem;
+  unsigned char* b_buf = smem + 2 * p.a_bytes;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(b_buf + p.nb * p.b_bytes);
+  // bars: [0,1] A_full, [2,3] A_empty, [4..4+nb) B_full, [4+nb..4+2nb) B_empty, [4+2nb] acc_full
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4 + 2 * p.nb + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int b = blockIdx.x / p.tiles_per_seq;
+  const int tile = blockIdx.x - b * p.tiles_per_seq;
+  const int TT = p.MT * 128;
+  const int t0 = tile * TT;
+
+  const unsigned bar0 = smem_u32(bars);
+  auto A_FULL = [&](int i) { return bar0 + 8u * i; };
+  auto A_EMPTY = [&](int i) { return bar0 + 8u * (2 + i); };
+  auto B_FULL = [&](int i) { return bar0 + 8u * (4 + i); };
+  auto B_EMPTY = [&](int i) { return bar0 + 8u * (4 + p.nb + i); };
+  const unsigned ACC_FULL = bar0 + 8u * (4 + 2 * p.nb);
+
+  if (tid == 0) {
+    mbar_init(A_FULL(0), 128);
+    mbar_init(A_FULL(1), 128);
+    mbar_init(A_EMPTY(0), 1);
+    mbar_init(A_EMPTY(1), 1);
+    for (int i = 0; i < p.nb; ++i) {
+      mbar_init(B_FULL(i), 1);
+      mbar_init(B_EMPTY(i), 1);
+    }
+    mbar_init(ACC_FULL, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((unsigned)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== A producers =====================
+    const float* xb = x + (long long)b * p.xbs;
+    for (int c = 0; c < p.nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(A_EMPTY(buf), ((c >> 1) & 1) ^ 1);
+      unsigned char* dst = a_buf + buf * p.a_bytes;
+      const float* xc = xb + (long long)(c * KC) * p.T_in;
+      for (int r = tid; r < p.R; r += 128) {
+        long long ts = (long long)t0 - p.padL + r;
+        bool ok = true;
+        if (ts < 0 || ts >= p.T_in) {
+          if (p.pad_mode == PWGB_PAD_ZERO) {
+            ok = false;
+          } else if (p.pad_mode == PWGB_PAD_REFLECT) {
+            ts = ts < 0 ? -ts : 2LL * (p.T_in - 1) - ts;
+            ok = ts >= 0 && ts < p.T_in;
+          } else {
+            ts = ts < 0 ? 0 : p.T_in - 1;
+          }
+        }
+        float v[KC];
+#pragma unroll
+        for (int j = 0; j < KC; ++j) v[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
+#pragma unroll
+        for (int g = 0; g < KC / 8; ++g) {
+          float u[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = lrelu(v[g * 8 + j], p.pre_slope);
+          uint4 hi, lo;
+          split8(u, hi, lo);
+          *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
+          *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
+        }
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(A_FULL(buf));
+    }
+    // ===================== epilogue =====================
+    mbar_wait(ACC_FULL, 0);
+    tc_fence_after();
+    const int m = warp * 32 + lane;
+    for (int mt = 0; mt < p.MT; ++mt) {
+      const int t = t0 + mt * 128 + m;
+      const bool tv = t < p.T_out;
+      for (int col = 0; col < p.Cout; col += 16) {
+        unsigned r[16];
+        tc_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(mt * p.Cout + col), r);
+        tc_wait_ld();
+        if (tv) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = col + j;
+            float v = __uint_as_float(r[j]);
+            if (bias) v += __ldg(bias + (p.shuffle > 1 ? co / p.shuffle : co));
+            if (p.post_act == PWGB_ACT_TANH)
+              v = tanhf(v);
+            else if (p.post_act == PWGB_ACT_LRELU)
+              v = lrelu(v, p.post_slope);
+            long long yi;
+            if (p.shuffle > 1) {
+              const int cof = co / p.shuffle;
+              const int of = t * p.shuffle + (co - cof * p.shuffle) - p.shuffle_pad;
+              if (of < 0 || of >= p.shuffle_tout) continue;
+              yi = (long long)b * p.ybs + (long long)cof * p.shuffle_tout + of;
+            } else {
+              yi = (long long)b * p.ybs + (long long)co * p.T_out + t;
+            }
+            if (res) v += __ldg(res + (long long)b * p.rbs + (long long)co * p.T_out + t);
+            v *= p.out_scale;
+            if (p.accumulate) v += y[yi];
+            y[yi] = v;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===================== B producer (TMA bulk copies of packed weight stages) =====================
+    if (lane == 0) {
+      const int total = p.nchunks * p.K;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(wpk);
+      for (int i = 0; i < total; ++i) {
+        const int s = i % p.nb;
+        const int n = i / p.nb;
+        mbar_wait(B_EMPTY(s), (n & 1) ^ 1);
+        mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
+        bulk_g2s(smem_u32(b_buf + s * p.b_bytes), src + (size_t)i * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const unsigned a_lbo = (unsigned)p.R * 16u;
+      const unsigned b_lbo = (unsigned)p.Cout * 16u;
+      int i = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(A_FULL(buf), (c >> 1) & 1);
+        const unsigned a_base = smem_u32(a_buf + buf * p.a_bytes);
+        for (int k = 0; k < p.K; ++k, ++i) {
+          const int s = i % p.nb;
+          mbar_wait(B_FULL(s), (i / p.nb) & 1);
+          tc_fence_after();
+          const unsigned b_base = smem_u32(b_buf + s * p.b_bytes);
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const unsigned row = (unsigned)(mt * 128 + k * p.D);
+              // (a_sub, b_sub): (hi,hi), (lo,hi), (hi,lo)
+#pragma unroll
+              for (int pass = 0; pass < 3; ++pass) {
+                const int asub = pass == 1 ? 1 : 0;
+                const int bsub = pass == 2 ? 1 : 0;
+                const unsigned a_addr = a_base + ((unsigned)(asub * (KC / 8) + 2 * ks) * p.R + row) * 16u;
+                const unsigned b_addr = b_base + (unsigned)(bsub * (KC / 8) + 2 * ks) * p.Cout * 16u;
+                const unsigned acc = (c | k | ks | pass) != 0 ? 1u : 0u;
+                if (p.variant & 1)
+                  tc_mma(tmem_base + (unsigned)(mt * p.Cout), make_desc(a_addr, 128u, a_lbo),
+                         make_desc(b_addr, 128u, b_lbo), p.idesc, acc);
+                else
+                  tc_mma(tmem_base + (unsigned)(mt * p.Cout), make_desc(a_addr, a_lbo, 128u),
+                         make_desc(b_addr, b_lbo, 128u), p.idesc, acc);
+              }
+            }
+          }
+          tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
+        }
+        tc_commit(A_EMPTY(buf));
+      }
+      tc_commit(ACC_FULL);
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+static int g_tc_variant = 0;
+
+static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes) {
+  p.variant = g_tc_variant;
+  const int P = d->period < 1 ? 1 : d->period;
+  if (d->stride != 1 || d->groups != 1 || P != 1 || d->pre_gate) return 0;
+  if (d->cin % KC != 0 || d->cout % 16 != 0 || d->cout < 16 || d->cout > 256) return 0;
+  if (d->t_valid > 0 && d->t_valid != d->t_in) return 0;
+  if (d->x_batch_stride || d->y_batch_stride || d->r_batch_stride) return 0;
+  const long long halo = (long long)(d->kernel - 1) * d->dilation;
+  if (halo > 160) return 0;
+  p.B = d->batch;
+  p.Cin = d->cin;
+  p.Cout = d->cout;
+  p.T_in = d->t_in;
+  p.T_out = d->t_out;
+  p.K = d->kernel;
+  p.D = d->dilation;
+  p.padL = d->pad_left;
+  p.pad_mode = d->pad_mode;
+  p.pre_slope = d->pre_slope;
+  p.post_act = d->post_act;
+  p.post_slope = d->post_slope;
+  p.out_scale = d->out_scale;
+  p.accumulate = d->accumulate;
+  p.shuffle = d->shuffle;
+  p.shuffle_pad = d->shuffle_pad;
+  p.shuffle_tout = d->shuffle_tout;
+  p.MT = (2 * d->cout <= 256) ? 2 : 1;
+  if (d->t_out <= 128) p.MT = 1;
+  p.R = p.MT * 128 + (int)halo;
+  p.nchunks = d->cin / KC;
+  p.tiles_per_seq = ceil_div(d->t_out, p.MT * 128);
+  p.xbs = (long long)d->cin * d->t_in;
+  p.ybs = d->shuffle > 1 ? (long long)(d->cout / d->shuffle) * d->shuffle_tout : (long long)d->cout * d->t_out;
+  p.rbs = (long long)d->cout * d->t_out;
+  // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(d->cout >> 3) << 17) | ((128u >> 4) << 24);
+  int cols = p.MT * d->cout;
+  int alloc = 32;
+  while (alloc < cols) alloc <<= 1;
+  p.tmem_cols = alloc;
+  p.a_bytes = 2 * (KC / 8) * p.R * 16;
+  p.b_bytes = 2 * (KC / 8) * d->cout * 16;
+  const size_t budget = 110 * 1024;
+  const size_t fixed = 2 * (size_t)p.a_bytes + 256;
+  if (fixed + 2 * (size_t)p.b_bytes > budget) return 0;
+  int nb = (int)((budget - fixed) / p.b_bytes);
+  if (nb > 6) nb = 6;
+  p.nb = nb;
+  smem_bytes = 2 * (size_t)p.a_bytes + (size_t)nb * p.b_bytes + 8 * (4 + 2 * nb + 1) + 16;
+  return 1;
+}
+
+}  // namespace pwgb
+
+using namespace pwgb;
+
+extern "C" void pwgb_debug_set(int key, int value) {
+  if (key == 1) g_tc_variant = value;
+}
+
+extern "C" size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kernel) {
+  if (cin <= 0 || cout <= 0 || kernel <= 0 || cin % KC != 0) return 0;
+  return (size_t)(cin / KC) * kernel * 2 * (KC / 8) * cout * 16;
+}
+
+extern "C" int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream) {
+  PWGB_CHECK_ARG(w && packed, "conv1d_tc_pack_weight: null argument");
+  PWGB_CHECK_ARG(cin > 0 && cin % KC == 0 && cout > 0 && kernel > 0, "conv1d_tc_pack_weight: cin must be a multiple of %d", KC);
+  const long long n = (long long)(cin / KC) * kernel * (KC / 8) * cout;
+  int blocks = (int)((n + 127) / 128);
+  if (blocks > 8192) blocks = 8192;
+  tc_pack_weight_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(w, (uint4*)packed, cin, cout, kernel);
+  return check_launch("tc_pack_weight_kernel");
+}
+
+extern "C" int pwgb_conv1d_tc_supported(const pwgb_conv1d_desc* d) {
+  if (!d) return 0;
+  TcK p;
+  size_t bytes;
+  return tc_plan(d, p, bytes);
+}
+
+extern "C" int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x, const void* packed_w,
+                                      const float* bias, const float* residual, float* y, void* stream) {
+  PWGB_CHECK_ARG(d && x && packed_w && y, "conv1d_tc: null argument");
+  TcK p;
+  size_t bytes = 0;
+  PWGB_UNSUPPORTED_IF(!tc_plan(d, p, bytes), "conv1d_tc: configuration not supported by the tcgen05 path");
+  PWGB_CHECK_ARG(d->t_out == d->t_in + 0 * d->pad_left || d->t_out > 0, "conv1d_tc: bad t_out");
+  if (p.B == 0 || p.T_out == 0) return PWGB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PWGB_CUDA_ERROR;
+    }
+    attr_set = true;
+  }
+  const long long grid = (long long)p.B * p.tiles_per_seq;
+  PWGB_UNSUPPORTED_IF(grid > 0x7fffffffLL, "conv1d_tc: grid too large");
+  conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, (cudaStream_t)stream>>>(p, x, (const uint4*)packed_w, bias,
+                                                                               residual, y);
+  return check_launch("conv1d_tc_kernel");
+}

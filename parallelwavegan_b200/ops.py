@@ -5,6 +5,7 @@ checks that its tensors live on a CUDA device and raises otherwise -- there is n
 CPU path in this package.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -32,6 +33,31 @@ class _Prof:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+
+
+# Engine selection: "auto" = tcgen05 path whenever pwgb_conv1d_tc_supported() says so, else the
+# FFMA kernel; "simt" forces the FFMA kernel (used by tests to cross-check the two paths).
+ENGINE = os.environ.get("PWGB_ENGINE", "auto")
+
+
+def packed_weight(w):
+    """bf16 hi/lo operand image of a conv weight for the tcgen05 path, cached on the tensor
+    object and invalidated by its version counter (in-place updates) -- a temporary such as a
+    weight-norm product is simply re-packed every forward."""
+    cache = getattr(w, "_pwgb_packed", None)
+    if cache is not None and cache[0] == w._version and cache[1].device == w.device:
+        return cache[1]
+    cout, cin, K = w.shape
+    L = capi.lib()
+    nbytes = L.pwgb_conv1d_tc_packed_weight_bytes(cin, cout, K)
+    buf = torch.empty(nbytes // 4, device=w.device, dtype=torch.int32)
+    rc = L.pwgb_conv1d_tc_pack_weight(_p(w), cin, cout, K, _p(buf), _stream())
+    capi.check(rc, "pwgb_conv1d_tc_pack_weight")
+    try:
+        w._pwgb_packed = (w._version, buf)
+    except Exception:
+        pass
+    return buf
 
 
 _PAD = {"zero": PAD_ZERO, "zeros": PAD_ZERO, "reflect": PAD_REFLECT, "replicate": PAD_REPLICATE}
@@ -123,8 +149,15 @@ def conv1d(
     )
     prof = _Prof("conv1d", 2.0 * B * cout * t_out * P * cin_g * K,
                  4.0 * (x.numel() + out.numel() * (2 if accumulate else 1) + (residual.numel() if residual is not None else 0)))
-    rc = capi.lib().pwgb_conv1d_forward(C.byref(d), _p(x), _p(w), _p(bias), _p(residual), _p(out), _stream())
-    capi.check(rc, "pwgb_conv1d_forward")
+    L = capi.lib()
+    if ENGINE != "simt" and L.pwgb_conv1d_tc_supported(C.byref(d)):
+        pk = packed_weight(w)
+        prof.name = "conv1d_tc"
+        rc = L.pwgb_conv1d_tc_forward(C.byref(d), _p(x), _p(pk), _p(bias), _p(residual), _p(out), _stream())
+        capi.check(rc, "pwgb_conv1d_tc_forward")
+    else:
+        rc = L.pwgb_conv1d_forward(C.byref(d), _p(x), _p(w), _p(bias), _p(residual), _p(out), _stream())
+        capi.check(rc, "pwgb_conv1d_forward")
     prof.done()
     return out
 

@@ -198,3 +198,62 @@ def test_pqmf_band_interleave_bit_exact(dev, n):
     s_ref = ref_ops.pqmf_synthesis(sub, sy)
     s = pq.synthesis(sub.to(dev))
     assert torch.equal(s.cpu(), s_ref)
+
+
+TC_TOL = 1e-4  # bf16x3 split: ~2^-16 per product, fp32 accumulation
+
+
+@pytest.mark.parametrize(
+    "cin,cout,k,dil,T,B,mode",
+    [
+        (32, 32, 3, 1, 300, 2, "zero"),
+        (32, 16, 1, 1, 128, 1, "zero"),
+        (64, 64, 7, 3, 1000, 2, "zero"),
+        (128, 128, 11, 5, 700, 2, "zero"),
+        (256, 256, 3, 1, 513, 1, "zero"),
+        (256, 256, 11, 5, 400, 2, "zero"),
+        (64, 128, 3, 2, 129, 3, "zero"),
+        (96, 192, 3, 9, 260, 2, "reflect"),
+        (192, 192, 3, 27, 300, 1, "reflect"),
+        (64, 64, 3, 4, 5, 2, "replicate"),
+        (32, 48, 5, 1, 2049, 1, "zero"),
+    ],
+)
+def test_conv1d_tcgen05_path(dev, cin, cout, k, dil, T, B, mode):
+    """tcgen05 bf16x3 path vs the oracle (ATen fp32 on CPU) and vs the FFMA kernel."""
+    import ctypes as C
+
+    from parallelwavegan_b200 import capi, ops
+
+    pad = (k - 1) // 2 * dil
+    x = synth.randn((B, cin, T), 1)
+    w = synth.randn((cout, cin, k), 2, 1.0 / (cin * k) ** 0.5)
+    b = synth.randn((cout,), 3, 0.1)
+    xa = F.leaky_relu(x, 0.1)
+    xp = F.pad(xa, (pad, pad)) if mode == "zero" else F.pad(xa, (pad, pad), mode=mode)
+    conv = F.conv1d(xp, w, b, dilation=dil)
+    res = synth.randn(conv.shape, 4)
+    prev = synth.randn(conv.shape, 5)
+    ref = prev + 0.5 * (conv + res)
+    kw = dict(padding=pad, dilation=dil, pad_mode=mode, pre_slope=0.1, residual=res.to(dev), out_scale=0.5, accumulate=True)
+    d = capi.Conv1dDesc(batch=B, cin=cin, cout=cout, t_in=T, t_out=T, kernel=k, stride=1, dilation=dil, groups=1,
+                        pad_left=pad, pad_mode=ops._PAD[mode], period=1, t_valid=T, pre_slope=0.1, out_scale=0.5)
+    assert capi.lib().pwgb_conv1d_tc_supported(C.byref(d)) == 1
+    old = ops.ENGINE
+    try:
+        ops.ENGINE = "auto"
+        ops.PROFILE = []
+        y_tc = ops.conv1d(x.to(dev), w.to(dev), b.to(dev), out=prev.clone().to(dev), **kw)
+        torch.cuda.synchronize()
+        assert ops.PROFILE[0][0] == "conv1d_tc"
+        ops.PROFILE = None
+        ops.ENGINE = "simt"
+        y_ff = ops.conv1d(x.to(dev), w.to(dev), b.to(dev), out=prev.clone().to(dev), **kw)
+    finally:
+        ops.ENGINE = old
+        ops.PROFILE = None
+    e_tc, e_ff = rel_l2(y_tc.cpu(), ref), rel_l2(y_ff.cpu(), ref)
+    print(f"tc rel {e_tc:.2e} simt rel {e_ff:.2e} maxabs/peak {max_abs_over_peak(y_tc.cpu(), ref):.2e}")
+    assert e_ff < FP32_TOL
+    assert e_tc < TC_TOL, (e_tc, e_ff)
+    assert max_abs_over_peak(y_tc.cpu(), ref) < TC_TOL * 5
