@@ -253,7 +253,7 @@ def main():
 
     # roofline of the dominant kernel class
     agg = {}
-    for name, fl, by, a, b in prof:
+    for name, fl, by, a, b, _desc in prof:
         d = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
         d[0] += fl
         d[1] += by

@@ -19,10 +19,10 @@ PROFILE = None
 
 
 class _Prof:
-    __slots__ = ("name", "flops", "bytes", "e0")
+    __slots__ = ("name", "flops", "bytes", "e0", "desc")
 
-    def __init__(self, name, flops, nbytes):
-        self.name, self.flops, self.bytes = name, flops, nbytes
+    def __init__(self, name, flops, nbytes, desc=""):
+        self.name, self.flops, self.bytes, self.desc = name, flops, nbytes, desc
         self.e0 = None
         if PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
@@ -32,7 +32,7 @@ class _Prof:
         if self.e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1, self.desc))
 
 
 # Engine selection: "auto" = tcgen05 path whenever pwgb_conv1d_tc_supported() says so, else the
@@ -148,7 +148,8 @@ def conv1d(
         x_batch_stride=0, y_batch_stride=0, r_batch_stride=0,
     )
     prof = _Prof("conv1d", 2.0 * B * cout * t_out * P * cin_g * K,
-                 4.0 * (x.numel() + out.numel() * (2 if accumulate else 1) + (residual.numel() if residual is not None else 0)))
+                 4.0 * (x.numel() + out.numel() * (2 if accumulate else 1) + (residual.numel() if residual is not None else 0)),
+                 f"B{B} cin{cin} cout{cout} k{K} d{dilation} s{stride} g{groups} T{t_out}" if PROFILE is not None else "")
     L = capi.lib()
     if ENGINE != "simt" and L.pwgb_conv1d_tc_supported(C.byref(d)):
         pk = packed_weight(w)
@@ -180,7 +181,8 @@ def conv_transpose1d(x, w, bias=None, *, stride, padding=0, output_padding=0, pr
     nbytes = L.pwgb_conv_transpose1d_workspace(C.byref(d))
     ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
     y = torch.empty((B, cout, t_out), device=x.device, dtype=torch.float32)
-    prof = _Prof("conv_transpose1d", 2.0 * B * cout * t_out * cin * ((K + stride - 1) // stride), 4.0 * (x.numel() + y.numel()))
+    prof = _Prof("conv_transpose1d", 2.0 * B * cout * t_out * cin * ((K + stride - 1) // stride), 4.0 * (x.numel() + y.numel()),
+                 f"B{B} cin{cin} cout{cout} k{K} s{stride} T{t_out}")
     rc = L.pwgb_conv_transpose1d_forward(C.byref(d), _p(x), _p(w), _p(bias), _p(y), _p(ws), C.c_size_t(nbytes), _stream())
     capi.check(rc, "pwgb_conv_transpose1d_forward")
     prof.done()
