@@ -41,6 +41,7 @@ struct TcK {
   unsigned idesc;
   int tmem_cols;
   int a_bytes, b_bytes;  // per buffer / per stage
+  int co_off;            // first output channel of this launch (N-chunked callers)
   int variant;           // debug: bit0 swaps LBO/SBO (bring-up aid, see pwgb_debug_set)
 };
 
@@ -252,30 +253,44 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       for (int col = 0; col < p.Cout; col += 16) {
         unsigned r[16];
         tc_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(mt * p.Cout + col), r);
-        tc_wait_ld();
-        if (tv) {
+        if (p.shuffle > 1) {
+          tc_wait_ld();
+          if (tv) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = p.co_off + col + j;
+              const int cof = co / p.shuffle;
+              float v = __uint_as_float(r[j]) + (bias ? __ldg(bias + cof) : 0.f);
+              if (p.post_act == PWGB_ACT_TANH)
+                v = tanhf(v);
+              else if (p.post_act == PWGB_ACT_LRELU)
+                v = lrelu(v, p.post_slope);
+              const int of = t * p.shuffle + (co - cof * p.shuffle) - p.shuffle_pad;
+              if (of >= 0 && of < p.shuffle_tout)
+                y[(long long)b * p.ybs + (long long)cof * p.shuffle_tout + of] = v * p.out_scale;
+            }
+          }
+        } else {
+          // issue every independent global load of this 16-column group before touching the results
+          const long long off = (long long)(p.co_off + col) * p.T_out + t;
+          float rv[16], yv[16], bv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = col + j;
-            float v = __uint_as_float(r[j]);
-            if (bias) v += __ldg(bias + (p.shuffle > 1 ? co / p.shuffle : co));
-            if (p.post_act == PWGB_ACT_TANH)
-              v = tanhf(v);
-            else if (p.post_act == PWGB_ACT_LRELU)
-              v = lrelu(v, p.post_slope);
-            long long yi;
-            if (p.shuffle > 1) {
-              const int cof = co / p.shuffle;
-              const int of = t * p.shuffle + (co - cof * p.shuffle) - p.shuffle_pad;
-              if (of < 0 || of >= p.shuffle_tout) continue;
-              yi = (long long)b * p.ybs + (long long)cof * p.shuffle_tout + of;
-            } else {
-              yi = (long long)b * p.ybs + (long long)co * p.T_out + t;
+            rv[j] = (res && tv) ? __ldg(res + (long long)b * p.rbs + off + (long long)j * p.T_out) : 0.f;
+            yv[j] = (p.accumulate && tv) ? y[(long long)b * p.ybs + off + (long long)j * p.T_out] : 0.f;
+            bv[j] = bias ? __ldg(bias + p.co_off + col + j) : 0.f;
+          }
+          tc_wait_ld();
+          if (tv) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float v = __uint_as_float(r[j]) + bv[j];
+              if (p.post_act == PWGB_ACT_TANH)
+                v = tanhf(v);
+              else if (p.post_act == PWGB_ACT_LRELU)
+                v = lrelu(v, p.post_slope);
+              y[(long long)b * p.ybs + off + (long long)j * p.T_out] = (v + rv[j]) * p.out_scale + yv[j];
             }
-            if (res) v += __ldg(res + (long long)b * p.rbs + (long long)co * p.T_out + t);
-            v *= p.out_scale;
-            if (p.accumulate) v += y[yi];
-            y[yi] = v;
           }
         }
       }
@@ -349,6 +364,7 @@ static int g_tc_variant = 0;
 
 static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes) {
   p.variant = g_tc_variant;
+  p.co_off = 0;
   const int P = d->period < 1 ? 1 : d->period;
   if (d->stride != 1 || d->groups != 1 || P != 1 || d->pre_gate) return 0;
   if (d->cin % KC != 0 || d->cout % 16 != 0 || d->cout < 16 || d->cout > 256) return 0;
@@ -399,6 +415,52 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes) {
   return 1;
 }
 
+static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w, const float* bias,
+                     const float* residual, float* y, cudaStream_t st) {
+  if (p.B == 0 || p.T_out == 0) return PWGB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PWGB_CUDA_ERROR;
+    }
+    attr_set = true;
+  }
+  const long long grid = (long long)p.B * p.tiles_per_seq;
+  if (grid > 0x7fffffffLL) {
+    set_error("conv1d_tc: grid too large");
+    return PWGB_UNSUPPORTED;
+  }
+  conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, (const uint4*)packed_w, bias, residual, y);
+  return check_launch("conv1d_tc_kernel");
+}
+
+// Internal entry for N-chunked callers (conv_transpose): runs output channels
+// [co_off, co_off + d->cout) of a conv whose full output has cout_total channels.
+int conv1d_tc_chunk(const pwgb_conv1d_desc* d, int co_off, int cout_total, const float* x, const void* packed_w,
+                    const float* bias, float* y, cudaStream_t st) {
+  TcK p;
+  size_t bytes = 0;
+  if (!tc_plan(d, p, bytes)) return PWGB_UNSUPPORTED;
+  p.co_off = co_off;
+  p.ybs = d->shuffle > 1 ? (long long)(cout_total / d->shuffle) * d->shuffle_tout : (long long)cout_total * d->t_out;
+  return tc_launch(p, bytes, x, packed_w, bias, nullptr, y, st);
+}
+
+int conv1d_tc_plan_ok(const pwgb_conv1d_desc* d) {
+  TcK p;
+  size_t bytes;
+  return tc_plan(d, p, bytes);
+}
+
+void tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, cudaStream_t st) {
+  const long long n = (long long)(cin / KC) * kernel * (KC / 8) * cout;
+  int blocks = (int)((n + 127) / 128);
+  if (blocks > 8192) blocks = 8192;
+  tc_pack_weight_kernel<<<blocks, 128, 0, st>>>(w, (uint4*)packed, cin, cout, kernel);
+}
+
 }  // namespace pwgb
 
 using namespace pwgb;
@@ -435,20 +497,5 @@ extern "C" int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x,
   TcK p;
   size_t bytes = 0;
   PWGB_UNSUPPORTED_IF(!tc_plan(d, p, bytes), "conv1d_tc: configuration not supported by the tcgen05 path");
-  PWGB_CHECK_ARG(d->t_out == d->t_in + 0 * d->pad_left || d->t_out > 0, "conv1d_tc: bad t_out");
-  if (p.B == 0 || p.T_out == 0) return PWGB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    if (e != cudaSuccess) {
-      set_error("conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return PWGB_CUDA_ERROR;
-    }
-    attr_set = true;
-  }
-  const long long grid = (long long)p.B * p.tiles_per_seq;
-  PWGB_UNSUPPORTED_IF(grid > 0x7fffffffLL, "conv1d_tc: grid too large");
-  conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, (cudaStream_t)stream>>>(p, x, (const uint4*)packed_w, bias,
-                                                                               residual, y);
-  return check_launch("conv1d_tc_kernel");
+  return tc_launch(p, bytes, x, packed_w, bias, residual, y, (cudaStream_t)stream);
 }

@@ -8,6 +8,10 @@ namespace pwgb {
 
 int conv1d_forward_simt(const pwgb_conv1d_desc* d, const float* x, const float* w, const float* bias,
                         const float* residual, float* y, cudaStream_t st);
+int conv1d_tc_chunk(const pwgb_conv1d_desc* d, int co_off, int cout_total, const float* x, const void* packed_w,
+                    const float* bias, float* y, cudaStream_t st);
+int conv1d_tc_plan_ok(const pwgb_conv1d_desc* d);
+void tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, cudaStream_t st);
 
 // w: (cin, cout, K) -> wv: (cout*s, cin, M), wv[co*s+ph][ci][m'] = w[ci][co][ph + (M-1-m')*s]
 __global__ void convtr_weight_kernel(const float* __restrict__ w, float* __restrict__ wv, int cin, int cout, int K,
@@ -31,7 +35,8 @@ using namespace pwgb;
 extern "C" size_t pwgb_conv_transpose1d_workspace(const pwgb_convtr1d_desc* d) {
   if (!d || d->stride <= 0) return 0;
   const int M = ceil_div(d->kernel, d->stride);
-  return (size_t)d->cout * d->stride * d->cin * M * sizeof(float);
+  // [virtual-conv fp32 weights][bf16 hi/lo operand image of the same weights for the tcgen05 path]
+  return 2 * (size_t)d->cout * d->stride * d->cin * M * sizeof(float);
 }
 
 extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const float* x, const float* w,
@@ -74,5 +79,29 @@ extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const 
   c.shuffle = s;
   c.shuffle_pad = d->padding;
   c.shuffle_tout = d->t_out;
+  // tcgen05 path: N (= cout*s virtual channels) in chunks of <= 256 accumulator columns
+  if (d->cin % 32 == 0 && c.cout % 16 == 0) {
+    int chunk = c.cout;
+    if (chunk > 256) {
+      chunk = 256;
+      while (c.cout % chunk) chunk -= 16;
+    }
+    pwgb_conv1d_desc cc = c;
+    cc.cout = chunk;
+    if (conv1d_tc_plan_ok(&cc)) {
+      unsigned char* pk = (unsigned char*)ws + need / 2;
+      // the operand image is laid out per (32-channel chunk, tap) over the rows of ONE launch, so
+      // each column chunk gets its own image
+      for (int co = 0; co < c.cout; co += chunk) {
+        unsigned char* pkc = pk + (size_t)co * d->cin * M * sizeof(float);
+        tc_pack_weight(wv + (size_t)co * d->cin * M, d->cin, chunk, M, pkc, st);
+        rc = check_launch("tc_pack_weight_kernel");
+        if (rc) return rc;
+        rc = conv1d_tc_chunk(&cc, co, c.cout, x, pkc, bias, y, st);
+        if (rc) return rc;
+      }
+      return PWGB_OK;
+    }
+  }
   return conv1d_forward_simt(&c, x, wv, bias, nullptr, y, st);
 }
