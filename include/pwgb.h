@@ -122,6 +122,42 @@ PWGB_API int pwgb_conv1d_tc_supported(const pwgb_conv1d_desc* d);
 PWGB_API int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x, const void* packed_w, const float* bias,
                            const float* residual, float* y, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Fused WaveNet residual layer of ParallelWaveGANGenerator (layers/residual_block.py:102-140,
+ * called 30x from models/parallel_wavegan.py:161-166):
+ *     g  = conv_{k,dilation}(x) + W_aux c (+ b_conv)
+ *     z  = tanh(g[:G/2]) * sigmoid(g[G/2:])
+ *     skips += W_skip z + b_skip ;   x_out = (W_out z + b_out + x) * sqrt(0.5)
+ * on the tcgen05 path (bf16x3, fp32 accumulate).  `c` must be stored with `aux_channels`
+ * channels, a multiple of 32 (zero-padded beyond the model's real aux_channels; the pack
+ * routine zero-fills the matching weight columns).  g_ws: workspace of batch*G*t floats.
+ * b_skip_out = concat(b_skip, b_out) or NULL.  pwgb_wavenet_supported() == 0 means the caller
+ * must compose the layer from pwgb_conv1d_forward (pre_gate / accumulate options) instead.
+ * ---------------------------------------------------------------------- */
+typedef struct pwgb_wavenet_desc {
+  int32_t batch, t;
+  int32_t residual_channels, gate_channels, skip_channels;
+  int32_t aux_channels; /* as stored, padded to a multiple of 32 (0 = no conditioning) */
+  int32_t kernel, dilation;
+} pwgb_wavenet_desc;
+PWGB_API int pwgb_wavenet_supported(const pwgb_wavenet_desc* d);
+PWGB_API size_t pwgb_wavenet_packed_bytes(const pwgb_wavenet_desc* d);
+PWGB_API int pwgb_wavenet_pack(const pwgb_wavenet_desc* d, const float* w_conv, const float* w_aux, int aux_channels_real,
+                      const float* w_skip, const float* w_out, void* packed, void* stream);
+PWGB_API int pwgb_wavenet_layer_forward(const pwgb_wavenet_desc* d, const float* x, const float* c, const void* packed,
+                               const float* b_conv, const float* b_skip_out, float* x_out, float* skips, float* g_ws,
+                               void* stream);
+
+/* ------------------------------------------------------------------------
+ * One stage of the PWG conditioning upsampler (layers/upsample.py:112-128): nearest repeat
+ * x`scale` along time followed by the (2*scale+1)-tap FIR shared by all rows, zero padded:
+ *   y[r, o] = sum_k f[k] * x[r, (o + k - scale) / scale]   for 0 <= o + k - scale < t_in*scale.
+ * x: rows x t_in (row stride t_in); y: row r of batch item r / rows_per_batch starts at
+ * (r / rows_per_batch) * y_batch_stride + (r % rows_per_batch) * t_in * scale.
+ * ---------------------------------------------------------------------- */
+PWGB_API int pwgb_upsample_fir_forward(int rows, int rows_per_batch, int t_in, int scale, const float* x, const float* fir,
+                              float* y, long long y_batch_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,13 @@ class ConvTr1dDesc(C.Structure):
     ]
 
 
+class WaveNetDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("t", C.c_int32), ("residual_channels", C.c_int32), ("gate_channels", C.c_int32),
+        ("skip_channels", C.c_int32), ("aux_channels", C.c_int32), ("kernel", C.c_int32), ("dilation", C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -66,6 +73,18 @@ def lib():
     L.pwgb_conv1d_tc_supported.argtypes = [C.POINTER(Conv1dDesc)]
     L.pwgb_conv1d_tc_forward.restype = C.c_int
     L.pwgb_conv1d_tc_forward.argtypes = [C.POINTER(Conv1dDesc), vp, vp, vp, vp, vp, vp]
+    L.pwgb_debug_set.restype = None
+    L.pwgb_debug_set.argtypes = [C.c_int, C.c_int]
+    L.pwgb_wavenet_supported.restype = C.c_int
+    L.pwgb_wavenet_supported.argtypes = [C.POINTER(WaveNetDesc)]
+    L.pwgb_wavenet_packed_bytes.restype = C.c_size_t
+    L.pwgb_wavenet_packed_bytes.argtypes = [C.POINTER(WaveNetDesc)]
+    L.pwgb_wavenet_pack.restype = C.c_int
+    L.pwgb_wavenet_pack.argtypes = [C.POINTER(WaveNetDesc), vp, vp, C.c_int, vp, vp, vp, vp]
+    L.pwgb_wavenet_layer_forward.restype = C.c_int
+    L.pwgb_wavenet_layer_forward.argtypes = [C.POINTER(WaveNetDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.pwgb_upsample_fir_forward.restype = C.c_int
+    L.pwgb_upsample_fir_forward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_longlong, vp]
     _lib = L
     return L
 
@@ -88,5 +107,6 @@ EXPORTED_SYMBOLS = [
     "pwgb_last_error", "pwgb_version", "pwgb_compiled_arch", "pwgb_launch_count", "pwgb_reset_launch_count",
     "pwgb_conv1d_forward", "pwgb_conv_transpose1d_workspace", "pwgb_conv_transpose1d_forward",
     "pwgb_conv1d_tc_packed_weight_bytes", "pwgb_conv1d_tc_pack_weight", "pwgb_conv1d_tc_supported",
-    "pwgb_conv1d_tc_forward", "pwgb_debug_set",
+    "pwgb_conv1d_tc_forward", "pwgb_debug_set", "pwgb_wavenet_supported", "pwgb_wavenet_packed_bytes",
+    "pwgb_wavenet_pack", "pwgb_wavenet_layer_forward", "pwgb_upsample_fir_forward",
 ]

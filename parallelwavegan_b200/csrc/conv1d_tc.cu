@@ -41,6 +41,11 @@ struct TcK {
   unsigned idesc;
   int tmem_cols;
   int a_bytes, b_bytes;  // per buffer / per stage
+  int win_mode;          // 1: one TT-row window per tap (halo too large for a contiguous tile)
+  int nchunks2, C2;      // auxiliary 1x1 source (WaveNet conditioning): extra K=1 chunks
+  int pre_gate;          // producer computes tanh(x[c]) * sigmoid(x[c + Cin])
+  int wavenet;           // epilogue: cols < split -> y2 += v ; cols >= split -> y = (v + res) * scale
+  int split;
   int co_off;            // first output channel of this launch (N-chunked callers)
   int variant;           // debug: bit0 swaps LBO/SBO (bring-up aid, see pwgb_debug_set)
 };
@@ -132,33 +137,48 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 }
 
 // ------------------------------------------------------------------ weight packing
-// w (Cout, Cin, K) fp32 -> [chunk][tap][hi|lo][ci8][co][8] bf16 (the smem image of a stage).
-__global__ void tc_pack_weight_kernel(const float* __restrict__ w, uint4* __restrict__ packed, int Cin, int Cout,
-                                      int K) {
-  const int nchunks = Cin / KC;
-  const long long n = (long long)nchunks * K * (KC / 8) * Cout;
+// w (rows, cin_real, K) fp32 -> rows [co_begin, co_begin + rows) of the operand image
+// [chunk][tap][hi|lo][ci8][co (cout_total)][8] bf16 (the smem image of a stage); input channels
+// >= cin_real (zero padding up to cin_pad, a multiple of KC) pack as zeros.
+__global__ void tc_pack_weight_kernel(const float* __restrict__ w, uint4* __restrict__ packed, int cin_real,
+                                      int cin_pad, int rows, int K, int co_begin, int cout_total) {
+  const int nchunks = cin_pad / KC;
+  const long long n = (long long)nchunks * K * (KC / 8) * rows;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int co = (int)(i % Cout);
-    long long t = i / Cout;
+    int co = (int)(i % rows);
+    long long t = i / rows;
     int g = (int)(t % (KC / 8));
     t /= (KC / 8);
     int k = (int)(t % K);
     int c = (int)(t / K);
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = w[((long long)co * Cin + c * KC + g * 8 + j) * K + k];
+    for (int j = 0; j < 8; ++j) {
+      const int ci = c * KC + g * 8 + j;
+      v[j] = ci < cin_real ? w[((long long)co * cin_real + ci) * K + k] : 0.f;
+    }
     uint4 hi, lo;
     split8(v, hi, lo);
-    const long long base = ((long long)(c * K + k) * 2) * (KC / 8) * Cout;
-    packed[base + (long long)g * Cout + co] = hi;
-    packed[base + (long long)(KC / 8) * Cout + (long long)g * Cout + co] = lo;
+    const long long base = ((long long)(c * K + k) * 2) * (KC / 8) * cout_total;
+    packed[base + (long long)g * cout_total + co_begin + co] = hi;
+    packed[base + (long long)(KC / 8) * cout_total + (long long)g * cout_total + co_begin + co] = lo;
   }
+}
+
+static void tc_pack_rows(const float* w, void* packed, int cin_real, int cin_pad, int rows, int K, int co_begin,
+                         int cout_total, cudaStream_t st) {
+  const long long n = (long long)(cin_pad / KC) * K * (KC / 8) * rows;
+  int blocks = (int)((n + 127) / 128);
+  if (blocks > 8192) blocks = 8192;
+  if (blocks < 1) blocks = 1;
+  tc_pack_weight_kernel<<<blocks, 128, 0, st>>>(w, (uint4*)packed, cin_real, cin_pad, rows, K, co_begin, cout_total);
 }
 
 // ------------------------------------------------------------------ main kernel
 __global__ void __launch_bounds__(TC_THREADS, 2)
-    conv1d_tc_kernel(const TcK p, const float* __restrict__ x, const uint4* __restrict__ wpk,
-                     const float* __restrict__ bias, const float* __restrict__ res, float* __restrict__ y) {
+    conv1d_tc_kernel(const TcK p, const float* __restrict__ x, const float* __restrict__ x2,
+                     const uint4* __restrict__ wpk, const float* __restrict__ bias, const float* __restrict__ res,
+                     float* __restrict__ y, float* __restrict__ y2) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: A[2] | B[nb] | barriers | tmem ptr
   unsigned char* a_buf = smem;
@@ -208,36 +228,73 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   if (warp < 4) {
     // ===================== A producers =====================
     const float* xb = x + (long long)b * p.xbs;
-    for (int c = 0; c < p.nchunks; ++c) {
+    const int nc_total = p.nchunks + p.nchunks2;
+    for (int c = 0; c < nc_total; ++c) {
       const int buf = c & 1;
       mbar_wait(A_EMPTY(buf), ((c >> 1) & 1) ^ 1);
       unsigned char* dst = a_buf + buf * p.a_bytes;
-      const float* xc = xb + (long long)(c * KC) * p.T_in;
-      for (int r = tid; r < p.R; r += 128) {
-        long long ts = (long long)t0 - p.padL + r;
-        bool ok = true;
-        if (ts < 0 || ts >= p.T_in) {
-          if (p.pad_mode == PWGB_PAD_ZERO) {
-            ok = false;
-          } else if (p.pad_mode == PWGB_PAD_REFLECT) {
-            ts = ts < 0 ? -ts : 2LL * (p.T_in - 1) - ts;
-            ok = ts >= 0 && ts < p.T_in;
+      if (c < p.nchunks) {
+        const float* xc = xb + (long long)(c * KC) * p.T_in;
+        for (int r = tid; r < p.R; r += 128) {
+          long long ts;
+          if (p.win_mode) {
+            const int k = r / TT;
+            ts = (long long)t0 - p.padL + (long long)k * p.D + (r - k * TT);
           } else {
-            ts = ts < 0 ? 0 : p.T_in - 1;
+            ts = (long long)t0 - p.padL + r;
+          }
+          bool ok = true;
+          if (ts < 0 || ts >= p.T_in) {
+            if (p.pad_mode == PWGB_PAD_ZERO) {
+              ok = false;
+            } else if (p.pad_mode == PWGB_PAD_REFLECT) {
+              ts = ts < 0 ? -ts : 2LL * (p.T_in - 1) - ts;
+              ok = ts >= 0 && ts < p.T_in;
+            } else {
+              ts = ts < 0 ? 0 : p.T_in - 1;
+            }
+          }
+          float v[KC];
+#pragma unroll
+          for (int j = 0; j < KC; ++j) v[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
+          if (p.pre_gate) {
+            const float* xg = xc + (long long)p.Cin * p.T_in;
+#pragma unroll
+            for (int j = 0; j < KC; ++j) {
+              const float sg = ok ? __ldg(xg + (long long)j * p.T_in + ts) : 0.f;
+              v[j] = tanhf(v[j]) * sigmoidf_(sg);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < KC; ++j) v[j] = lrelu(v[j], p.pre_slope);
+          }
+#pragma unroll
+          for (int g = 0; g < KC / 8; ++g) {
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = v[g * 8 + j];
+            uint4 hi, lo;
+            split8(u, hi, lo);
+            *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
+            *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
           }
         }
-        float v[KC];
+      } else {
+        // auxiliary 1x1 source: TT rows aligned with the output tile, no padding shift, no activation
+        const float* xc = x2 + ((long long)b * p.C2 + (long long)(c - p.nchunks) * KC) * p.T_out;
+        for (int r = tid; r < TT; r += 128) {
+          const long long ts = (long long)t0 + r;
+          const bool ok = ts < p.T_out;
 #pragma unroll
-        for (int j = 0; j < KC; ++j) v[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
+          for (int g = 0; g < KC / 8; ++g) {
+            float u[8];
 #pragma unroll
-        for (int g = 0; g < KC / 8; ++g) {
-          float u[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = lrelu(v[g * 8 + j], p.pre_slope);
-          uint4 hi, lo;
-          split8(u, hi, lo);
-          *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
-          *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
+            for (int j = 0; j < 8; ++j) u[j] = ok ? __ldg(xc + (long long)(g * 8 + j) * p.T_out + ts) : 0.f;
+            uint4 hi, lo;
+            split8(u, hi, lo);
+            *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
+            *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
+          }
         }
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -270,6 +327,30 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
                 y[(long long)b * p.ybs + (long long)cof * p.shuffle_tout + of] = v * p.out_scale;
             }
           }
+        } else if (p.wavenet) {
+          // WaveNet split epilogue (residual_block.py:131-138): columns [0, split) are the skip 1x1
+          // (accumulated into y2), columns [split, Cout) the residual 1x1: y = (v + x) * sqrt(0.5)
+          const bool is_skip = col < p.split;
+          const int ch = is_skip ? col : col - p.split;
+          const int nch = is_skip ? p.split : p.Cout - p.split;
+          const long long off = ((long long)b * nch + ch) * p.T_out + t;
+          float rv[16], bv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            rv[j] = tv ? (is_skip ? y2[off + (long long)j * p.T_out] : __ldg(res + off + (long long)j * p.T_out)) : 0.f;
+            bv[j] = bias ? __ldg(bias + col + j) : 0.f;
+          }
+          tc_wait_ld();
+          if (tv) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float v = __uint_as_float(r[j]) + bv[j];
+              if (is_skip)
+                y2[off + (long long)j * p.T_out] = rv[j] + v;
+              else
+                y[off + (long long)j * p.T_out] = (v + rv[j]) * p.out_scale;
+            }
+          }
         } else {
           // issue every independent global load of this 16-column group before touching the results
           const long long off = (long long)(p.co_off + col) * p.T_out + t;
@@ -299,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
   } else if (warp == 4) {
     // ===================== B producer (TMA bulk copies of packed weight stages) =====================
     if (lane == 0) {
-      const int total = p.nchunks * p.K;
+      const int total = p.nchunks * p.K + p.nchunks2;
       const unsigned char* src = reinterpret_cast<const unsigned char*>(wpk);
       for (int i = 0; i < total; ++i) {
         const int s = i % p.nb;
@@ -315,19 +396,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
       const unsigned a_lbo = (unsigned)p.R * 16u;
       const unsigned b_lbo = (unsigned)p.Cout * 16u;
       int i = 0;
-      for (int c = 0; c < p.nchunks; ++c) {
+      const int TTm = p.MT * 128;
+      const int nc_total = p.nchunks + p.nchunks2;
+      for (int c = 0; c < nc_total; ++c) {
         const int buf = c & 1;
         mbar_wait(A_FULL(buf), (c >> 1) & 1);
         const unsigned a_base = smem_u32(a_buf + buf * p.a_bytes);
-        for (int k = 0; k < p.K; ++k, ++i) {
+        const int ntaps = c < p.nchunks ? p.K : 1;
+        for (int k = 0; k < ntaps; ++k, ++i) {
           const int s = i % p.nb;
           mbar_wait(B_FULL(s), (i / p.nb) & 1);
           tc_fence_after();
           const unsigned b_base = smem_u32(b_buf + s * p.b_bytes);
+          const unsigned tap_row = c < p.nchunks ? (unsigned)(p.win_mode ? k * TTm : k * p.D) : 0u;
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks) {
             for (int mt = 0; mt < p.MT; ++mt) {
-              const unsigned row = (unsigned)(mt * 128 + k * p.D);
+              const unsigned row = (unsigned)(mt * 128) + tap_row;
               // (a_sub, b_sub): (hi,hi), (lo,hi), (hi,lo)
 #pragma unroll
               for (int pass = 0; pass < 3; ++pass) {
@@ -362,16 +447,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 
 static int g_tc_variant = 0;
 
-static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes) {
+// aux_c2: channels of the auxiliary 1x1 source (0 = none, else multiple of KC); split > 0 selects the
+// WaveNet epilogue.  pre_gate: d->cin is the number of gated channels, x holds 2*cin channels.
+static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int aux_c2 = 0, int split = 0) {
   p.variant = g_tc_variant;
   p.co_off = 0;
   const int P = d->period < 1 ? 1 : d->period;
-  if (d->stride != 1 || d->groups != 1 || P != 1 || d->pre_gate) return 0;
+  if (d->stride != 1 || d->groups != 1 || P != 1) return 0;
   if (d->cin % KC != 0 || d->cout % 16 != 0 || d->cout < 16 || d->cout > 256) return 0;
+  if (aux_c2 % KC != 0 || split % 16 != 0 || split > d->cout) return 0;
   if (d->t_valid > 0 && d->t_valid != d->t_in) return 0;
   if (d->x_batch_stride || d->y_batch_stride || d->r_batch_stride) return 0;
   const long long halo = (long long)(d->kernel - 1) * d->dilation;
-  if (halo > 160) return 0;
   p.B = d->batch;
   p.Cin = d->cin;
   p.Cout = d->cout;
@@ -382,6 +469,7 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes) {
   p.padL = d->pad_left;
   p.pad_mode = d->pad_mode;
   p.pre_slope = d->pre_slope;
+  p.pre_gate = d->pre_gate;
   p.post_act = d->post_act;
   p.post_slope = d->post_slope;
   p.out_scale = d->out_scale;
@@ -389,38 +477,63 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes) {
   p.shuffle = d->shuffle;
   p.shuffle_pad = d->shuffle_pad;
   p.shuffle_tout = d->shuffle_tout;
-  p.MT = (2 * d->cout <= 256) ? 2 : 1;
-  if (d->t_out <= 128) p.MT = 1;
-  p.R = p.MT * 128 + (int)halo;
   p.nchunks = d->cin / KC;
-  p.tiles_per_seq = ceil_div(d->t_out, p.MT * 128);
-  p.xbs = (long long)d->cin * d->t_in;
+  p.nchunks2 = aux_c2 / KC;
+  p.C2 = aux_c2;
+  p.wavenet = split > 0;
+  p.split = split;
+  if (aux_c2 && d->t_in != d->t_out) return 0;
+  p.xbs = (long long)d->cin * (d->pre_gate ? 2 : 1) * d->t_in;
   p.ybs = d->shuffle > 1 ? (long long)(d->cout / d->shuffle) * d->shuffle_tout : (long long)d->cout * d->t_out;
   p.rbs = (long long)d->cout * d->t_out;
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(d->cout >> 3) << 17) | ((128u >> 4) << 24);
-  int cols = p.MT * d->cout;
-  int alloc = 32;
-  while (alloc < cols) alloc <<= 1;
-  p.tmem_cols = alloc;
-  p.a_bytes = 2 * (KC / 8) * p.R * 16;
   p.b_bytes = 2 * (KC / 8) * d->cout * 16;
-  const size_t budget = 110 * 1024;
-  const size_t fixed = 2 * (size_t)p.a_bytes + 256;
-  if (fixed + 2 * (size_t)p.b_bytes > budget) return 0;
-  int nb = (int)((budget - fixed) / p.b_bytes);
-  if (nb > 6) nb = 6;
-  p.nb = nb;
-  smem_bytes = 2 * (size_t)p.a_bytes + (size_t)nb * p.b_bytes + 8 * (4 + 2 * nb + 1) + 16;
-  return 1;
+  // tile shape: contiguous halo tile at 2 CTAs/SM when it fits, else one window per tap at 1 CTA/SM
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    size_t budget;
+    if (attempt == 0) {
+      p.MT = (2 * d->cout <= 256 && d->t_out > 128) ? 2 : 1;
+      p.win_mode = 0;
+      p.R = p.MT * 128 + (int)halo;
+      budget = 110 * 1024;
+      if (halo > 1024) continue;
+    } else if (attempt == 1) {
+      p.MT = 1;
+      p.win_mode = 0;
+      p.R = 128 + (int)halo;
+      budget = 110 * 1024;
+      if (halo > 1024) continue;
+    } else {
+      p.MT = 1;
+      p.win_mode = 1;
+      p.R = d->kernel * 128;
+      budget = 200 * 1024;
+    }
+    p.a_bytes = 2 * (KC / 8) * p.R * 16;
+    const size_t fixed = 2 * (size_t)p.a_bytes + 256;
+    if (fixed + 2 * (size_t)p.b_bytes > budget) continue;
+    int nb = (int)((budget - fixed) / p.b_bytes);
+    if (nb > 6) nb = 6;
+    p.nb = nb;
+    p.tiles_per_seq = ceil_div(d->t_out, p.MT * 128);
+    int cols = p.MT * d->cout;
+    int alloc = 32;
+    while (alloc < cols) alloc <<= 1;
+    p.tmem_cols = alloc;
+    smem_bytes = 2 * (size_t)p.a_bytes + (size_t)nb * p.b_bytes + 8 * (4 + 2 * nb + 1) + 16;
+    return 1;
+  }
+  return 0;
 }
 
 static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w, const float* bias,
-                     const float* residual, float* y, cudaStream_t st) {
+                     const float* residual, float* y, cudaStream_t st, const float* x2 = nullptr,
+                     float* y2 = nullptr) {
   if (p.B == 0 || p.T_out == 0) return PWGB_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
     if (e != cudaSuccess) {
       set_error("conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PWGB_CUDA_ERROR;
@@ -432,7 +545,7 @@ static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w,
     set_error("conv1d_tc: grid too large");
     return PWGB_UNSUPPORTED;
   }
-  conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, (const uint4*)packed_w, bias, residual, y);
+  conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, x2, (const uint4*)packed_w, bias, residual, y, y2);
   return check_launch("conv1d_tc_kernel");
 }
 
@@ -455,10 +568,7 @@ int conv1d_tc_plan_ok(const pwgb_conv1d_desc* d) {
 }
 
 void tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, cudaStream_t st) {
-  const long long n = (long long)(cin / KC) * kernel * (KC / 8) * cout;
-  int blocks = (int)((n + 127) / 128);
-  if (blocks > 8192) blocks = 8192;
-  tc_pack_weight_kernel<<<blocks, 128, 0, st>>>(w, (uint4*)packed, cin, cout, kernel);
+  tc_pack_rows(w, packed, cin, cin, cout, kernel, 0, cout, st);
 }
 
 }  // namespace pwgb
@@ -477,10 +587,7 @@ extern "C" size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kern
 extern "C" int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream) {
   PWGB_CHECK_ARG(w && packed, "conv1d_tc_pack_weight: null argument");
   PWGB_CHECK_ARG(cin > 0 && cin % KC == 0 && cout > 0 && kernel > 0, "conv1d_tc_pack_weight: cin must be a multiple of %d", KC);
-  const long long n = (long long)(cin / KC) * kernel * (KC / 8) * cout;
-  int blocks = (int)((n + 127) / 128);
-  if (blocks > 8192) blocks = 8192;
-  tc_pack_weight_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(w, (uint4*)packed, cin, cout, kernel);
+  tc_pack_rows(w, packed, cin, cin, cout, kernel, 0, cout, (cudaStream_t)stream);
   return check_launch("tc_pack_weight_kernel");
 }
 
@@ -498,4 +605,118 @@ extern "C" int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x,
   size_t bytes = 0;
   PWGB_UNSUPPORTED_IF(!tc_plan(d, p, bytes), "conv1d_tc: configuration not supported by the tcgen05 path");
   return tc_launch(p, bytes, x, packed_w, bias, residual, y, (cudaStream_t)stream);
+}
+
+// ======================================================================================
+// WaveNet residual layer (layers/residual_block.py:102-140) as two tcgen05 launches:
+//   1) g = conv_k,dil(x) + W_aux c + b        (aux 1x1 folded into the same TMEM accumulation)
+//   2) z = tanh(g[:G/2]) * sigmoid(g[G/2:]) in the producer;  [skip | out] 1x1 stacked as one
+//      N = S + R contraction;  epilogue: skips += s,  x' = (o + x) * sqrt(0.5)
+// ======================================================================================
+static size_t wn_image1_bytes(const pwgb_wavenet_desc* d) {
+  return (size_t)(d->residual_channels / KC) * d->kernel * 2 * (KC / 8) * d->gate_channels * 16;
+}
+static size_t wn_aux_bytes(const pwgb_wavenet_desc* d) {
+  return (size_t)(d->aux_channels / KC) * 2 * (KC / 8) * d->gate_channels * 16;
+}
+static size_t wn_image2_bytes(const pwgb_wavenet_desc* d) {
+  return (size_t)((d->gate_channels / 2) / KC) * 2 * (KC / 8) * (d->skip_channels + d->residual_channels) * 16;
+}
+
+static void wn_descs(const pwgb_wavenet_desc* d, pwgb_conv1d_desc& c1, pwgb_conv1d_desc& c2) {
+  c1 = pwgb_conv1d_desc{};
+  c1.batch = d->batch;
+  c1.cin = d->residual_channels;
+  c1.cout = d->gate_channels;
+  c1.t_in = c1.t_out = d->t;
+  c1.kernel = d->kernel;
+  c1.stride = 1;
+  c1.dilation = d->dilation;
+  c1.groups = 1;
+  c1.pad_left = (d->kernel - 1) / 2 * d->dilation;
+  c1.pad_mode = PWGB_PAD_ZERO;
+  c1.period = 1;
+  c1.t_valid = d->t;
+  c1.pre_slope = 1.f;
+  c1.out_scale = 1.f;
+  c2 = pwgb_conv1d_desc{};
+  c2.batch = d->batch;
+  c2.cin = d->gate_channels / 2;
+  c2.cout = d->skip_channels + d->residual_channels;
+  c2.t_in = c2.t_out = d->t;
+  c2.kernel = 1;
+  c2.stride = 1;
+  c2.dilation = 1;
+  c2.groups = 1;
+  c2.pad_mode = PWGB_PAD_ZERO;
+  c2.period = 1;
+  c2.t_valid = d->t;
+  c2.pre_slope = 1.f;
+  c2.pre_gate = 1;
+  c2.out_scale = 0.70710678118654752440f;
+}
+
+static int wn_valid(const pwgb_wavenet_desc* d) {
+  return d && d->batch >= 0 && d->t > 0 && d->kernel > 0 && d->kernel % 2 == 1 && d->dilation > 0 &&
+         d->residual_channels > 0 && d->gate_channels > 0 && d->gate_channels % 2 == 0 && d->skip_channels > 0 &&
+         d->aux_channels >= 0;
+}
+
+extern "C" int pwgb_wavenet_supported(const pwgb_wavenet_desc* d) {
+  if (!wn_valid(d)) return 0;
+  if (d->residual_channels % KC || (d->gate_channels / 2) % KC || d->aux_channels % KC || d->skip_channels % 16) return 0;
+  pwgb_conv1d_desc c1, c2;
+  wn_descs(d, c1, c2);
+  TcK p;
+  size_t bytes;
+  return tc_plan(&c1, p, bytes, d->aux_channels, 0) && tc_plan(&c2, p, bytes, 0, d->skip_channels);
+}
+
+extern "C" size_t pwgb_wavenet_packed_bytes(const pwgb_wavenet_desc* d) {
+  if (!pwgb_wavenet_supported(d)) return 0;
+  return wn_image1_bytes(d) + wn_aux_bytes(d) + wn_image2_bytes(d);
+}
+
+extern "C" int pwgb_wavenet_pack(const pwgb_wavenet_desc* d, const float* w_conv, const float* w_aux,
+                                 int aux_channels_real, const float* w_skip, const float* w_out, void* packed,
+                                 void* stream) {
+  PWGB_UNSUPPORTED_IF(!pwgb_wavenet_supported(d), "wavenet_pack: configuration not supported by the tcgen05 path");
+  PWGB_CHECK_ARG(w_conv && w_skip && w_out && packed && (w_aux || d->aux_channels == 0), "wavenet_pack: null argument");
+  PWGB_CHECK_ARG(aux_channels_real <= d->aux_channels, "wavenet_pack: aux_channels_real > padded aux_channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* img = (unsigned char*)packed;
+  const int G = d->gate_channels, H = G / 2, S = d->skip_channels, R = d->residual_channels;
+  tc_pack_rows(w_conv, img, R, R, G, d->kernel, 0, G, st);
+  int rc = check_launch("tc_pack_weight_kernel");
+  if (rc) return rc;
+  if (d->aux_channels) {
+    tc_pack_rows(w_aux, img + wn_image1_bytes(d), aux_channels_real, d->aux_channels, G, 1, 0, G, st);
+    rc = check_launch("tc_pack_weight_kernel");
+    if (rc) return rc;
+  }
+  unsigned char* img2 = img + wn_image1_bytes(d) + wn_aux_bytes(d);
+  tc_pack_rows(w_skip, img2, H, H, S, 1, 0, S + R, st);
+  rc = check_launch("tc_pack_weight_kernel");
+  if (rc) return rc;
+  tc_pack_rows(w_out, img2, H, H, R, 1, S, S + R, st);
+  return check_launch("tc_pack_weight_kernel");
+}
+
+extern "C" int pwgb_wavenet_layer_forward(const pwgb_wavenet_desc* d, const float* x, const float* c,
+                                          const void* packed, const float* b_conv, const float* b_skip_out,
+                                          float* x_out, float* skips, float* g_ws, void* stream) {
+  PWGB_UNSUPPORTED_IF(!pwgb_wavenet_supported(d), "wavenet_layer: configuration not supported by the tcgen05 path");
+  PWGB_CHECK_ARG(x && packed && x_out && skips && g_ws && (c || d->aux_channels == 0), "wavenet_layer: null argument");
+  PWGB_CHECK_ARG(x != x_out, "wavenet_layer: x_out must not alias x (halo reads)");
+  cudaStream_t st = (cudaStream_t)stream;
+  pwgb_conv1d_desc c1, c2;
+  wn_descs(d, c1, c2);
+  TcK p;
+  size_t bytes = 0;
+  tc_plan(&c1, p, bytes, d->aux_channels, 0);
+  int rc = tc_launch(p, bytes, x, packed, b_conv, nullptr, g_ws, st, c, nullptr);
+  if (rc) return rc;
+  tc_plan(&c2, p, bytes, 0, d->skip_channels);
+  const unsigned char* img2 = (const unsigned char*)packed + wn_image1_bytes(d) + wn_aux_bytes(d);
+  return tc_launch(p, bytes, g_ws, img2, b_skip_out, x, x_out, st, nullptr, skips);
 }

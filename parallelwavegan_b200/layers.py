@@ -226,3 +226,124 @@ class PQMF(torch.nn.Module):
         n = self.subbands
         w = (self.synthesis_filter[0].flip(-1) * float(n)).unsqueeze(1).contiguous()  # (N, 1, taps+1)
         return ops.conv_transpose1d(x, w, None, stride=n, padding=self.taps // 2, output_padding=n - 1)
+
+
+# --------------------------------------------------------------------------
+# Parallel WaveGAN blocks (layers/residual_block.py:43-140, layers/upsample.py)
+# --------------------------------------------------------------------------
+
+
+class WaveNetResidualBlock(torch.nn.Module):
+    """layers/residual_block.py:43-140.  ``forward(x, c, skips)`` runs the fused layer and
+    accumulates the skip branch in place; it returns the new residual stream."""
+
+    def __init__(
+        self,
+        kernel_size=3,
+        residual_channels=64,
+        gate_channels=128,
+        skip_channels=64,
+        aux_channels=80,
+        dropout=0.0,
+        dilation=1,
+        bias=True,
+        use_causal_conv=False,
+    ):
+        super().__init__()
+        if use_causal_conv:
+            raise PwgbError("WaveNetResidualBlock(use_causal_conv=True) has no sm_100a kernel yet")
+        if dropout != 0.0:
+            raise PwgbError("WaveNetResidualBlock(dropout>0) has no sm_100a kernel (all reference configs use 0.0)")
+        assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
+        self.dropout = dropout
+        self.dilation = dilation
+        self.aux_channels = aux_channels
+        self.use_causal_conv = use_causal_conv
+        padding = (kernel_size - 1) // 2 * dilation
+        self.conv = Conv1d(residual_channels, gate_channels, kernel_size, padding=padding, dilation=dilation, bias=bias)
+        self.conv1x1_aux = Conv1d1x1(aux_channels, gate_channels, bias=False) if aux_channels > 0 else None
+        gate_out_channels = gate_channels // 2
+        self.conv1x1_out = Conv1d1x1(gate_out_channels, residual_channels, bias=bias)
+        self.conv1x1_skip = Conv1d1x1(gate_out_channels, skip_channels, bias=bias)
+        self._cache = {}
+
+    def forward(self, x, c, skips=None):
+        """x: (B, R, T); c: (B, aux[_padded], T) or None; skips: (B, S, T) accumulated in place.
+        Returns (x_out, skips) -- with ``skips=None`` a fresh zero tensor is used so that the pair
+        equals the reference's ``(x, s)`` (layers/residual_block.py:140)."""
+        if skips is None:
+            skips = torch.zeros((x.shape[0], self.conv1x1_skip.out_channels, x.shape[2]), device=x.device, dtype=x.dtype)
+        aux = self.conv1x1_aux
+        x_out = ops.wavenet_layer(
+            x, c,
+            effective_weight(self.conv), self.conv.bias,
+            effective_weight(aux) if aux is not None else None,
+            effective_weight(self.conv1x1_skip), self.conv1x1_skip.bias,
+            effective_weight(self.conv1x1_out), self.conv1x1_out.bias,
+            self.dilation, skips, self.aux_channels, cache=self._cache,
+        )
+        return x_out, skips
+
+
+class Stretch2d(torch.nn.Module):
+    """layers/upsample.py:16-45 (parameter-free; fused into the FIR stage kernel)."""
+
+    def __init__(self, x_scale, y_scale, mode="nearest"):
+        super().__init__()
+        if mode != "nearest" or y_scale != 1:
+            raise PwgbError("Stretch2d: only nearest time-axis stretching has an sm_100a kernel")
+        self.x_scale, self.y_scale, self.mode = x_scale, y_scale, mode
+
+
+class Conv2d(torch.nn.Conv2d):
+    """layers/upsample.py:48-59: box-filter initialised Conv2d (container for the FIR taps)."""
+
+    def reset_parameters(self):
+        self.weight.data.fill_(1.0 / np.prod(self.kernel_size))
+        if self.bias is not None:
+            torch.nn.init.constant_(self.bias, 0.0)
+
+
+class UpsampleNetwork(torch.nn.Module):
+    """layers/upsample.py:62-128."""
+
+    def __init__(self, upsample_scales, nonlinear_activation=None, nonlinear_activation_params={},
+                 interpolate_mode="nearest", freq_axis_kernel_size=1, use_causal_conv=False):
+        super().__init__()
+        if use_causal_conv or nonlinear_activation is not None or freq_axis_kernel_size != 1:
+            raise PwgbError("UpsampleNetwork: causal / nonlinear / freq-axis-kernel variants have no sm_100a kernel yet")
+        self.use_causal_conv = use_causal_conv
+        self.upsample_scales = list(upsample_scales)
+        self.up_layers = torch.nn.ModuleList()
+        for scale in upsample_scales:
+            self.up_layers += [Stretch2d(scale, 1, interpolate_mode)]
+            self.up_layers += [Conv2d(1, 1, kernel_size=(1, scale * 2 + 1), padding=(0, scale), bias=False)]
+
+    def forward(self, c, out_channels=None):
+        """(B, C, T') -> (B, C [padded to out_channels], T' * prod(scales))."""
+        n = len(self.upsample_scales)
+        for i, s in enumerate(self.upsample_scales):
+            fir = effective_weight(self.up_layers[2 * i + 1])
+            c = ops.upsample_fir(c, fir, s, out_channels=out_channels if i == n - 1 else None)
+        return c
+
+
+class ConvInUpsampleNetwork(torch.nn.Module):
+    """layers/upsample.py:131-194."""
+
+    def __init__(self, upsample_scales, nonlinear_activation=None, nonlinear_activation_params={},
+                 interpolate_mode="nearest", freq_axis_kernel_size=1, aux_channels=80, aux_context_window=0,
+                 use_causal_conv=False):
+        super().__init__()
+        if use_causal_conv:
+            raise PwgbError("ConvInUpsampleNetwork(use_causal_conv=True) has no sm_100a kernel yet")
+        self.aux_context_window = aux_context_window
+        self.use_causal_conv = False
+        kernel_size = 2 * aux_context_window + 1
+        self.conv_in = Conv1d(aux_channels, aux_channels, kernel_size=kernel_size, bias=False)
+        self.upsample = UpsampleNetwork(upsample_scales, nonlinear_activation, nonlinear_activation_params,
+                                        interpolate_mode, freq_axis_kernel_size, use_causal_conv)
+
+    def forward(self, c, out_channels=None):
+        c_ = ops.conv1d(c, effective_weight(self.conv_in), None)  # no padding: input already carries the context
+        return self.upsample(c_, out_channels=out_channels)

@@ -271,3 +271,144 @@ class MelGANGenerator(_GeneratorBase):
         if self.pqmf is not None:
             c = self.pqmf.synthesis(c)
         return c.squeeze(0).transpose(1, 0)
+
+
+class ParallelWaveGANGenerator(_GeneratorBase):
+    """models/parallel_wavegan.py:21-261."""
+
+    def __init__(
+        self,
+        in_channels=1,
+        out_channels=1,
+        kernel_size=3,
+        layers=30,
+        stacks=3,
+        residual_channels=64,
+        gate_channels=128,
+        skip_channels=64,
+        aux_channels=80,
+        aux_context_window=2,
+        dropout=0.0,
+        bias=True,
+        use_weight_norm=True,
+        use_causal_conv=False,
+        upsample_conditional_features=True,
+        upsample_net="ConvInUpsampleNetwork",
+        upsample_params={"upsample_scales": [4, 4, 4, 4]},
+    ):
+        super().__init__()
+        import math
+
+        from . import layers as L
+
+        if use_causal_conv:
+            raise PwgbError("ParallelWaveGANGenerator(use_causal_conv=True) has no sm_100a kernel yet")
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.aux_channels = aux_channels
+        self.aux_context_window = aux_context_window
+        self.layers = layers
+        self.stacks = stacks
+        self.kernel_size = kernel_size
+        assert layers % stacks == 0
+        layers_per_stack = layers // stacks
+        self.first_conv = L.Conv1d1x1(in_channels, residual_channels, bias=True)
+        upsample_params = dict(upsample_params)
+        if upsample_conditional_features:
+            upsample_params.update({"use_causal_conv": use_causal_conv})
+            if upsample_net == "MelGANGenerator":
+                assert aux_context_window == 0
+                upsample_params.update({"use_weight_norm": False, "use_final_nonlinear_activation": False})
+                self.upsample_net = MelGANGenerator(**upsample_params)
+            else:
+                if upsample_net == "ConvInUpsampleNetwork":
+                    upsample_params.update({"aux_channels": aux_channels, "aux_context_window": aux_context_window})
+                self.upsample_net = getattr(L, upsample_net)(**upsample_params)
+            self.upsample_factor = int(np.prod(upsample_params["upsample_scales"]))
+        else:
+            self.upsample_net = None
+            self.upsample_factor = 1
+        self.conv_layers = torch.nn.ModuleList()
+        for layer in range(layers):
+            dilation = 2 ** (layer % layers_per_stack)
+            self.conv_layers += [
+                L.WaveNetResidualBlock(
+                    kernel_size=kernel_size, residual_channels=residual_channels, gate_channels=gate_channels,
+                    skip_channels=skip_channels, aux_channels=aux_channels, dilation=dilation, dropout=dropout,
+                    bias=bias, use_causal_conv=use_causal_conv,
+                )
+            ]
+        self.last_conv_layers = torch.nn.ModuleList(
+            [
+                torch.nn.ReLU(inplace=True),
+                L.Conv1d1x1(skip_channels, skip_channels, bias=True),
+                torch.nn.ReLU(inplace=True),
+                L.Conv1d1x1(skip_channels, out_channels, bias=True),
+            ]
+        )
+        self._skip_scale = math.sqrt(1.0 / layers)
+        self._aux_pad = (aux_channels + 31) // 32 * 32
+        if use_weight_norm:
+            self.apply_weight_norm()
+
+    def forward(self, z, c):
+        """z: (B, 1, T) noise, c: (B, aux, T') -> (B, out_channels, T)  (parallel_wavegan.py:144-173)."""
+        if c is not None and self.upsample_net is not None:
+            if isinstance(self.upsample_net, MelGANGenerator):
+                c = self.upsample_net(c)
+            else:
+                c = self.upsample_net(c, out_channels=self._aux_pad)
+            assert c.size(-1) == z.size(-1)
+        if c is not None and c.shape[1] != self._aux_pad:
+            cp = torch.zeros((c.shape[0], self._aux_pad, c.shape[2]), device=c.device, dtype=c.dtype)
+            cp[:, : c.shape[1]].copy_(c)
+            c = cp
+        fc = self.first_conv
+        x = ops.conv1d(z, effective_weight(fc), fc.bias)
+        skips = torch.zeros((x.shape[0], self.conv_layers[0].conv1x1_skip.out_channels, x.shape[2]), device=x.device, dtype=torch.float32)
+        for f in self.conv_layers:
+            x, _ = f(x, c, skips)
+        # relu(a * s) = a * relu(s) for a > 0: the sqrt(1/layers) scale is folded into the 1x1 weights
+        l1, l3 = self.last_conv_layers[1], self.last_conv_layers[3]
+        h = ops.conv1d(skips, effective_weight(l1) * self._skip_scale, l1.bias, pre_slope=0.0)
+        return ops.conv1d(h, effective_weight(l3), l3.bias, pre_slope=0.0)
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d)):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+    @staticmethod
+    def _get_receptive_field_size(layers, stacks, kernel_size, dilation=lambda x: 2**x):
+        assert layers % stacks == 0
+        layers_per_cycle = layers // stacks
+        dilations = [dilation(i % layers_per_cycle) for i in range(layers)]
+        return (kernel_size - 1) * sum(dilations) + 1
+
+    @property
+    def receptive_field_size(self):
+        return self._get_receptive_field_size(self.layers, self.stacks, self.kernel_size)
+
+    def inference(self, c=None, x=None, normalize_before=False):
+        """c: (T', aux) | None, x: (T, 1) noise | None -> (T, out_channels)  (parallel_wavegan.py:229-261)."""
+        dev = next(self.parameters()).device
+        if x is not None:
+            if not isinstance(x, torch.Tensor):
+                x = torch.tensor(x, dtype=torch.float).to(dev)
+            x = x.transpose(1, 0).unsqueeze(0).contiguous()
+        else:
+            assert c is not None
+            x = torch.randn(1, 1, len(c) * self.upsample_factor).to(dev)
+        if c is not None:
+            if not isinstance(c, torch.Tensor):
+                c = torch.tensor(c, dtype=torch.float).to(dev)
+            if normalize_before:
+                c = (c - self.mean) / self.scale
+            c = c.transpose(1, 0).unsqueeze(0)
+            # ReplicationPad1d(aux_context_window): pure index gather of the edge frames
+            w = self.aux_context_window
+            idx = torch.arange(-w, c.shape[-1] + w, device=c.device).clamp_(0, c.shape[-1] - 1)
+            c = c[:, :, idx].contiguous()
+        return self.forward(x, c).squeeze(0).transpose(1, 0)

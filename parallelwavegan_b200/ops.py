@@ -187,3 +187,78 @@ def conv_transpose1d(x, w, bias=None, *, stride, padding=0, output_padding=0, pr
     capi.check(rc, "pwgb_conv_transpose1d_forward")
     prof.done()
     return y
+
+
+def upsample_fir(x, fir, scale, out=None, out_channels=None):
+    """One stage of the PWG conditioning upsampler (layers/upsample.py:112-128):
+    nearest repeat x`scale` + (2*scale+1)-tap FIR, zero padded -- pwgb_upsample_fir_forward.
+    x: (B, C, T) -> (B, C, T*scale); with ``out_channels`` > C the result is written into the
+    first C channels of a zero-initialised (B, out_channels, T*scale) tensor (channel padding
+    for the tcgen05 conditioning contraction)."""
+    x = _dev(x, "x")
+    fir = _dev(fir, "fir").reshape(-1)
+    B, Cc, T = x.shape
+    if fir.numel() != 2 * scale + 1:
+        raise PwgbError("upsample_fir: filter must have 2*scale+1 taps")
+    oc = Cc if out_channels is None else int(out_channels)
+    if out is None:
+        out = (torch.zeros if oc != Cc else torch.empty)((B, oc, T * scale), device=x.device, dtype=torch.float32)
+    prof = _Prof("upsample_fir", 2.0 * B * Cc * T * scale * (2 * scale + 1), 4.0 * (x.numel() + B * Cc * T * scale), f"B{B} C{Cc} T{T} s{scale}")
+    rc = capi.lib().pwgb_upsample_fir_forward(B * Cc, Cc, T, int(scale), _p(x), _p(fir), _p(out), oc * T * scale, _stream())
+    capi.check(rc, "pwgb_upsample_fir_forward")
+    prof.done()
+    return out
+
+
+class WaveNetLayerWeights:
+    """Device-side operand images of one WaveNetResidualBlock for pwgb_wavenet_layer_forward."""
+
+    __slots__ = ("desc", "packed", "b_conv", "b_skip_out", "key")
+
+
+def wavenet_layer(x, c, w_conv, b_conv, w_aux, w_skip, b_skip, w_out, b_out, dilation, skips, aux_real, cache=None):
+    """WaveNetResidualBlock.forward (layers/residual_block.py:102-140), in place on ``skips``:
+    returns x_out.  ``c``: (B, aux_pad, T) conditioning, zero-padded to a multiple of 32 channels
+    (or None).  Uses the fused tcgen05 layer when pwgb_wavenet_supported(), otherwise composes the
+    layer from the generic fused conv (gate pre-op, accumulate, residual epilogue)."""
+    x = _dev(x, "x")
+    B, R, T = x.shape
+    G, _, K = w_conv.shape
+    S = w_skip.shape[0]
+    L = capi.lib()
+    aux_pad = 0 if c is None else c.shape[1]
+    d = capi.WaveNetDesc(batch=B, t=T, residual_channels=R, gate_channels=G, skip_channels=S, aux_channels=aux_pad,
+                         kernel=K, dilation=int(dilation))
+    if ENGINE != "simt" and L.pwgb_wavenet_supported(C.byref(d)):
+        key = tuple((t.data_ptr(), t._version) for t in (w_conv, w_aux, w_skip, w_out) if t is not None)
+        ent = cache.get("wn") if cache is not None else None
+        if ent is None or ent[0] != key:
+            nbytes = L.pwgb_wavenet_packed_bytes(C.byref(d))
+            packed = torch.empty(nbytes // 4, device=x.device, dtype=torch.int32)
+            rc = L.pwgb_wavenet_pack(C.byref(d), _p(_dev(w_conv, "w_conv")), _p(w_aux.contiguous() if w_aux is not None else None),
+                                     int(aux_real), _p(_dev(w_skip, "w_skip")), _p(_dev(w_out, "w_out")), _p(packed), _stream())
+            capi.check(rc, "pwgb_wavenet_pack")
+            bso = None
+            if b_skip is not None:
+                bso = torch.cat([b_skip.detach().reshape(-1), b_out.detach().reshape(-1)]).contiguous()
+            ent = (key, packed, bso)
+            if cache is not None:
+                cache["wn"] = ent
+        _, packed, bso = ent
+        g_ws = torch.empty((B, G, T), device=x.device, dtype=torch.float32)
+        x_out = torch.empty_like(x)
+        prof = _Prof("wavenet_layer_tc", 2.0 * B * T * (G * R * K + G * aux_real + (S + R) * (G // 2)),
+                     4.0 * B * T * (2 * R + aux_real + 2 * S), f"B{B} R{R} G{G} S{S} A{aux_real} k{K} d{dilation} T{T}")
+        rc = L.pwgb_wavenet_layer_forward(C.byref(d), _p(x), _p(c), _p(packed), _p(b_conv), _p(bso), _p(x_out), _p(skips), _p(g_ws), _stream())
+        capi.check(rc, "pwgb_wavenet_layer_forward")
+        prof.done()
+        return x_out
+    # generic composition (any channel counts): 4 launches
+    g = conv1d(x, w_conv, b_conv, dilation=dilation, padding=(K - 1) // 2 * dilation)
+    if c is not None:
+        wa = w_aux
+        if c.shape[1] != w_aux.shape[1]:  # conditioning stored channel-padded
+            wa = torch.nn.functional.pad(w_aux, (0, 0, 0, c.shape[1] - w_aux.shape[1]))
+        conv1d(c, wa, None, out=g, accumulate=True)
+    conv1d(g, w_skip, b_skip, pre_gate=True, out=skips, accumulate=True)
+    return conv1d(g, w_out, b_out, pre_gate=True, residual=x, out_scale=0.7071067811865476)

@@ -257,3 +257,77 @@ def test_conv1d_tcgen05_path(dev, cin, cout, k, dil, T, B, mode):
     assert e_ff < FP32_TOL
     assert e_tc < TC_TOL, (e_tc, e_ff)
     assert max_abs_over_peak(y_tc.cpu(), ref) < TC_TOL * 5
+
+
+@pytest.mark.parametrize("name", ["pwg_v1", "pwg_small"])
+def test_pwg_generator_vs_reference(dev, name):
+    meta, g, m = _load_mirror(name, dev)
+    kw = meta["kwargs"]
+    c = synth.randn(meta["c_shape"], meta["c_seed"]).to(dev)
+    z = synth.randn(meta["z_shape"], meta["z_seed"]).to(dev)
+    ctx = kw["aux_context_window"]
+    with torch.no_grad():
+        c_up = m.upsample_net(c)
+        y = m(z, c)
+        y_inf = m.inference(c=c[0, :, ctx : c.shape[-1] - ctx].t(), x=z[0].t())
+        x0 = m.first_conv.weight  # noqa: F841  (container only)
+    assert rel_l2(c_up[:, :, :512].cpu(), g["c_up"]) < FP32_TOL * 5
+    assert tuple(y.shape) == tuple(g["y"].shape)
+    assert rel_l2(y.cpu(), g["y"]) < REL_TOL and max_abs_over_peak(y.cpu(), g["y"]) < REL_TOL
+    assert rel_l2(y_inf.cpu(), g["y_inf"]) < REL_TOL
+    cfg = dict(kw, upsample_scales=kw["upsample_params"]["upsample_scales"])
+    ref = ref_ops.pwg_generator(golden_effective_weights(meta), z.cpu(), c.cpu(), cfg)
+    assert rel_l2(y.cpu(), ref) < REL_TOL
+
+
+@pytest.mark.parametrize("dilation,T,B", [(1, 700, 2), (16, 1000, 2), (64, 515, 1), (128, 1500, 2), (512, 2100, 1)])
+@pytest.mark.parametrize("engine", ["auto", "simt"])
+def test_wavenet_layer(dev, dilation, T, B, engine):
+    """One WaveNetResidualBlock (PWG v1 sizes) vs the oracle, both engines; dilation 128/512
+    exercise the per-tap window mode of the tcgen05 kernel."""
+    from parallelwavegan_b200 import layers, ops
+
+    blk = layers.WaveNetResidualBlock(dilation=dilation)
+    spec = [(k, tuple(v.shape)) for k, v in blk.state_dict().items()]
+    sd = synth.synth_state_dict(spec, 40 + dilation, 1.0)
+    blk.load_state_dict(sd)
+    blk = blk.to(dev)
+    x = synth.randn((B, 64, T), 1)
+    c = synth.randn((B, 80, T), 2)
+    sk0 = synth.randn((B, 64, T), 3)
+    w = {f"b.{k}": v for k, v in sd.items()}
+    xr, sr = ref_ops.wavenet_residual_block(w, "b", x, c, dilation, 3)
+    cp = torch.zeros(B, 96, T)
+    cp[:, :80] = c
+    skips = sk0.clone().to(dev)
+    old = ops.ENGINE
+    try:
+        ops.ENGINE = engine
+        ops.PROFILE = []
+        with torch.no_grad():
+            xo, so = blk(x.to(dev), cp.to(dev), skips)
+        torch.cuda.synchronize()
+        names = [p[0] for p in ops.PROFILE]
+    finally:
+        ops.ENGINE = old
+        ops.PROFILE = None
+    if engine == "auto":
+        assert names == ["wavenet_layer_tc"]
+    tol = TC_TOL if engine == "auto" else FP32_TOL
+    assert rel_l2(xo.cpu(), xr) < tol
+    assert rel_l2(so.cpu(), sk0 + sr) < tol
+
+
+def test_upsample_fir(dev):
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((3, 7, 33), 5)
+    for s in (2, 4, 5):
+        f = synth.randn((2 * s + 1,), 6 + s, 0.3)
+        ref = torch.repeat_interleave(x, s, dim=-1)
+        ref = F.conv1d(ref.reshape(21, 1, -1), f.reshape(1, 1, -1), padding=s).reshape(3, 7, -1)
+        y = ops.upsample_fir(x.to(dev), f.to(dev), s)
+        assert rel_l2(y.cpu(), ref) < FP32_TOL
+        yp = ops.upsample_fir(x.to(dev), f.to(dev), s, out_channels=32)
+        assert tuple(yp.shape) == (3, 32, 33 * s)
+        assert rel_l2(yp[:, :7].cpu(), ref) < FP32_TOL and float(yp[:, 7:].abs().max()) == 0.0
