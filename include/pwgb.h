@@ -158,6 +158,42 @@ PWGB_API int pwgb_wavenet_layer_forward(const pwgb_wavenet_desc* d, const float*
 PWGB_API int pwgb_upsample_fir_forward(int rows, int rows_per_batch, int t_in, int scale, const float* x, const float* fir,
                               float* y, long long y_batch_stride, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Spectral losses.  stft(): losses/stft_loss.py:16-40 (center=True, reflect pad n_fft/2, window of
+ * win_length centred in n_fft, rFFT, sqrt(clamp(re^2+im^2, eps))).
+ * pwgb_mr_stft_loss_forward = MultiResolutionSTFTLoss.forward (stft_loss.py:146-170) for signals
+ * x (predicted) and y (ground truth), both (batch, t): out2[0] = sc, out2[1] = mag, averaged over
+ * the n_res resolutions; windows[r] is a DEVICE pointer to win_length floats (the module buffer).
+ * pwgb_stft_amplitude_forward writes sqrt(clamp(|STFT|^2, eps)) as (batch, frames, n_fft/2+1) for
+ * one or two signals; pwgb_mel_project_forward is the rest of MelSpectrogram(.Loss)
+ * (mel_loss.py:105-110, 150-165): mel = clamp(amp @ melmat, eps), log * log_scale, optional
+ * (batch, n_mels, frames) output and/or the mean L1 between the two signals' log-mels.
+ * ---------------------------------------------------------------------- */
+typedef struct pwgb_stft_desc {
+  int32_t batch, t, n_fft, hop, win_length;
+  float clamp_eps;
+} pwgb_stft_desc;
+PWGB_API size_t pwgb_mr_stft_loss_workspace(const pwgb_stft_desc* descs, int n_res);
+PWGB_API int pwgb_mr_stft_loss_forward(const pwgb_stft_desc* descs, int n_res, const float* x, const float* y,
+                              const float* const* windows, float* out2, void* ws, size_t ws_bytes, void* stream);
+PWGB_API int pwgb_stft_amplitude_forward(const pwgb_stft_desc* d, const float* x, const float* y, const float* window,
+                                float* amp_x, float* amp_y, void* stream);
+PWGB_API int pwgb_mel_project_forward(int batch, int frames, int bins, int n_mels, const float* amp_x, const float* amp_y,
+                             const float* melmat, float eps, float log_scale, float* mel_x, float* loss, float* ws,
+                             void* stream);
+
+/* ------------------------------------------------------------------------
+ * Deterministic mean reductions for the GAN losses (losses/adversarial_loss.py:29-123,
+ * losses/feat_match_loss.py:27-54): out[0] (+)= weight * mean_i f(x_i [, y_i]) with
+ * mode 0: (x-c)^2, 1: |x-y|, 2: max(0, c - s*x), 3: s*x.  ws: >= 1 float of scratch
+ * (more = more parallel partials, up to 1024).
+ * AvgPool1d between discriminator scales (hifigan.py:758-775, melgan.py:478-493).
+ * ---------------------------------------------------------------------- */
+PWGB_API int pwgb_reduce_mean_forward(int mode, const float* x, const float* y, long long n, float c, float s, float weight,
+                             int accumulate, float* out, float* ws, int ws_floats, void* stream);
+PWGB_API int pwgb_avg_pool1d_forward(const float* x, float* y, int rows, int t_in, int kernel, int stride, int padding,
+                            int count_include_pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

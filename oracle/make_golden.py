@@ -183,8 +183,95 @@ def gen_conv_cases():
     save("conv_cases", dict(kind="conv_cases", cases=cases), **arrays)
 
 
+def summarize(outs):
+    """Compact fingerprint of a (nested) list of feature maps: shape, float64 sum / L2, head+tail."""
+    arrays, shapes = {}, []
+    flat = []
+    for i, o in enumerate(outs):
+        if isinstance(o, (list, tuple)):
+            for j, t in enumerate(o):
+                flat.append((f"o{i}_{j}", t))
+        else:
+            flat.append((f"o{i}", o))
+    for name, t in flat:
+        t = t.detach()
+        v = t.reshape(-1).double()
+        arrays[name + "_stat"] = np.array([float(v.sum()), float(v.norm())])
+        arrays[name + "_head"] = t.reshape(-1)[:96].clone()
+        arrays[name + "_tail"] = t.reshape(-1)[-96:].clone()
+        shapes.append((name, list(t.shape)))
+    return arrays, shapes
+
+
+def gen_discriminator(name, cls_name, kwargs, B, T, seed, gain, train_mode=False):
+    import parallel_wavegan.models as M
+
+    torch.manual_seed(0)
+    m = getattr(M, cls_name)(**json.loads(json.dumps(kwargs)))
+    m.train(train_mode)
+    spec, sd = load_synth(m, seed, gain)
+    x = synth.randn((B, 1, T), seed + 1, 0.5)
+    with torch.no_grad():
+        outs = m(x)
+    if isinstance(outs, torch.Tensor):
+        outs = [outs]
+    arrays, shapes = summarize(outs)
+    final = [o[-1] if isinstance(o, (list, tuple)) else o for o in outs]
+    for i, f in enumerate(final):
+        arrays[f"final{i}"] = f
+    if train_mode:  # spectral-norm power iteration mutates weight_u / weight_v
+        for k, v in m.state_dict().items():
+            if k.endswith("weight_u"):
+                arrays["u__" + k.replace(".", "__")] = v
+    meta = dict(kind="discriminator", cls=cls_name, kwargs=kwargs, spec=spec, seed=seed, gain=gain, checksum=synth.checksum(sd),
+                x_shape=list(x.shape), x_seed=seed + 1, x_scale=0.5, shapes=shapes, train_mode=train_mode)
+    save(name, meta, **arrays)
+
+
+def gen_losses():
+    from parallel_wavegan.losses import (DiscriminatorAdversarialLoss, FeatureMatchLoss, GeneratorAdversarialLoss,
+                                         MelSpectrogram, MelSpectrogramLoss, MultiResolutionSTFTLoss)
+    from parallel_wavegan.losses.stft_loss import stft
+
+    x = synth.randn((3, 8192), 501, 0.3)
+    y = synth.randn((3, 8192), 502, 0.3)
+    y = 0.7 * y + 0.3 * x
+    arrays = {}
+    mr = MultiResolutionSTFTLoss()
+    sc, mag = mr(x, y)
+    arrays["mr_default"] = torch.stack([sc, mag])
+    sc, mag = mr(x.view(1, 3, -1), y.view(1, 3, -1))
+    arrays["mr_3d"] = torch.stack([sc, mag])
+    mr2 = MultiResolutionSTFTLoss([64, 128, 256], [16, 32, 64], [64, 128, 256])  # test/test_parallel_wavegan.py sizes
+    sc, mag = mr2(x[:, :2048], y[:, :2048])
+    arrays["mr_small"] = torch.stack([sc, mag])
+    arrays["stft_mag"] = stft(x[:1, :4096], 1024, 120, 600, torch.hann_window(600))[:, :8]
+    for tag, kw in (("v1", dict(fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80, fmin=0, fmax=11025, log_base=None)),
+                    ("default", dict())):
+        ms = MelSpectrogram(**kw)
+        arrays[f"mel_{tag}"] = ms(x[:2])
+        arrays[f"melmat_{tag}"] = ms.melmat
+        arrays[f"mel_loss_{tag}"] = MelSpectrogramLoss(**kw)(x.unsqueeze(1), y.unsqueeze(1)).reshape(1)
+    # GAN losses on synthetic discriminator outputs (lists of lists, last = logits)
+    g = torch.Generator().manual_seed(77)
+    outs_hat = [[torch.randn(2, 4, 50, generator=g), torch.randn(2, 8, 25, generator=g), torch.randn(2, 1, 25, generator=g)] for _ in range(3)]
+    outs = [[torch.randn(2, 4, 50, generator=g), torch.randn(2, 8, 25, generator=g), torch.randn(2, 1, 25, generator=g)] for _ in range(3)]
+    for lt in ("mse", "hinge"):
+        arrays[f"gen_adv_{lt}"] = GeneratorAdversarialLoss(loss_type=lt)(outs_hat).reshape(1)
+        r, f = DiscriminatorAdversarialLoss(loss_type=lt)(outs_hat, outs)
+        arrays[f"dis_adv_{lt}"] = torch.stack([r, f])
+    arrays["feat_match"] = FeatureMatchLoss()(outs_hat, outs).reshape(1)
+    arrays["feat_match_noavg"] = FeatureMatchLoss(False, False, True)(outs_hat, outs).reshape(1)
+    save("losses", dict(kind="losses"), **arrays)
+
+
 def main():
     import_reference()
+    gen_losses()
+    gen_discriminator("hifigan_msmpd_v1", "HiFiGANMultiScaleMultiPeriodDiscriminator", {}, B=2, T=8192, seed=61, gain=1.4)
+    gen_discriminator("hifigan_msmpd_v1_train", "HiFiGANMultiScaleMultiPeriodDiscriminator", {}, B=1, T=4099, seed=62, gain=1.4, train_mode=True)
+    gen_discriminator("melgan_msd", "MelGANMultiScaleDiscriminator", dict(downsample_scales=[4, 4, 4], max_downsample_channels=512), B=2, T=16200, seed=63, gain=1.4)
+    gen_discriminator("pwg_disc", "ParallelWaveGANDiscriminator", {}, B=2, T=5000, seed=64, gain=1.4)
     gen_conv_cases()
     gen_pqmf()
     # reference unit-test shapes (test/test_hifigan.py:35-53)

@@ -36,7 +36,7 @@ def fold_weight_norm(sd):
             dims = tuple(range(1, vv.dim()))
             norm = vv.pow(2).sum(dim=dims, keepdim=True).sqrt()
             out[base] = g * vv / norm
-        elif k.endswith(".weight_v"):
+        elif k.endswith(".weight_v") and (k[: -len("_v")] + "_g") in sd:
             continue
         else:
             out[k] = v
@@ -484,3 +484,158 @@ def mel_spectrogram(x, melmat, fft_size=1024, hop_size=256, win_length=None, eps
 def mel_loss(y_hat, y, melmat, **kw):
     """MelSpectrogramLoss.forward (losses/mel_loss.py:150-165)."""
     return F.l1_loss(mel_spectrogram(y_hat, melmat, **kw), mel_spectrogram(y, melmat, **kw))
+
+
+# --------------------------------------------------------------------------
+# Discriminators (models/hifigan.py:270-864, models/melgan.py:260-534,
+# models/parallel_wavegan.py:264-371).  Weights: effective (norm-folded) dict.
+# --------------------------------------------------------------------------
+
+
+def hifigan_period_discriminator(w, prefix, x, period, n_layers=5, strides=(3, 3, 3, 3, 1), slope=0.1, k0=5, k1=3):
+    """HiFiGANPeriodDiscriminator.forward (hifigan.py:354-381)."""
+    b, c, t = x.shape
+    if t % period != 0:
+        n_pad = period - (t % period)
+        x = F.pad(x, (0, n_pad), "reflect")
+        t += n_pad
+    x = x.view(b, c, t // period, period)
+    outs = []
+    for i in range(n_layers):
+        x = F.conv2d(x, w[f"{prefix}.convs.{i}.0.weight"], w.get(f"{prefix}.convs.{i}.0.bias"), stride=(strides[i], 1), padding=((k0 - 1) // 2, 0))
+        x = F.leaky_relu(x, slope)
+        outs.append(x)
+    x = F.conv2d(x, w[f"{prefix}.output_conv.weight"], w.get(f"{prefix}.output_conv.bias"), padding=((k1 - 1) // 2, 0))
+    outs.append(torch.flatten(x, 1, -1))
+    return outs
+
+
+def hifigan_scale_discriminator(w, prefix, x, strides=(2, 2, 4, 4, 1), groups=(4, 16, 16, 16, 16), ks=(15, 41, 5, 3), slope=0.1):
+    """HiFiGANScaleDiscriminator.forward (hifigan.py:586-601)."""
+    outs = []
+    x = F.leaky_relu(F.conv1d(x, w[f"{prefix}.layers.0.0.weight"], w.get(f"{prefix}.layers.0.0.bias"), padding=(ks[0] - 1) // 2), slope)
+    outs.append(x)
+    for i, (s, g) in enumerate(zip(strides, groups)):
+        p = f"{prefix}.layers.{i + 1}.0"
+        x = F.leaky_relu(F.conv1d(x, w[p + ".weight"], w.get(p + ".bias"), stride=s, padding=(ks[1] - 1) // 2, groups=g), slope)
+        outs.append(x)
+    n = len(strides)
+    p = f"{prefix}.layers.{n + 1}.0"
+    x = F.leaky_relu(F.conv1d(x, w[p + ".weight"], w.get(p + ".bias"), padding=(ks[2] - 1) // 2), slope)
+    outs.append(x)
+    p = f"{prefix}.layers.{n + 2}"
+    x = F.conv1d(x, w[p + ".weight"], w.get(p + ".bias"), padding=(ks[3] - 1) // 2)
+    outs.append(x)
+    return outs
+
+
+def hifigan_msmpd(w, x, scales=3, periods=(2, 3, 5, 7, 11)):
+    """HiFiGANMultiScaleMultiPeriodDiscriminator.forward (hifigan.py:850-864), v1 config:
+    AvgPool1d(4, 2, padding=2) between scales (hifigan.py:758-775)."""
+    outs = []
+    xs = x
+    for i in range(scales):
+        outs.append(hifigan_scale_discriminator(w, f"msd.discriminators.{i}", xs))
+        xs = F.avg_pool1d(xs, 4, 2, padding=2)
+    for i, p in enumerate(periods):
+        outs.append(hifigan_period_discriminator(w, f"mpd.discriminators.{i}", x, p))
+    return outs
+
+
+def melgan_discriminator(w, prefix, x, downsample_scales=(4, 4, 4, 4), kernel_sizes=(5, 3), channels=16, max_ch=1024, slope=0.2):
+    """MelGANDiscriminator.forward (melgan.py:364-379)."""
+    outs = []
+    k0 = kernel_sizes[0] * kernel_sizes[1]
+    x = F.leaky_relu(F.conv1d(F.pad(x, ((k0 - 1) // 2,) * 2, mode="reflect"), w[f"{prefix}.layers.0.1.weight"], w.get(f"{prefix}.layers.0.1.bias")), slope)
+    outs.append(x)
+    in_chs = channels
+    for i, s in enumerate(downsample_scales):
+        p = f"{prefix}.layers.{i + 1}.0"
+        x = F.leaky_relu(F.conv1d(x, w[p + ".weight"], w.get(p + ".bias"), stride=s, padding=s * 5, groups=in_chs // 4), slope)
+        outs.append(x)
+        in_chs = min(in_chs * s, max_ch)
+    n = len(downsample_scales)
+    p = f"{prefix}.layers.{n + 1}.0"
+    x = F.leaky_relu(F.conv1d(x, w[p + ".weight"], w.get(p + ".bias"), padding=(kernel_sizes[0] - 1) // 2), slope)
+    outs.append(x)
+    p = f"{prefix}.layers.{n + 2}"
+    x = F.conv1d(x, w[p + ".weight"], w.get(p + ".bias"), padding=(kernel_sizes[1] - 1) // 2)
+    outs.append(x)
+    return outs
+
+
+def melgan_msd(w, x, scales=3, **kw):
+    """MelGANMultiScaleDiscriminator.forward (melgan.py:478-493): AvgPool1d(4,2,1,count_include_pad=False)."""
+    outs = []
+    for i in range(scales):
+        outs.append(melgan_discriminator(w, f"discriminators.{i}", x, **kw))
+        x = F.avg_pool1d(x, 4, 2, padding=1, count_include_pad=False)
+    return outs
+
+
+def pwg_discriminator(w, x, layers=10, kernel_size=3, slope=0.2):
+    """ParallelWaveGANDiscriminator.forward (parallel_wavegan.py:337-349): dilation i for layer i>0."""
+    for i in range(layers - 1):
+        d = 1 if i == 0 else i
+        p = f"conv_layers.{2 * i}"
+        x = F.leaky_relu(F.conv1d(x, w[p + ".weight"], w.get(p + ".bias"), dilation=d, padding=(kernel_size - 1) // 2 * d), slope)
+    p = f"conv_layers.{2 * (layers - 1)}"
+    return F.conv1d(x, w[p + ".weight"], w.get(p + ".bias"), padding=(kernel_size - 1) // 2)
+
+
+def fold_spectral_norm_eval(sd):
+    """Eval-mode spectral norm (no power iteration): w = w_orig / (u . (W v)); keys X.weight_orig,
+    X.weight_u, X.weight_v -> X.weight."""
+    out = {}
+    for k, v in sd.items():
+        if k.endswith(".weight_orig"):
+            base = k[: -len("_orig")]
+            wm = v.reshape(v.shape[0], -1)
+            sigma = torch.dot(sd[base + "_u"], torch.mv(wm, sd[base + "_v"]))
+            out[base] = v / sigma
+        elif k.endswith(".weight_u") or (k.endswith(".weight_v") and (k[: -len("_v")] + "_orig") in sd):
+            continue
+        else:
+            out[k] = v
+    return out
+
+
+# --------------------------------------------------------------------------
+# GAN losses (losses/adversarial_loss.py, losses/feat_match_loss.py), default flags
+# --------------------------------------------------------------------------
+
+
+def generator_adv_loss(outputs, loss_type="mse", average=True):
+    tot = 0.0
+    for i, o in enumerate(outputs):
+        o = o[-1] if isinstance(o, (list, tuple)) else o
+        tot = tot + (F.mse_loss(o, torch.ones_like(o)) if loss_type == "mse" else -o.mean())
+    return tot / (i + 1) if average else tot
+
+
+def discriminator_adv_loss(outputs_hat, outputs, loss_type="mse", average=True):
+    real = fake = 0.0
+    for i, (oh, o) in enumerate(zip(outputs_hat, outputs)):
+        oh = oh[-1] if isinstance(oh, (list, tuple)) else oh
+        o = o[-1] if isinstance(o, (list, tuple)) else o
+        if loss_type == "mse":
+            real = real + F.mse_loss(o, torch.ones_like(o))
+            fake = fake + F.mse_loss(oh, torch.zeros_like(oh))
+        else:
+            real = real - torch.mean(torch.min(o - 1, torch.zeros_like(o)))
+            fake = fake - torch.mean(torch.min(-oh - 1, torch.zeros_like(oh)))
+    return (real / (i + 1), fake / (i + 1)) if average else (real, fake)
+
+
+def feature_match_loss(feats_hat, feats, average_by_layers=True, average_by_discriminators=True, include_final_outputs=False):
+    tot = 0.0
+    for i, (fh, f) in enumerate(zip(feats_hat, feats)):
+        if not include_final_outputs:
+            fh, f = fh[:-1], f[:-1]
+        li = 0.0
+        for j, (a, b) in enumerate(zip(fh, f)):
+            li = li + F.l1_loss(a, b)
+        if average_by_layers:
+            li = li / (j + 1)
+        tot = tot + li
+    return tot / (i + 1) if average_by_discriminators else tot

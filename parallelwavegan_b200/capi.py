@@ -39,6 +39,11 @@ class WaveNetDesc(C.Structure):
     ]
 
 
+class StftDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("t", C.c_int32), ("n_fft", C.c_int32), ("hop", C.c_int32),
+                ("win_length", C.c_int32), ("clamp_eps", C.c_float)]
+
+
 _lib = None
 
 
@@ -85,6 +90,18 @@ def lib():
     L.pwgb_wavenet_layer_forward.argtypes = [C.POINTER(WaveNetDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pwgb_upsample_fir_forward.restype = C.c_int
     L.pwgb_upsample_fir_forward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_longlong, vp]
+    L.pwgb_mr_stft_loss_workspace.restype = C.c_size_t
+    L.pwgb_mr_stft_loss_workspace.argtypes = [C.POINTER(StftDesc), C.c_int]
+    L.pwgb_mr_stft_loss_forward.restype = C.c_int
+    L.pwgb_mr_stft_loss_forward.argtypes = [C.POINTER(StftDesc), C.c_int, vp, vp, C.POINTER(vp), vp, vp, C.c_size_t, vp]
+    L.pwgb_stft_amplitude_forward.restype = C.c_int
+    L.pwgb_stft_amplitude_forward.argtypes = [C.POINTER(StftDesc), vp, vp, vp, vp, vp, vp]
+    L.pwgb_mel_project_forward.restype = C.c_int
+    L.pwgb_mel_project_forward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp]
+    L.pwgb_reduce_mean_forward.restype = C.c_int
+    L.pwgb_reduce_mean_forward.argtypes = [C.c_int, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, C.c_int, vp]
+    L.pwgb_avg_pool1d_forward.restype = C.c_int
+    L.pwgb_avg_pool1d_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     _lib = L
     return L
 
@@ -109,4 +126,6 @@ EXPORTED_SYMBOLS = [
     "pwgb_conv1d_tc_packed_weight_bytes", "pwgb_conv1d_tc_pack_weight", "pwgb_conv1d_tc_supported",
     "pwgb_conv1d_tc_forward", "pwgb_debug_set", "pwgb_wavenet_supported", "pwgb_wavenet_packed_bytes",
     "pwgb_wavenet_pack", "pwgb_wavenet_layer_forward", "pwgb_upsample_fir_forward",
+    "pwgb_mr_stft_loss_workspace", "pwgb_mr_stft_loss_forward", "pwgb_stft_amplitude_forward",
+    "pwgb_mel_project_forward", "pwgb_reduce_mean_forward", "pwgb_avg_pool1d_forward",
 ]

@@ -29,13 +29,13 @@ def effective_weight(m):
     if hasattr(m, "weight_orig"):
         w = m.weight_orig
         w_mat = w.reshape(w.shape[0], -1)
-        u, v = m.weight_u, m.weight_v
         if m.training:
             with torch.no_grad():
-                v = torch.nn.functional.normalize(torch.mv(w_mat.t(), u), dim=0, eps=1e-12, out=v)
-                u = torch.nn.functional.normalize(torch.mv(w_mat, v), dim=0, eps=1e-12, out=u)
-                u = u.clone(memory_format=torch.contiguous_format)
-                v = v.clone(memory_format=torch.contiguous_format)
+                v = torch.nn.functional.normalize(torch.mv(w_mat.t(), m.weight_u), dim=0, eps=1e-12)
+                u = torch.nn.functional.normalize(torch.mv(w_mat, v), dim=0, eps=1e-12)
+                m.weight_v.copy_(v)
+                m.weight_u.copy_(u)
+        u, v = m.weight_u.clone(), m.weight_v.clone()
         sigma = torch.dot(u, torch.mv(w_mat, v))
         return w / sigma
     return m.weight

@@ -412,3 +412,432 @@ class ParallelWaveGANGenerator(_GeneratorBase):
             idx = torch.arange(-w, c.shape[-1] + w, device=c.device).clamp_(0, c.shape[-1] - 1)
             c = c[:, :, idx].contiguous()
         return self.forward(x, c).squeeze(0).transpose(1, 0)
+
+
+# ==========================================================================
+# Discriminators (forward: every layer is one fused conv launch -- bias, LeakyReLU and the
+# padding policy live inside the kernel; feature maps are written exactly once)
+# ==========================================================================
+import copy  # noqa: E402
+
+
+class _NormMixin:
+    def remove_weight_norm(self):
+        def _remove_weight_norm(m):
+            try:
+                torch.nn.utils.remove_weight_norm(m)
+            except ValueError:
+                return
+
+        self.apply(_remove_weight_norm)
+
+    def remove_spectral_norm(self):
+        def _remove_spectral_norm(m):
+            try:
+                torch.nn.utils.remove_spectral_norm(m)
+            except ValueError:
+                return
+
+        self.apply(_remove_spectral_norm)
+
+
+class ParallelWaveGANDiscriminator(torch.nn.Module, _NormMixin):
+    """models/parallel_wavegan.py:264-371."""
+
+    def __init__(self, in_channels=1, out_channels=1, kernel_size=3, layers=10, conv_channels=64, dilation_factor=1,
+                 nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.2}, bias=True,
+                 use_weight_norm=True):
+        super().__init__()
+        from . import layers as L
+
+        assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
+        assert dilation_factor > 0, "Dilation factor must be > 0."
+        self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
+        self.conv_layers = torch.nn.ModuleList()
+        conv_in_channels = in_channels
+        for i in range(layers - 1):
+            if i == 0:
+                dilation = 1
+            else:
+                dilation = i if dilation_factor == 1 else dilation_factor**i
+                conv_in_channels = conv_channels
+            padding = (kernel_size - 1) // 2 * dilation
+            self.conv_layers += [
+                L.Conv1d(conv_in_channels, conv_channels, kernel_size=kernel_size, padding=padding, dilation=dilation, bias=bias),
+                getattr(torch.nn, nonlinear_activation)(inplace=True, **nonlinear_activation_params),
+            ]
+        self.conv_layers += [L.Conv1d(conv_in_channels, out_channels, kernel_size=kernel_size, padding=(kernel_size - 1) // 2, bias=bias)]
+        if use_weight_norm:
+            self.apply_weight_norm()
+
+    def forward(self, x):
+        """(B, 1, T) -> (B, 1, T)."""
+        mods = list(self.conv_layers)
+        for i, m in enumerate(mods):
+            if isinstance(m, torch.nn.Conv1d):
+                act = i + 1 < len(mods) and not isinstance(mods[i + 1], torch.nn.Conv1d)
+                x = ops.conv1d(x, effective_weight(m), m.bias, padding=m.padding[0], dilation=m.dilation[0],
+                               post_act="lrelu" if act else None, post_slope=self.slope)
+        return x
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d)):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+
+class HiFiGANPeriodDiscriminator(torch.nn.Module, _NormMixin):
+    """models/hifigan.py:270-401.  The (B, C, T/P, P) Conv2d (k,1) stack runs as period-strided 1-D
+    convs directly on the flat waveform: the reflect extension to a multiple of P and the view are
+    index arithmetic inside the kernel's tile loader (no padded copy)."""
+
+    def __init__(self, in_channels=1, out_channels=1, period=3, kernel_sizes=[5, 3], channels=32,
+                 downsample_scales=[3, 3, 3, 3, 1], max_downsample_channels=1024, bias=True,
+                 nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
+                 use_weight_norm=True, use_spectral_norm=False):
+        super().__init__()
+        assert len(kernel_sizes) == 2
+        assert kernel_sizes[0] % 2 == 1, "Kernel size must be odd number."
+        assert kernel_sizes[1] % 2 == 1, "Kernel size must be odd number."
+        self.period = period
+        self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
+        self.convs = torch.nn.ModuleList()
+        in_chs, out_chs = in_channels, channels
+        for downsample_scale in downsample_scales:
+            self.convs += [
+                torch.nn.Sequential(
+                    torch.nn.Conv2d(in_chs, out_chs, (kernel_sizes[0], 1), (downsample_scale, 1), padding=((kernel_sizes[0] - 1) // 2, 0)),
+                    getattr(torch.nn, nonlinear_activation)(**nonlinear_activation_params),
+                )
+            ]
+            in_chs = out_chs
+            out_chs = min(out_chs * 4, max_downsample_channels)
+        self.output_conv = torch.nn.Conv2d(out_chs, out_channels, (kernel_sizes[1] - 1, 1), 1, padding=((kernel_sizes[1] - 1) // 2, 0))
+        if use_weight_norm and use_spectral_norm:
+            raise ValueError("Either use use_weight_norm or use_spectral_norm.")
+        if use_weight_norm:
+            self.apply_weight_norm()
+        if use_spectral_norm:
+            self.apply_spectral_norm()
+
+    def forward(self, x):
+        """(B, in_channels, T) -> list of per-layer outputs (4-D) + flattened logits."""
+        outs = []
+        for layer in self.convs:
+            m = layer[0]
+            x = ops.conv1d(x, effective_weight(m), m.bias, stride=m.stride[0], padding=m.padding[0], period=self.period,
+                           post_act="lrelu", post_slope=self.slope)
+            outs += [x]
+        m = self.output_conv
+        x = ops.conv1d(x, effective_weight(m), m.bias, stride=1, padding=m.padding[0], period=self.period)
+        outs += [torch.flatten(x, 1, -1)]
+        return outs
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, torch.nn.Conv2d):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+    def apply_spectral_norm(self):
+        def _apply_spectral_norm(m):
+            if isinstance(m, torch.nn.Conv2d):
+                torch.nn.utils.spectral_norm(m)
+
+        self.apply(_apply_spectral_norm)
+
+
+class HiFiGANMultiPeriodDiscriminator(torch.nn.Module):
+    """models/hifigan.py:404-453."""
+
+    def __init__(self, periods=[2, 3, 5, 7, 11], discriminator_params={
+        "in_channels": 1, "out_channels": 1, "kernel_sizes": [5, 3], "channels": 32,
+        "downsample_scales": [3, 3, 3, 3, 1], "max_downsample_channels": 1024, "bias": True,
+        "nonlinear_activation": "LeakyReLU", "nonlinear_activation_params": {"negative_slope": 0.1},
+        "use_weight_norm": True, "use_spectral_norm": False,
+    }):
+        super().__init__()
+        self.discriminators = torch.nn.ModuleList()
+        for period in periods:
+            params = copy.deepcopy(discriminator_params)
+            params["period"] = period
+            self.discriminators += [HiFiGANPeriodDiscriminator(**params)]
+
+    def forward(self, x):
+        return [f(x) for f in self.discriminators]
+
+
+class HiFiGANScaleDiscriminator(torch.nn.Module, _NormMixin):
+    """models/hifigan.py:456-702 (including the load pre-hook that strips wn / sn when the
+    checkpoint was trained without them, hifigan.py:647-702)."""
+
+    def __init__(self, in_channels=1, out_channels=1, kernel_sizes=[15, 41, 5, 3], channels=128,
+                 max_downsample_channels=1024, max_groups=16, bias=True, downsample_scales=[2, 2, 4, 4, 1],
+                 nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
+                 use_weight_norm=True, use_spectral_norm=False):
+        super().__init__()
+        self.layers = torch.nn.ModuleList()
+        assert len(kernel_sizes) == 4
+        for ks in kernel_sizes:
+            assert ks % 2 == 1
+        self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
+        act = getattr(torch.nn, nonlinear_activation)
+        self.layers += [
+            torch.nn.Sequential(
+                torch.nn.Conv1d(in_channels, channels, kernel_sizes[0], bias=bias, padding=(kernel_sizes[0] - 1) // 2),
+                act(**nonlinear_activation_params),
+            )
+        ]
+        in_chs = channels
+        out_chs = channels
+        groups = 4
+        for downsample_scale in downsample_scales:
+            self.layers += [
+                torch.nn.Sequential(
+                    torch.nn.Conv1d(in_chs, out_chs, kernel_size=kernel_sizes[1], stride=downsample_scale,
+                                    padding=(kernel_sizes[1] - 1) // 2, groups=groups, bias=bias),
+                    act(**nonlinear_activation_params),
+                )
+            ]
+            in_chs = out_chs
+            out_chs = min(in_chs * 2, max_downsample_channels)
+            groups = min(groups * 4, max_groups)
+        out_chs = min(in_chs * 2, max_downsample_channels)
+        self.layers += [
+            torch.nn.Sequential(
+                torch.nn.Conv1d(in_chs, out_chs, kernel_size=kernel_sizes[2], stride=1, padding=(kernel_sizes[2] - 1) // 2, bias=bias),
+                act(**nonlinear_activation_params),
+            )
+        ]
+        self.layers += [torch.nn.Conv1d(out_chs, out_channels, kernel_size=kernel_sizes[3], stride=1, padding=(kernel_sizes[3] - 1) // 2, bias=bias)]
+        if use_weight_norm and use_spectral_norm:
+            raise ValueError("Either use use_weight_norm or use_spectral_norm.")
+        self.use_weight_norm = use_weight_norm
+        if use_weight_norm:
+            self.apply_weight_norm()
+        self.use_spectral_norm = use_spectral_norm
+        if use_spectral_norm:
+            self.apply_spectral_norm()
+        self._register_load_state_dict_pre_hook(self._load_state_dict_pre_hook)
+
+    def forward(self, x):
+        """(B, 1, T) -> list of the outputs of every layer."""
+        outs = []
+        for f in self.layers:
+            m, act = (f[0], True) if isinstance(f, torch.nn.Sequential) else (f, False)
+            x = ops.conv1d(x, effective_weight(m), m.bias, stride=m.stride[0], padding=m.padding[0], groups=m.groups,
+                           post_act="lrelu" if act else None, post_slope=self.slope)
+            outs += [x]
+        return outs
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, torch.nn.Conv1d):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+    def apply_spectral_norm(self):
+        def _apply_spectral_norm(m):
+            if isinstance(m, torch.nn.Conv1d):
+                torch.nn.utils.spectral_norm(m)
+
+        self.apply(_apply_spectral_norm)
+
+    def _load_state_dict_pre_hook(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        current_module_keys = [x for x in state_dict.keys() if x.startswith(prefix)]
+        if self.use_weight_norm and not any(["weight_g" in k for k in current_module_keys]):
+            logging.warning("weight norm is not applied in the pretrained model but the current model uses it: removing it (hifigan.py:665-683)")
+            self.remove_weight_norm()
+            self.use_weight_norm = False
+        if self.use_spectral_norm and not any(["weight_u" in k for k in current_module_keys]):
+            logging.warning("spectral norm is not applied in the pretrained model but the current model uses it: removing it (hifigan.py:685-702)")
+            self.remove_spectral_norm()
+            self.use_spectral_norm = False
+
+
+class HiFiGANMultiScaleDiscriminator(torch.nn.Module):
+    """models/hifigan.py:705-777."""
+
+    def __init__(self, scales=3, downsample_pooling="AvgPool1d",
+                 downsample_pooling_params={"kernel_size": 4, "stride": 2, "padding": 2},
+                 discriminator_params={
+                     "in_channels": 1, "out_channels": 1, "kernel_sizes": [15, 41, 5, 3], "channels": 128,
+                     "max_downsample_channels": 1024, "max_groups": 16, "bias": True,
+                     "downsample_scales": [2, 2, 4, 4, 1], "nonlinear_activation": "LeakyReLU",
+                     "nonlinear_activation_params": {"negative_slope": 0.1},
+                 }, follow_official_norm=False):
+        super().__init__()
+        if downsample_pooling != "AvgPool1d":
+            raise PwgbError(f"downsample_pooling={downsample_pooling!r} has no sm_100a kernel (AvgPool1d only)")
+        self.discriminators = torch.nn.ModuleList()
+        for i in range(scales):
+            params = copy.deepcopy(discriminator_params)
+            if follow_official_norm:
+                params["use_weight_norm"] = i != 0
+                params["use_spectral_norm"] = i == 0
+            self.discriminators += [HiFiGANScaleDiscriminator(**params)]
+        self.pooling = torch.nn.AvgPool1d(**downsample_pooling_params)  # parameter container
+
+    def _pool(self, x):
+        p = self.pooling
+        k = p.kernel_size[0] if isinstance(p.kernel_size, tuple) else p.kernel_size
+        s = p.stride[0] if isinstance(p.stride, tuple) else p.stride
+        pad = p.padding[0] if isinstance(p.padding, tuple) else p.padding
+        return ops.avg_pool1d(x, k, s, pad, p.count_include_pad)
+
+    def forward(self, x):
+        outs = []
+        for i, f in enumerate(self.discriminators):
+            outs += [f(x)]
+            if i + 1 < len(self.discriminators):
+                x = self._pool(x)
+        return outs
+
+
+class HiFiGANMultiScaleMultiPeriodDiscriminator(torch.nn.Module):
+    """models/hifigan.py:780-864."""
+
+    def __init__(self, scales=3, scale_downsample_pooling="AvgPool1d",
+                 scale_downsample_pooling_params={"kernel_size": 4, "stride": 2, "padding": 2},
+                 scale_discriminator_params={
+                     "in_channels": 1, "out_channels": 1, "kernel_sizes": [15, 41, 5, 3], "channels": 128,
+                     "max_downsample_channels": 1024, "max_groups": 16, "bias": True,
+                     "downsample_scales": [2, 2, 4, 4, 1], "nonlinear_activation": "LeakyReLU",
+                     "nonlinear_activation_params": {"negative_slope": 0.1},
+                 }, follow_official_norm=True, periods=[2, 3, 5, 7, 11],
+                 period_discriminator_params={
+                     "in_channels": 1, "out_channels": 1, "kernel_sizes": [5, 3], "channels": 32,
+                     "downsample_scales": [3, 3, 3, 3, 1], "max_downsample_channels": 1024, "bias": True,
+                     "nonlinear_activation": "LeakyReLU", "nonlinear_activation_params": {"negative_slope": 0.1},
+                     "use_weight_norm": True, "use_spectral_norm": False,
+                 }):
+        super().__init__()
+        self.msd = HiFiGANMultiScaleDiscriminator(scales=scales, downsample_pooling=scale_downsample_pooling,
+                                                  downsample_pooling_params=scale_downsample_pooling_params,
+                                                  discriminator_params=scale_discriminator_params,
+                                                  follow_official_norm=follow_official_norm)
+        self.mpd = HiFiGANMultiPeriodDiscriminator(periods=periods, discriminator_params=period_discriminator_params)
+
+    def forward(self, x):
+        """Multi-scale outputs followed by multi-period outputs (hifigan.py:850-864)."""
+        return self.msd(x) + self.mpd(x)
+
+
+class MelGANDiscriminator(torch.nn.Module):
+    """models/melgan.py:260-396."""
+
+    def __init__(self, in_channels=1, out_channels=1, kernel_sizes=[5, 3], channels=16, max_downsample_channels=1024,
+                 bias=True, downsample_scales=[4, 4, 4, 4], nonlinear_activation="LeakyReLU",
+                 nonlinear_activation_params={"negative_slope": 0.2}, pad="ReflectionPad1d", pad_params={}):
+        super().__init__()
+        self.layers = torch.nn.ModuleList()
+        assert len(kernel_sizes) == 2
+        assert kernel_sizes[0] % 2 == 1
+        assert kernel_sizes[1] % 2 == 1
+        self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
+        self.pad_mode = pad_mode_of(pad, pad_params)
+        act = getattr(torch.nn, nonlinear_activation)
+        k0 = int(np.prod(kernel_sizes))
+        self.layers += [
+            torch.nn.Sequential(
+                getattr(torch.nn, pad)((k0 - 1) // 2, **pad_params),
+                torch.nn.Conv1d(in_channels, channels, k0, bias=bias),
+                act(**nonlinear_activation_params),
+            )
+        ]
+        in_chs = channels
+        for downsample_scale in downsample_scales:
+            out_chs = min(in_chs * downsample_scale, max_downsample_channels)
+            self.layers += [
+                torch.nn.Sequential(
+                    torch.nn.Conv1d(in_chs, out_chs, kernel_size=downsample_scale * 10 + 1, stride=downsample_scale,
+                                    padding=downsample_scale * 5, groups=in_chs // 4, bias=bias),
+                    act(**nonlinear_activation_params),
+                )
+            ]
+            in_chs = out_chs
+        out_chs = min(in_chs * 2, max_downsample_channels)
+        self.layers += [
+            torch.nn.Sequential(
+                torch.nn.Conv1d(in_chs, out_chs, kernel_sizes[0], padding=(kernel_sizes[0] - 1) // 2, bias=bias),
+                act(**nonlinear_activation_params),
+            )
+        ]
+        self.layers += [torch.nn.Conv1d(out_chs, out_channels, kernel_sizes[1], padding=(kernel_sizes[1] - 1) // 2, bias=bias)]
+        self.reset_parameters()
+
+    def forward(self, x):
+        outs = []
+        for i, f in enumerate(self.layers):
+            if isinstance(f, torch.nn.Sequential):
+                m = [q for q in f if isinstance(q, torch.nn.Conv1d)][0]
+                first = i == 0
+                x = ops.conv1d(x, effective_weight(m), m.bias, stride=m.stride[0],
+                               padding=(m.kernel_size[0] - 1) // 2 if first else m.padding[0],
+                               pad_mode=self.pad_mode if first else "zero", groups=m.groups,
+                               post_act="lrelu", post_slope=self.slope)
+            else:
+                x = ops.conv1d(x, effective_weight(f), f.bias, padding=f.padding[0])
+            outs += [x]
+        return outs
+
+    def reset_parameters(self):
+        def _reset_parameters(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                m.weight.data.normal_(0.0, 0.02)
+
+        self.apply(_reset_parameters)
+
+
+class MelGANMultiScaleDiscriminator(torch.nn.Module, _NormMixin):
+    """models/melgan.py:399-534."""
+
+    def __init__(self, in_channels=1, out_channels=1, scales=3, downsample_pooling="AvgPool1d",
+                 downsample_pooling_params={"kernel_size": 4, "stride": 2, "padding": 1, "count_include_pad": False},
+                 kernel_sizes=[5, 3], channels=16, max_downsample_channels=1024, bias=True,
+                 downsample_scales=[4, 4, 4, 4], nonlinear_activation="LeakyReLU",
+                 nonlinear_activation_params={"negative_slope": 0.2}, pad="ReflectionPad1d", pad_params={},
+                 use_weight_norm=True):
+        super().__init__()
+        if downsample_pooling != "AvgPool1d":
+            raise PwgbError(f"downsample_pooling={downsample_pooling!r} has no sm_100a kernel (AvgPool1d only)")
+        self.discriminators = torch.nn.ModuleList()
+        for _ in range(scales):
+            self.discriminators += [
+                MelGANDiscriminator(in_channels=in_channels, out_channels=out_channels, kernel_sizes=kernel_sizes,
+                                    channels=channels, max_downsample_channels=max_downsample_channels, bias=bias,
+                                    downsample_scales=downsample_scales, nonlinear_activation=nonlinear_activation,
+                                    nonlinear_activation_params=nonlinear_activation_params, pad=pad, pad_params=pad_params)
+            ]
+        self.pooling = torch.nn.AvgPool1d(**downsample_pooling_params)
+        if use_weight_norm:
+            self.apply_weight_norm()
+        self.reset_parameters()
+
+    _pool = HiFiGANMultiScaleDiscriminator._pool
+
+    def forward(self, x):
+        outs = []
+        for i, f in enumerate(self.discriminators):
+            outs += [f(x)]
+            if i + 1 < len(self.discriminators):
+                x = self._pool(x)
+        return outs
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+    def reset_parameters(self):
+        def _reset_parameters(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                m.weight.data.normal_(0.0, 0.02)
+
+        self.apply(_reset_parameters)

@@ -262,3 +262,97 @@ def wavenet_layer(x, c, w_conv, b_conv, w_aux, w_skip, b_skip, w_out, b_out, dil
         conv1d(c, wa, None, out=g, accumulate=True)
     conv1d(g, w_skip, b_skip, pre_gate=True, out=skips, accumulate=True)
     return conv1d(g, w_out, b_out, pre_gate=True, residual=x, out_scale=0.7071067811865476)
+
+
+def mr_stft_loss(x, y, fft_sizes, hop_sizes, win_lengths, windows, eps=1e-7):
+    """MultiResolutionSTFTLoss.forward (losses/stft_loss.py:146-170) -> device tensor [sc, mag].
+    x, y: (B, T) or (B, C, T); windows: list of device tensors (win_length,)."""
+    x = _dev(x, "x")
+    y = _dev(y, "y")
+    if x.dim() == 3:
+        x = x.reshape(-1, x.shape[2])
+        y = y.reshape(-1, y.shape[2])
+    if x.shape != y.shape:
+        raise PwgbError("mr_stft_loss: x and y must have the same shape")
+    B, T = x.shape
+    n = len(fft_sizes)
+    descs = (capi.StftDesc * n)(*[capi.StftDesc(batch=B, t=T, n_fft=int(f), hop=int(h), win_length=int(w), clamp_eps=float(eps))
+                                  for f, h, w in zip(fft_sizes, hop_sizes, win_lengths)])
+    wins = [_dev(w, "window") for w in windows]
+    wptr = (C.c_void_p * n)(*[w.data_ptr() for w in wins])
+    L = capi.lib()
+    nbytes = L.pwgb_mr_stft_loss_workspace(descs, n)
+    if nbytes == 0:
+        raise PwgbError("mr_stft_loss: unsupported STFT configuration (n_fft must be a power of two <= 4096 and T > n_fft/2)")
+    ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
+    out = torch.empty(2, device=x.device, dtype=torch.float32)
+    prof = _Prof("mr_stft_loss", 0.0, 8.0 * B * T, f"B{B} T{T} res{n}")
+    rc = L.pwgb_mr_stft_loss_forward(descs, n, _p(x), _p(y), wptr, _p(out), _p(ws), C.c_size_t(nbytes), _stream())
+    capi.check(rc, "pwgb_mr_stft_loss_forward")
+    prof.done()
+    return out
+
+
+def stft_amplitude(x, y, n_fft, hop, win_length, window, eps):
+    """sqrt(clamp(|STFT|^2, eps)) as (B, frames, bins) for x and (optionally) y."""
+    x = _dev(x, "x")
+    B, T = x.shape
+    d = capi.StftDesc(batch=B, t=T, n_fft=int(n_fft), hop=int(hop), win_length=int(win_length), clamp_eps=float(eps))
+    frames, bins = 1 + T // hop, n_fft // 2 + 1
+    ax = torch.empty((B, frames, bins), device=x.device, dtype=torch.float32)
+    ay = None
+    if y is not None:
+        y = _dev(y, "y")
+        ay = torch.empty_like(ax)
+    rc = capi.lib().pwgb_stft_amplitude_forward(C.byref(d), _p(x), _p(y), _p(_dev(window, "window")), _p(ax), _p(ay), _stream())
+    capi.check(rc, "pwgb_stft_amplitude_forward")
+    return ax, ay
+
+
+def mel_project(ax, ay, melmat, eps, log_scale, want_mel=True, want_loss=False):
+    """clamp(amp @ melmat, eps) -> log * log_scale; returns (log-mel of x as (B, n_mels, frames) or None,
+    mean-L1 loss between the two log-mels as a 1-element tensor or None)."""
+    B, frames, bins = ax.shape
+    melmat = _dev(melmat, "melmat")
+    n_mels = melmat.shape[1]
+    mel = torch.empty((B, n_mels, frames), device=ax.device, dtype=torch.float32) if want_mel else None
+    loss = ws = None
+    if want_loss:
+        loss = torch.empty(1, device=ax.device, dtype=torch.float32)
+        ws = torch.empty(B * frames, device=ax.device, dtype=torch.float32)
+    rc = capi.lib().pwgb_mel_project_forward(B, frames, bins, n_mels, _p(ax), _p(ay), _p(melmat), float(eps), float(log_scale),
+                                             _p(mel), _p(loss), _p(ws), _stream())
+    capi.check(rc, "pwgb_mel_project_forward")
+    return mel, loss
+
+
+_REDUCE = {"mse_const": 0, "l1": 1, "hinge": 2, "linear": 3}
+
+
+def reduce_mean(mode, x, y=None, c=0.0, s=1.0, weight=1.0, out=None, accumulate=False):
+    """out[0] (+)= weight * mean(f(x[, y])) -- pwgb_reduce_mean_forward (deterministic)."""
+    x = _dev(x, "x")
+    if y is not None:
+        y = _dev(y, "y")
+        if y.numel() != x.numel():
+            raise PwgbError("reduce_mean: size mismatch")
+    if out is None:
+        out = torch.zeros(1, device=x.device, dtype=torch.float32)
+        accumulate = False
+    ws = torch.empty(1024, device=x.device, dtype=torch.float32)
+    rc = capi.lib().pwgb_reduce_mean_forward(_REDUCE[mode], _p(x), _p(y), x.numel(), float(c), float(s), float(weight),
+                                             int(bool(accumulate)), _p(out), _p(ws), 1024, _stream())
+    capi.check(rc, "pwgb_reduce_mean_forward")
+    return out
+
+
+def avg_pool1d(x, kernel_size, stride, padding=0, count_include_pad=True):
+    """torch.nn.AvgPool1d semantics on (B, C, T) -- pwgb_avg_pool1d_forward."""
+    x = _dev(x, "x")
+    B, Cc, T = x.shape
+    t_out = (T + 2 * padding - kernel_size) // stride + 1
+    y = torch.empty((B, Cc, t_out), device=x.device, dtype=torch.float32)
+    rc = capi.lib().pwgb_avg_pool1d_forward(_p(x), _p(y), B * Cc, T, int(kernel_size), int(stride), int(padding),
+                                            int(bool(count_include_pad)), _stream())
+    capi.check(rc, "pwgb_avg_pool1d_forward")
+    return y

@@ -46,3 +46,31 @@ def golden_weights(meta):
 
 def golden_effective_weights(meta):
     return fold_weight_norm(golden_weights(meta))
+
+
+def flatten_outs(outs):
+    """(nested) list of feature maps -> [(name, tensor)] with the naming of oracle/make_golden.summarize."""
+    flat = []
+    if isinstance(outs, torch.Tensor):
+        outs = [outs]
+    for i, o in enumerate(outs):
+        if isinstance(o, (list, tuple)):
+            for j, t in enumerate(o):
+                flat.append((f"o{i}_{j}", t))
+        else:
+            flat.append((f"o{i}", o))
+    return flat
+
+
+def check_fingerprint(outs, meta, g, tol):
+    """Compare feature maps with the golden fingerprint (shape, sum / L2 norm in float64, head, tail)."""
+    flat = flatten_outs(outs)
+    assert [(n, list(t.shape)) for n, t in flat] == [(n, list(s)) for n, s in meta["shapes"]]
+    for n, t in flat:
+        t = t.detach().cpu()
+        v = t.reshape(-1).double()
+        ssum, snorm = float(g[n + "_stat"][0]), float(g[n + "_stat"][1])
+        assert abs(float(v.norm()) - snorm) <= tol * snorm, (n, float(v.norm()), snorm)
+        assert abs(float(v.sum()) - ssum) <= tol * max(snorm * v.numel() ** 0.5, 1e-12), (n, float(v.sum()), ssum)
+        assert rel_l2(t.reshape(-1)[:96], g[n + "_head"]) < tol, n
+        assert rel_l2(t.reshape(-1)[-96:], g[n + "_tail"]) < tol, n
