@@ -25,7 +25,7 @@
 namespace pwgb {
 
 constexpr int KC = 32;  // input channels per activation chunk / weight stage (2 UMMA K-steps)
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 constexpr unsigned SPIN_LIMIT = 1u << 22;
 
 struct TcK {
@@ -36,7 +36,7 @@ struct TcK {
   float out_scale;
   int accumulate;
   int shuffle, shuffle_pad, shuffle_tout;
-  int MT, R, nchunks, tiles_per_seq, nb;
+  int MT, R, nchunks, tiles_per_seq, nb, na, nacc, total_tiles;
   long long xbs, ybs, rbs;
   unsigned idesc;
   int tmem_cols;
@@ -175,46 +175,131 @@ static void tc_pack_rows(const float* w, void* packed, int cin_real, int cin_pad
 }
 
 // ------------------------------------------------------------------ main kernel
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// Persistent: one CTA per SM loops over (batch, time-tile) work items; every role runs the same
+// tile sequence and talks through mbarriers only, so the load of tile i+1, the MMAs of tile i and
+// the epilogue of tile i-1 overlap (TMEM holds two accumulator sets when they fit 512 columns).
+
+// stage one activation chunk (KC channels x R rows) into the operand layout
+__device__ __forceinline__ void fill_main_chunk(const TcK& p, const float* __restrict__ xc, int t0, int TT,
+                                                unsigned char* dst, int tid) {
+  auto src_of = [&](int r, bool& ok) -> long long {
+    long long ts;
+    if (p.win_mode) {
+      const int k = r / TT;
+      ts = (long long)t0 - p.padL + (long long)k * p.D + (r - k * TT);
+    } else {
+      ts = (long long)t0 - p.padL + r;
+    }
+    ok = true;
+    if (ts < 0 || ts >= p.T_in) {
+      if (p.pad_mode == PWGB_PAD_ZERO) {
+        ok = false;
+      } else if (p.pad_mode == PWGB_PAD_REFLECT) {
+        ts = ts < 0 ? -ts : 2LL * (p.T_in - 1) - ts;
+        ok = ts >= 0 && ts < p.T_in;
+      } else {
+        ts = ts < 0 ? 0 : p.T_in - 1;
+      }
+    }
+    return ts;
+  };
+  auto store_row = [&](const float (&v)[KC], int r) {
+#pragma unroll
+    for (int g = 0; g < KC / 8; ++g) {
+      float u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = v[g * 8 + j];
+      uint4 hi, lo;
+      split8(u, hi, lo);
+      *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
+      *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
+    }
+  };
+  if (p.pre_gate) {
+    const float* xg = xc + (long long)p.Cin * p.T_in;
+    for (int r = tid; r < p.R; r += 128) {
+      bool ok;
+      const long long ts = src_of(r, ok);
+      float v[KC], sg[KC];
+#pragma unroll
+      for (int j = 0; j < KC; ++j) {
+        v[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
+        sg[j] = ok ? __ldg(xg + (long long)j * p.T_in + ts) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < KC; ++j) v[j] = tanhf(v[j]) * sigmoidf_(sg[j]);
+      store_row(v, r);
+    }
+    return;
+  }
+  // software-pipelined rows: the loads of row r+128 are in flight while row r is converted
+  float cur[KC], nxt[KC];
+  int r = tid;
+  if (r < p.R) {
+    bool ok;
+    const long long ts = src_of(r, ok);
+#pragma unroll
+    for (int j = 0; j < KC; ++j) cur[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
+  }
+  for (; r < p.R; r += 128) {
+    const int rn = r + 128;
+    if (rn < p.R) {
+      bool ok;
+      const long long ts = src_of(rn, ok);
+#pragma unroll
+      for (int j = 0; j < KC; ++j) nxt[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < KC; ++j) cur[j] = lrelu(cur[j], p.pre_slope);
+    store_row(cur, r);
+#pragma unroll
+    for (int j = 0; j < KC; ++j) cur[j] = nxt[j];
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
     conv1d_tc_kernel(const TcK p, const float* __restrict__ x, const float* __restrict__ x2,
                      const uint4* __restrict__ wpk, const float* __restrict__ bias, const float* __restrict__ res,
                      float* __restrict__ y, float* __restrict__ y2) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: A[2] | B[nb] | barriers | tmem ptr
+  // layout: A[na] | B[nb] | barriers | tmem ptr
   unsigned char* a_buf = smem;
-  unsigned char* b_buf = smem + 2 * p.a_bytes;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(b_buf + p.nb * p.b_bytes);
-  // bars: [0,1] A_full, [2,3] A_empty, [4..4+nb) B_full, [4+nb..4+2nb) B_empty, [4+2nb] acc_full
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4 + 2 * p.nb + 1);
+  unsigned char* b_buf = smem + (size_t)p.na * p.a_bytes;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(b_buf + (size_t)p.nb * p.b_bytes);
+  const int nbar = 2 * p.na + 2 * p.nb + 4;
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + nbar);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int b = blockIdx.x / p.tiles_per_seq;
-  const int tile = blockIdx.x - b * p.tiles_per_seq;
   const int TT = p.MT * 128;
-  const int t0 = tile * TT;
+  const int nc_total = p.nchunks + p.nchunks2;
+  const int acc_cols = p.MT * p.Cout;
 
   const unsigned bar0 = smem_u32(bars);
   auto A_FULL = [&](int i) { return bar0 + 8u * i; };
-  auto A_EMPTY = [&](int i) { return bar0 + 8u * (2 + i); };
-  auto B_FULL = [&](int i) { return bar0 + 8u * (4 + i); };
-  auto B_EMPTY = [&](int i) { return bar0 + 8u * (4 + p.nb + i); };
-  const unsigned ACC_FULL = bar0 + 8u * (4 + 2 * p.nb);
+  auto A_EMPTY = [&](int i) { return bar0 + 8u * (p.na + i); };
+  auto B_FULL = [&](int i) { return bar0 + 8u * (2 * p.na + i); };
+  auto B_EMPTY = [&](int i) { return bar0 + 8u * (2 * p.na + p.nb + i); };
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * p.na + 2 * p.nb + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * p.na + 2 * p.nb + 2 + i); };
 
   if (tid == 0) {
-    mbar_init(A_FULL(0), 128);
-    mbar_init(A_FULL(1), 128);
-    mbar_init(A_EMPTY(0), 1);
-    mbar_init(A_EMPTY(1), 1);
+    for (int i = 0; i < p.na; ++i) {
+      mbar_init(A_FULL(i), 128);
+      mbar_init(A_EMPTY(i), 1);
+    }
     for (int i = 0; i < p.nb; ++i) {
       mbar_init(B_FULL(i), 1);
       mbar_init(B_EMPTY(i), 1);
     }
-    mbar_init(ACC_FULL, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(ACC_FULL(i), 1);
+      mbar_init(ACC_EMPTY(i), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((unsigned)p.tmem_cols)
                  : "memory");
@@ -227,167 +312,139 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 
   if (warp < 4) {
     // ===================== A producers =====================
-    const float* xb = x + (long long)b * p.xbs;
-    const int nc_total = p.nchunks + p.nchunks2;
-    for (int c = 0; c < nc_total; ++c) {
-      const int buf = c & 1;
-      mbar_wait(A_EMPTY(buf), ((c >> 1) & 1) ^ 1);
-      unsigned char* dst = a_buf + buf * p.a_bytes;
-      if (c < p.nchunks) {
-        const float* xc = xb + (long long)(c * KC) * p.T_in;
-        for (int r = tid; r < p.R; r += 128) {
-          long long ts;
-          if (p.win_mode) {
-            const int k = r / TT;
-            ts = (long long)t0 - p.padL + (long long)k * p.D + (r - k * TT);
-          } else {
-            ts = (long long)t0 - p.padL + r;
-          }
-          bool ok = true;
-          if (ts < 0 || ts >= p.T_in) {
-            if (p.pad_mode == PWGB_PAD_ZERO) {
-              ok = false;
-            } else if (p.pad_mode == PWGB_PAD_REFLECT) {
-              ts = ts < 0 ? -ts : 2LL * (p.T_in - 1) - ts;
-              ok = ts >= 0 && ts < p.T_in;
-            } else {
-              ts = ts < 0 ? 0 : p.T_in - 1;
-            }
-          }
-          float v[KC];
-#pragma unroll
-          for (int j = 0; j < KC; ++j) v[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
-          if (p.pre_gate) {
-            const float* xg = xc + (long long)p.Cin * p.T_in;
-#pragma unroll
-            for (int j = 0; j < KC; ++j) {
-              const float sg = ok ? __ldg(xg + (long long)j * p.T_in + ts) : 0.f;
-              v[j] = tanhf(v[j]) * sigmoidf_(sg);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < KC; ++j) v[j] = lrelu(v[j], p.pre_slope);
-          }
-#pragma unroll
-          for (int g = 0; g < KC / 8; ++g) {
-            float u[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] = v[g * 8 + j];
-            uint4 hi, lo;
-            split8(u, hi, lo);
-            *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
-            *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
-          }
-        }
-      } else {
-        // auxiliary 1x1 source: TT rows aligned with the output tile, no padding shift, no activation
-        const float* xc = x2 + ((long long)b * p.C2 + (long long)(c - p.nchunks) * KC) * p.T_out;
-        for (int r = tid; r < TT; r += 128) {
-          const long long ts = (long long)t0 + r;
-          const bool ok = ts < p.T_out;
-#pragma unroll
-          for (int g = 0; g < KC / 8; ++g) {
-            float u[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] = ok ? __ldg(xc + (long long)(g * 8 + j) * p.T_out + ts) : 0.f;
-            uint4 hi, lo;
-            split8(u, hi, lo);
-            *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
-            *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
-          }
-        }
-      }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(A_FULL(buf));
-    }
-    // ===================== epilogue =====================
-    mbar_wait(ACC_FULL, 0);
-    tc_fence_after();
-    const int m = warp * 32 + lane;
-    for (int mt = 0; mt < p.MT; ++mt) {
-      const int t = t0 + mt * 128 + m;
-      const bool tv = t < p.T_out;
-      for (int col = 0; col < p.Cout; col += 16) {
-        unsigned r[16];
-        tc_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(mt * p.Cout + col), r);
-        if (p.shuffle > 1) {
-          tc_wait_ld();
-          if (tv) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int co = p.co_off + col + j;
-              const int cof = co / p.shuffle;
-              float v = __uint_as_float(r[j]) + (bias ? __ldg(bias + cof) : 0.f);
-              if (p.post_act == PWGB_ACT_TANH)
-                v = tanhf(v);
-              else if (p.post_act == PWGB_ACT_LRELU)
-                v = lrelu(v, p.post_slope);
-              const int of = t * p.shuffle + (co - cof * p.shuffle) - p.shuffle_pad;
-              if (of >= 0 && of < p.shuffle_tout)
-                y[(long long)b * p.ybs + (long long)cof * p.shuffle_tout + of] = v * p.out_scale;
-            }
-          }
-        } else if (p.wavenet) {
-          // WaveNet split epilogue (residual_block.py:131-138): columns [0, split) are the skip 1x1
-          // (accumulated into y2), columns [split, Cout) the residual 1x1: y = (v + x) * sqrt(0.5)
-          const bool is_skip = col < p.split;
-          const int ch = is_skip ? col : col - p.split;
-          const int nch = is_skip ? p.split : p.Cout - p.split;
-          const long long off = ((long long)b * nch + ch) * p.T_out + t;
-          float rv[16], bv[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            rv[j] = tv ? (is_skip ? y2[off + (long long)j * p.T_out] : __ldg(res + off + (long long)j * p.T_out)) : 0.f;
-            bv[j] = bias ? __ldg(bias + col + j) : 0.f;
-          }
-          tc_wait_ld();
-          if (tv) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float v = __uint_as_float(r[j]) + bv[j];
-              if (is_skip)
-                y2[off + (long long)j * p.T_out] = rv[j] + v;
-              else
-                y[off + (long long)j * p.T_out] = (v + rv[j]) * p.out_scale;
-            }
-          }
+    unsigned ca = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_seq;
+      const int t0 = (tile - b * p.tiles_per_seq) * TT;
+      const float* xb = x + (long long)b * p.xbs;
+      for (int c = 0; c < nc_total; ++c, ++ca) {
+        const int buf = ca % p.na;
+        mbar_wait(A_EMPTY(buf), ((ca / p.na) & 1) ^ 1);
+        unsigned char* dst = a_buf + (size_t)buf * p.a_bytes;
+        if (c < p.nchunks) {
+          fill_main_chunk(p, xb + (long long)(c * KC) * p.T_in, t0, TT, dst, tid);
         } else {
-          // issue every independent global load of this 16-column group before touching the results
-          const long long off = (long long)(p.co_off + col) * p.T_out + t;
-          float rv[16], yv[16], bv[16];
+          // auxiliary 1x1 source: TT rows aligned with the output tile, no padding shift, no activation
+          const float* xc = x2 + ((long long)b * p.C2 + (long long)(c - p.nchunks) * KC) * p.T_out;
+          for (int r = tid; r < TT; r += 128) {
+            const long long ts = (long long)t0 + r;
+            const bool ok = ts < p.T_out;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            rv[j] = (res && tv) ? __ldg(res + (long long)b * p.rbs + off + (long long)j * p.T_out) : 0.f;
-            yv[j] = (p.accumulate && tv) ? y[(long long)b * p.ybs + off + (long long)j * p.T_out] : 0.f;
-            bv[j] = bias ? __ldg(bias + p.co_off + col + j) : 0.f;
+            for (int g = 0; g < KC / 8; ++g) {
+              float u[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) u[j] = ok ? __ldg(xc + (long long)(g * 8 + j) * p.T_out + ts) : 0.f;
+              uint4 hi, lo;
+              split8(u, hi, lo);
+              *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
+              *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
+            }
           }
-          tc_wait_ld();
-          if (tv) {
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(A_FULL(buf));
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = ew * 32 + lane;
+    unsigned it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.tiles_per_seq;
+      const int t0 = (tile - b * p.tiles_per_seq) * TT;
+      const int as = it % p.nacc;
+      mbar_wait(ACC_FULL(as), (it / p.nacc) & 1);
+      tc_fence_after();
+      const unsigned tacc = tmem_base + ((unsigned)(ew * 32) << 16) + (unsigned)(as * acc_cols);
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int t = t0 + mt * 128 + m;
+        const bool tv = t < p.T_out;
+        for (int col = 0; col < p.Cout; col += 16) {
+          unsigned r[16];
+          tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
+          if (p.shuffle > 1) {
+            tc_wait_ld();
+            if (tv) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int co = p.co_off + col + j;
+                const int cof = co / p.shuffle;
+                float v = __uint_as_float(r[j]) + (bias ? __ldg(bias + cof) : 0.f);
+                if (p.post_act == PWGB_ACT_TANH)
+                  v = tanhf(v);
+                else if (p.post_act == PWGB_ACT_LRELU)
+                  v = lrelu(v, p.post_slope);
+                const int of = t * p.shuffle + (co - cof * p.shuffle) - p.shuffle_pad;
+                if (of >= 0 && of < p.shuffle_tout)
+                  y[(long long)b * p.ybs + (long long)cof * p.shuffle_tout + of] = v * p.out_scale;
+              }
+            }
+          } else if (p.wavenet) {
+            // WaveNet split epilogue (residual_block.py:131-138): columns [0, split) are the skip 1x1
+            // (accumulated into y2), columns [split, Cout) the residual 1x1: y = (v + x) * sqrt(0.5)
+            const bool is_skip = col < p.split;
+            const int ch = is_skip ? col : col - p.split;
+            const int nch = is_skip ? p.split : p.Cout - p.split;
+            const long long off = ((long long)b * nch + ch) * p.T_out + t;
+            float rv[16], bv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float v = __uint_as_float(r[j]) + bv[j];
-              if (p.post_act == PWGB_ACT_TANH)
-                v = tanhf(v);
-              else if (p.post_act == PWGB_ACT_LRELU)
-                v = lrelu(v, p.post_slope);
-              y[(long long)b * p.ybs + off + (long long)j * p.T_out] = (v + rv[j]) * p.out_scale + yv[j];
+              rv[j] = tv ? (is_skip ? y2[off + (long long)j * p.T_out] : __ldg(res + off + (long long)j * p.T_out)) : 0.f;
+              bv[j] = bias ? __ldg(bias + col + j) : 0.f;
+            }
+            tc_wait_ld();
+            if (tv) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float v = __uint_as_float(r[j]) + bv[j];
+                if (is_skip)
+                  y2[off + (long long)j * p.T_out] = rv[j] + v;
+                else
+                  y[off + (long long)j * p.T_out] = (v + rv[j]) * p.out_scale;
+              }
+            }
+          } else {
+            // issue every independent global load of this 16-column group before touching the results
+            const long long off = (long long)(p.co_off + col) * p.T_out + t;
+            float rv[16], yv[16], bv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              rv[j] = (res && tv) ? __ldg(res + (long long)b * p.rbs + off + (long long)j * p.T_out) : 0.f;
+              yv[j] = (p.accumulate && tv) ? y[(long long)b * p.ybs + off + (long long)j * p.T_out] : 0.f;
+              bv[j] = bias ? __ldg(bias + p.co_off + col + j) : 0.f;
+            }
+            tc_wait_ld();
+            if (tv) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float v = __uint_as_float(r[j]) + bv[j];
+                if (p.post_act == PWGB_ACT_TANH)
+                  v = tanhf(v);
+                else if (p.post_act == PWGB_ACT_LRELU)
+                  v = lrelu(v, p.post_slope);
+                y[(long long)b * p.ybs + off + (long long)j * p.T_out] = (v + rv[j]) * p.out_scale + yv[j];
+              }
             }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(ACC_EMPTY(as));  // accumulator set drained: the MMA warp may overwrite it
     }
-    tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===================== B producer (TMA bulk copies of packed weight stages) =====================
     if (lane == 0) {
-      const int total = p.nchunks * p.K + p.nchunks2;
+      const int per_tile = p.nchunks * p.K + p.nchunks2;
       const unsigned char* src = reinterpret_cast<const unsigned char*>(wpk);
-      for (int i = 0; i < total; ++i) {
-        const int s = i % p.nb;
-        const int n = i / p.nb;
-        mbar_wait(B_EMPTY(s), (n & 1) ^ 1);
-        mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
-        bulk_g2s(smem_u32(b_buf + s * p.b_bytes), src + (size_t)i * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
+      unsigned i = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int j = 0; j < per_tile; ++j, ++i) {
+          const int s = i % p.nb;
+          mbar_wait(B_EMPTY(s), ((i / p.nb) & 1) ^ 1);
+          mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
+          bulk_g2s(smem_u32(b_buf + (size_t)s * p.b_bytes), src + (size_t)j * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
+        }
       }
     }
   } else {
@@ -395,50 +452,54 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
     if (lane == 0) {
       const unsigned a_lbo = (unsigned)p.R * 16u;
       const unsigned b_lbo = (unsigned)p.Cout * 16u;
-      int i = 0;
-      const int TTm = p.MT * 128;
-      const int nc_total = p.nchunks + p.nchunks2;
-      for (int c = 0; c < nc_total; ++c) {
-        const int buf = c & 1;
-        mbar_wait(A_FULL(buf), (c >> 1) & 1);
-        const unsigned a_base = smem_u32(a_buf + buf * p.a_bytes);
-        const int ntaps = c < p.nchunks ? p.K : 1;
-        for (int k = 0; k < ntaps; ++k, ++i) {
-          const int s = i % p.nb;
-          mbar_wait(B_FULL(s), (i / p.nb) & 1);
-          tc_fence_after();
-          const unsigned b_base = smem_u32(b_buf + s * p.b_bytes);
-          const unsigned tap_row = c < p.nchunks ? (unsigned)(p.win_mode ? k * TTm : k * p.D) : 0u;
+      unsigned ca = 0, i = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it % p.nacc;
+        mbar_wait(ACC_EMPTY(as), ((it / p.nacc) & 1) ^ 1);
+        tc_fence_after();
+        const unsigned d_base = tmem_base + (unsigned)(as * acc_cols);
+        for (int c = 0; c < nc_total; ++c, ++ca) {
+          const int buf = ca % p.na;
+          mbar_wait(A_FULL(buf), (ca / p.na) & 1);
+          const unsigned a_base = smem_u32(a_buf + (size_t)buf * p.a_bytes);
+          const int ntaps = c < p.nchunks ? p.K : 1;
+          for (int k = 0; k < ntaps; ++k, ++i) {
+            const int s = i % p.nb;
+            mbar_wait(B_FULL(s), (i / p.nb) & 1);
+            tc_fence_after();
+            const unsigned b_base = smem_u32(b_buf + (size_t)s * p.b_bytes);
+            const unsigned tap_row = c < p.nchunks ? (unsigned)(p.win_mode ? k * TT : k * p.D) : 0u;
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            for (int mt = 0; mt < p.MT; ++mt) {
-              const unsigned row = (unsigned)(mt * 128) + tap_row;
-              // (a_sub, b_sub): (hi,hi), (lo,hi), (hi,lo)
+            for (int ks = 0; ks < KC / 16; ++ks) {
+              for (int mt = 0; mt < p.MT; ++mt) {
+                const unsigned row = (unsigned)(mt * 128) + tap_row;
+                // (a_sub, b_sub): (hi,hi), (lo,hi), (hi,lo)
 #pragma unroll
-              for (int pass = 0; pass < 3; ++pass) {
-                const int asub = pass == 1 ? 1 : 0;
-                const int bsub = pass == 2 ? 1 : 0;
-                const unsigned a_addr = a_base + ((unsigned)(asub * (KC / 8) + 2 * ks) * p.R + row) * 16u;
-                const unsigned b_addr = b_base + (unsigned)(bsub * (KC / 8) + 2 * ks) * p.Cout * 16u;
-                const unsigned acc = (c | k | ks | pass) != 0 ? 1u : 0u;
-                if (p.variant & 1)
-                  tc_mma(tmem_base + (unsigned)(mt * p.Cout), make_desc(a_addr, 128u, a_lbo),
-                         make_desc(b_addr, 128u, b_lbo), p.idesc, acc);
-                else
-                  tc_mma(tmem_base + (unsigned)(mt * p.Cout), make_desc(a_addr, a_lbo, 128u),
-                         make_desc(b_addr, b_lbo, 128u), p.idesc, acc);
+                for (int pass = 0; pass < 3; ++pass) {
+                  const int asub = pass == 1 ? 1 : 0;
+                  const int bsub = pass == 2 ? 1 : 0;
+                  const unsigned a_addr = a_base + ((unsigned)(asub * (KC / 8) + 2 * ks) * p.R + row) * 16u;
+                  const unsigned b_addr = b_base + (unsigned)(bsub * (KC / 8) + 2 * ks) * p.Cout * 16u;
+                  const unsigned acc = (c | k | ks | pass) != 0 ? 1u : 0u;
+                  if (p.variant & 1)
+                    tc_mma(d_base + (unsigned)(mt * p.Cout), make_desc(a_addr, 128u, a_lbo),
+                           make_desc(b_addr, 128u, b_lbo), p.idesc, acc);
+                  else
+                    tc_mma(d_base + (unsigned)(mt * p.Cout), make_desc(a_addr, a_lbo, 128u),
+                           make_desc(b_addr, b_lbo, 128u), p.idesc, acc);
+                }
               }
             }
+            tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
           }
-          tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
+          tc_commit(A_EMPTY(buf));
         }
-        tc_commit(A_EMPTY(buf));
+        tc_commit(ACC_FULL(as));
       }
-      tc_commit(ACC_FULL);
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols)
                  : "memory");
@@ -489,39 +550,46 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
   // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(d->cout >> 3) << 17) | ((128u >> 4) << 24);
   p.b_bytes = 2 * (KC / 8) * d->cout * 16;
-  // tile shape: contiguous halo tile at 2 CTAs/SM when it fits, else one window per tap at 1 CTA/SM
-  for (int attempt = 0; attempt < 3; ++attempt) {
-    size_t budget;
+  // tile shape (1 persistent CTA / SM, ~216 KB of shared memory): prefer a contiguous halo tile of
+  // 2 x 128 rows; fall back to 128 rows, then to one window per tap (very large dilation)
+  const size_t budget = 216 * 1024;
+  for (int attempt = 0; attempt < 4; ++attempt) {
     if (attempt == 0) {
       p.MT = (2 * d->cout <= 256 && d->t_out > 128) ? 2 : 1;
       p.win_mode = 0;
       p.R = p.MT * 128 + (int)halo;
-      budget = 110 * 1024;
-      if (halo > 1024) continue;
     } else if (attempt == 1) {
       p.MT = 1;
       p.win_mode = 0;
       p.R = 128 + (int)halo;
-      budget = 110 * 1024;
-      if (halo > 1024) continue;
+    } else if (attempt == 2) {
+      p.MT = (2 * d->cout <= 256 && d->t_out > 128) ? 2 : 1;
+      p.win_mode = 1;
+      p.R = d->kernel * p.MT * 128;
     } else {
       p.MT = 1;
       p.win_mode = 1;
       p.R = d->kernel * 128;
-      budget = 200 * 1024;
     }
+    if (!p.win_mode && halo > 2048) continue;
+    if (p.win_mode && halo <= p.MT * 128) continue;  // a contiguous tile is never larger in that case
     p.a_bytes = 2 * (KC / 8) * p.R * 16;
-    const size_t fixed = 2 * (size_t)p.a_bytes + 256;
+    int na = 3;
+    if (3 * (size_t)p.a_bytes + 2 * (size_t)p.b_bytes + 512 > budget) na = 2;
+    const size_t fixed = (size_t)na * p.a_bytes + 512;
     if (fixed + 2 * (size_t)p.b_bytes > budget) continue;
     int nb = (int)((budget - fixed) / p.b_bytes);
-    if (nb > 6) nb = 6;
+    if (nb > 8) nb = 8;
+    p.na = na;
     p.nb = nb;
     p.tiles_per_seq = ceil_div(d->t_out, p.MT * 128);
-    int cols = p.MT * d->cout;
+    p.total_tiles = p.tiles_per_seq * d->batch;
+    const int cols = p.MT * d->cout;
+    p.nacc = 2 * cols <= 512 ? 2 : 1;
     int alloc = 32;
-    while (alloc < cols) alloc <<= 1;
+    while (alloc < p.nacc * cols) alloc <<= 1;
     p.tmem_cols = alloc;
-    smem_bytes = 2 * (size_t)p.a_bytes + (size_t)nb * p.b_bytes + 8 * (4 + 2 * nb + 1) + 16;
+    smem_bytes = (size_t)na * p.a_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4) + 16;
     return 1;
   }
   return 0;
@@ -533,18 +601,25 @@ static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w,
   if (p.B == 0 || p.T_out == 0) return PWGB_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) {
       set_error("conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PWGB_CUDA_ERROR;
     }
     attr_set = true;
   }
-  const long long grid = (long long)p.B * p.tiles_per_seq;
-  if (grid > 0x7fffffffLL) {
-    set_error("conv1d_tc: grid too large");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  if ((long long)p.B * p.tiles_per_seq > 0x7fffffffLL) {
+    set_error("conv1d_tc: too many tiles");
     return PWGB_UNSUPPORTED;
   }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, x2, (const uint4*)packed_w, bias, residual, y, y2);
   return check_launch("conv1d_tc_kernel");
 }

@@ -93,7 +93,7 @@ def test_losses_vs_reference(dev):
 
 def test_mr_stft_loss_properties_full_size(dev):
     """BASELINE C3 size (64 x 25600): size-independent properties -- identical signals give
-    (sc, mag) = (0, 0); the loss is invariant to batch order; scaling both signals by a power of two
+    (sc, mag) ~ (0, 0); the loss is invariant to batch order; scaling both signals by a power of two
     leaves sc unchanged (magnitudes scale exactly) wherever the clamp is inactive."""
     from parallelwavegan_b200 import losses
 
@@ -102,7 +102,8 @@ def test_mr_stft_loss_properties_full_size(dev):
     x = (torch.rand(64, 25600, generator=g) - 0.5).to(dev)
     y = (torch.rand(64, 25600, generator=g) - 0.5).to(dev)
     sc, mag = mr(x, x)
-    assert float(sc) == 0.0 and float(mag) == 0.0
+    # X and Y come out of the two halves of one complex FFT, so they agree to rounding, not bitwise
+    assert float(sc) < 1e-6 and float(mag) < 1e-6
     sc1, mag1 = mr(x, y)
     perm = torch.randperm(64, generator=g).to(dev)
     sc2, mag2 = mr(x[perm].contiguous(), y[perm].contiguous())
