@@ -25,7 +25,9 @@
 namespace pwgb {
 
 constexpr int KC = 32;  // input channels per activation chunk / weight stage (2 UMMA K-steps)
-constexpr int TC_THREADS = 320;
+constexpr int NPROD = 256;  // producer threads (warps 0-7)
+constexpr int NEPI = 256;   // epilogue threads (warps 8-15)
+constexpr int TC_THREADS = NPROD + NEPI + 64;
 constexpr unsigned SPIN_LIMIT = 1u << 22;
 
 struct TcK {
@@ -92,11 +94,25 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One elected lane of a converged warp (all 32 lanes must call this).  Keeping the issuing warp
+// converged lets the compiler hold descriptors in uniform registers; a `lane == 0` branch instead
+// forces R2UR moves + an ELECT retry loop around every UTCHMMA (~150 cycles per MMA, measured).
+__device__ __forceinline__ unsigned elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void tc_commit(unsigned bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (elect_one())
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_mma(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
                                        unsigned idesc, unsigned accumulate) {
+  if (elect_one())
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -217,7 +233,7 @@ __device__ __forceinline__ void fill_main_chunk(const TcK& p, const float* __res
   };
   if (p.pre_gate) {
     const float* xg = xc + (long long)p.Cin * p.T_in;
-    for (int r = tid; r < p.R; r += 128) {
+    for (int r = tid; r < p.R; r += NPROD) {
       bool ok;
       const long long ts = src_of(r, ok);
       float v[KC], sg[KC];
@@ -232,28 +248,15 @@ __device__ __forceinline__ void fill_main_chunk(const TcK& p, const float* __res
     }
     return;
   }
-  // software-pipelined rows: the loads of row r+128 are in flight while row r is converted
-  float cur[KC], nxt[KC];
-  int r = tid;
-  if (r < p.R) {
+  for (int r = tid; r < p.R; r += NPROD) {
     bool ok;
     const long long ts = src_of(r, ok);
+    float v[KC];
 #pragma unroll
-    for (int j = 0; j < KC; ++j) cur[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
-  }
-  for (; r < p.R; r += 128) {
-    const int rn = r + 128;
-    if (rn < p.R) {
-      bool ok;
-      const long long ts = src_of(rn, ok);
+    for (int j = 0; j < KC; ++j) v[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
 #pragma unroll
-      for (int j = 0; j < KC; ++j) nxt[j] = ok ? __ldg(xc + (long long)j * p.T_in + ts) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < KC; ++j) cur[j] = lrelu(cur[j], p.pre_slope);
-    store_row(cur, r);
-#pragma unroll
-    for (int j = 0; j < KC; ++j) cur[j] = nxt[j];
+    for (int j = 0; j < KC; ++j) v[j] = lrelu(v[j], p.pre_slope);
+    store_row(v, r);
   }
 }
 
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   if (tid == 0) {
     for (int i = 0; i < p.na; ++i) {
-      mbar_init(A_FULL(i), 128);
+      mbar_init(A_FULL(i), NPROD);
       mbar_init(A_EMPTY(i), 1);
     }
     for (int i = 0; i < p.nb; ++i) {
@@ -295,11 +298,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(ACC_FULL(i), 1);
-      mbar_init(ACC_EMPTY(i), 128);
+      mbar_init(ACC_EMPTY(i), NEPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == 17) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((unsigned)p.tmem_cols)
                  : "memory");
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== A producers =====================
     unsigned ca = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         } else {
           // auxiliary 1x1 source: TT rows aligned with the output tile, no padding shift, no activation
           const float* xc = x2 + ((long long)b * p.C2 + (long long)(c - p.nchunks) * KC) * p.T_out;
-          for (int r = tid; r < TT; r += 128) {
+          for (int r = tid; r < TT; r += NPROD) {
             const long long ts = (long long)t0 + r;
             const bool ok = ts < p.T_out;
 #pragma unroll
@@ -345,9 +348,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_arrive(A_FULL(buf));
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 16) {
     // ===================== epilogue =====================
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 warps: lane quarter = warp % 4 (hardware TMEM access rule), column half = (warp - 8) / 4
+    const int ew = warp & 3;
+    const int ngroups = p.Cout / 16;
+    const int col_begin = ((warp - 8) >> 2) ? (ngroups / 2) * 16 : 0;
+    const int col_end = ((warp - 8) >> 2) ? p.Cout : (ngroups / 2) * 16;
     const int m = ew * 32 + lane;
     unsigned it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -360,7 +367,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int mt = 0; mt < p.MT; ++mt) {
         const int t = t0 + mt * 128 + m;
         const bool tv = t < p.T_out;
-        for (int col = 0; col < p.Cout; col += 16) {
+        for (int col = col_begin; col < col_end; col += 16) {
           unsigned r[16];
           tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
           if (p.shuffle > 1) {
@@ -432,9 +439,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(as));  // accumulator set drained: the MMA warp may overwrite it
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // ===================== B producer (TMA bulk copies of packed weight stages) =====================
-    if (lane == 0) {
+    {
       const int per_tile = p.nchunks * p.K + p.nchunks2;
       const unsigned char* src = reinterpret_cast<const unsigned char*>(wpk);
       unsigned i = 0;
@@ -442,16 +449,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int j = 0; j < per_tile; ++j, ++i) {
           const int s = i % p.nb;
           mbar_wait(B_EMPTY(s), ((i / p.nb) & 1) ^ 1);
-          mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
-          bulk_g2s(smem_u32(b_buf + (size_t)s * p.b_bytes), src + (size_t)j * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
+          if (elect_one()) {
+            mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
+            bulk_g2s(smem_u32(b_buf + (size_t)s * p.b_bytes), src + (size_t)j * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
+          }
+          __syncwarp();
         }
       }
     }
   } else {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const unsigned a_lbo = (unsigned)p.R * 16u;
-      const unsigned b_lbo = (unsigned)p.Cout * 16u;
+    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+    {
+      // descriptor = hi_const : (lo_const + (addr >> 4));  LBO/SBO/version never change in a launch
+      const unsigned long long hi_const = ((unsigned long long)((128u >> 4) | (1u << 14))) << 32;
+      const unsigned a_lo = (((unsigned)p.R) & 0x3FFFu) << 16;     // LBO = R*16 B  -> R 16-byte units
+      const unsigned b_lo = (((unsigned)p.Cout) & 0x3FFFu) << 16;  // LBO = Cout*16 B
+      const unsigned a_sub = (unsigned)(KC / 8) * p.R;             // hi -> lo image distance (16 B units)
+      const unsigned b_sub = (unsigned)(KC / 8) * p.Cout;
       unsigned ca = 0, i = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int as = it % p.nacc;
@@ -461,33 +475,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int c = 0; c < nc_total; ++c, ++ca) {
           const int buf = ca % p.na;
           mbar_wait(A_FULL(buf), (ca / p.na) & 1);
-          const unsigned a_base = smem_u32(a_buf + (size_t)buf * p.a_bytes);
+          const unsigned a16 = smem_u32(a_buf + (size_t)buf * p.a_bytes) >> 4;
           const int ntaps = c < p.nchunks ? p.K : 1;
           for (int k = 0; k < ntaps; ++k, ++i) {
             const int s = i % p.nb;
             mbar_wait(B_FULL(s), (i / p.nb) & 1);
             tc_fence_after();
-            const unsigned b_base = smem_u32(b_buf + (size_t)s * p.b_bytes);
+            const unsigned b16 = smem_u32(b_buf + (size_t)s * p.b_bytes) >> 4;
             const unsigned tap_row = c < p.nchunks ? (unsigned)(p.win_mode ? k * TT : k * p.D) : 0u;
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks) {
+              const unsigned bk = b16 + (unsigned)(2 * ks) * p.Cout;
+              const unsigned long long b_hi = hi_const | (unsigned long long)(b_lo + bk);
+              const unsigned long long b_lo_img = hi_const | (unsigned long long)(b_lo + bk + b_sub);
               for (int mt = 0; mt < p.MT; ++mt) {
-                const unsigned row = (unsigned)(mt * 128) + tap_row;
-                // (a_sub, b_sub): (hi,hi), (lo,hi), (hi,lo)
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                  const int asub = pass == 1 ? 1 : 0;
-                  const int bsub = pass == 2 ? 1 : 0;
-                  const unsigned a_addr = a_base + ((unsigned)(asub * (KC / 8) + 2 * ks) * p.R + row) * 16u;
-                  const unsigned b_addr = b_base + (unsigned)(bsub * (KC / 8) + 2 * ks) * p.Cout * 16u;
-                  const unsigned acc = (c | k | ks | pass) != 0 ? 1u : 0u;
-                  if (p.variant & 1)
-                    tc_mma(d_base + (unsigned)(mt * p.Cout), make_desc(a_addr, 128u, a_lbo),
-                           make_desc(b_addr, 128u, b_lbo), p.idesc, acc);
-                  else
-                    tc_mma(d_base + (unsigned)(mt * p.Cout), make_desc(a_addr, a_lbo, 128u),
-                           make_desc(b_addr, b_lbo, 128u), p.idesc, acc);
-                }
+                const unsigned ak = a16 + (unsigned)(2 * ks) * p.R + (unsigned)(mt * 128) + tap_row;
+                const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + ak);
+                const unsigned long long a_lo_img = hi_const | (unsigned long long)(a_lo + ak + a_sub);
+                const unsigned d = d_base + (unsigned)(mt * p.Cout);
+                tc_mma(d, a_hi, b_hi, p.idesc, (c | k | ks) != 0 ? 1u : 0u);  // xh * wh
+                tc_mma(d, a_lo_img, b_hi, p.idesc, 1u);                       // xl * wh
+                tc_mma(d, a_hi, b_lo_img, p.idesc, 1u);                       // xh * wl
               }
             }
             tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   }
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols)
                  : "memory");
