@@ -39,6 +39,7 @@ struct TcK {
   int accumulate;
   int shuffle, shuffle_pad, shuffle_tout;
   int MT, R, nchunks, tiles_per_seq, nb, na, nacc, total_tiles;
+  int ns;                // raw fp32 cp.async staging buffers for the activation chunks (0 = direct register path)
   long long xbs, ybs, rbs;
   unsigned idesc;
   int tmem_cols;
@@ -91,6 +92,15 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void cp_async4(unsigned dst, const float* src, unsigned src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void producer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(256) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -265,10 +275,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                      const uint4* __restrict__ wpk, const float* __restrict__ bias, const float* __restrict__ res,
                      float* __restrict__ y, float* __restrict__ y2) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: A[na] | B[nb] | barriers | tmem ptr
+  // layout: A[na] | B[nb] | raw staging[ns] | barriers | tmem ptr
   unsigned char* a_buf = smem;
   unsigned char* b_buf = smem + (size_t)p.na * p.a_bytes;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(b_buf + (size_t)p.nb * p.b_bytes);
+  unsigned char* raw_buf = b_buf + (size_t)p.nb * p.b_bytes;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(raw_buf + (size_t)p.ns * p.a_bytes);
   const int nbar = 2 * p.na + 2 * p.nb + 4;
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + nbar);
 
@@ -313,8 +324,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
 
-  if (warp < 8) {
-    // ===================== A producers =====================
+  if (warp < 8 && p.ns > 0) {
+    // ===================== A producers, cp.async-staged =====================
+    // The raw fp32 chunk q+1 streams into shared memory (no registers held, any padding policy by
+    // per-element addressing, zero-fill through src-size 0) while chunk q is converted to the bf16
+    // hi/lo operand image: global-memory latency is decoupled from the conversion.
+    const int ntile_local = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nq = ntile_local * nc_total;
+    auto issue = [&](int q) {
+      const int tile = blockIdx.x + (q / nc_total) * gridDim.x;
+      const int c = q % nc_total;
+      const int b = tile / p.tiles_per_seq;
+      const int t0 = (tile - b * p.tiles_per_seq) * TT;
+      const unsigned raw = smem_u32(raw_buf + (size_t)(q % p.ns) * p.a_bytes);
+      if (c < p.nchunks) {
+        const float* xc = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in;
+        for (int r = tid; r < p.R; r += NPROD) {
+          long long ts;
+          if (p.win_mode) {
+            const int k = r / TT;
+            ts = (long long)t0 - p.padL + (long long)k * p.D + (r - k * TT);
+          } else {
+            ts = (long long)t0 - p.padL + r;
+          }
+          bool ok = true;
+          if (ts < 0 || ts >= p.T_in) {
+            if (p.pad_mode == PWGB_PAD_ZERO) {
+              ok = false;
+            } else if (p.pad_mode == PWGB_PAD_REFLECT) {
+              ts = ts < 0 ? -ts : 2LL * (p.T_in - 1) - ts;
+              ok = ts >= 0 && ts < p.T_in;
+            } else {
+              ts = ts < 0 ? 0 : p.T_in - 1;
+            }
+          }
+          const float* src = ok ? xc + ts : xc;
+          const unsigned nbytes = ok ? 4u : 0u;
+#pragma unroll 8
+          for (int j = 0; j < KC; ++j) cp_async4(raw + (unsigned)(j * p.R + r) * 4u, src + (long long)j * p.T_in, nbytes);
+        }
+      } else {
+        const float* xc = x2 + ((long long)b * p.C2 + (long long)(c - p.nchunks) * KC) * p.T_out;
+        for (int r = tid; r < TT; r += NPROD) {
+          const long long ts = (long long)t0 + r;
+          const bool ok = ts < p.T_out;
+          const float* src = ok ? xc + ts : xc;
+          const unsigned nbytes = ok ? 4u : 0u;
+#pragma unroll 8
+          for (int j = 0; j < KC; ++j) cp_async4(raw + (unsigned)(j * p.R + r) * 4u, src + (long long)j * p.T_out, nbytes);
+        }
+      }
+      cp_async_commit();
+    };
+    if (nq > 0) issue(0);
+    for (int q = 0; q < nq; ++q) {
+      if (q + 1 < nq) {
+        issue(q + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      producer_barrier();  // every producer's copies of chunk q have landed
+      const int c = q % nc_total;
+      const int buf = q % p.na;
+      mbar_wait(A_EMPTY(buf), ((q / p.na) & 1) ^ 1);
+      unsigned char* dst = a_buf + (size_t)buf * p.a_bytes;
+      const float* raw = reinterpret_cast<const float*>(raw_buf + (size_t)(q % p.ns) * p.a_bytes);
+      const int rows = c < p.nchunks ? p.R : TT;
+      const float slope = c < p.nchunks ? p.pre_slope : 1.f;
+      for (int r = tid; r < rows; r += NPROD) {
+#pragma unroll
+        for (int g = 0; g < KC / 8; ++g) {
+          float u[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = lrelu(raw[(g * 8 + j) * p.R + r], slope);
+          uint4 hi, lo;
+          split8(u, hi, lo);
+          *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
+          *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(A_FULL(buf));
+      producer_barrier();  // raw[q % ns] may be overwritten by issue(q + 2)
+    }
+  } else if (warp < 8) {
+    // ===================== A producers, direct register path =====================
     unsigned ca = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_seq;
@@ -582,14 +677,27 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     if (!p.win_mode && halo > 2048) continue;
     if (p.win_mode && halo <= p.MT * 128) continue;  // a contiguous tile is never larger in that case
     p.a_bytes = 2 * (KC / 8) * p.R * 16;
-    int na = 3;
-    if (3 * (size_t)p.a_bytes + 2 * (size_t)p.b_bytes + 512 > budget) na = 2;
-    const size_t fixed = (size_t)na * p.a_bytes + 512;
-    if (fixed + 2 * (size_t)p.b_bytes > budget) continue;
-    int nb = (int)((budget - fixed) / p.b_bytes);
+    // shared-memory split: [na operand buffers][nb weight stages][ns raw staging buffers]
+    int na = 0, nb = 0, ns = 0;
+    const size_t A = (size_t)p.a_bytes, Bs = (size_t)p.b_bytes, slack = 512;
+    if (!d->pre_gate && 2 * A + 3 * A + 3 * Bs + slack <= budget) {
+      ns = 2;
+      na = 3;
+    } else if (!d->pre_gate && 2 * A + 2 * A + 2 * Bs + slack <= budget) {
+      ns = 2;
+      na = 2;
+    } else if (3 * A + 2 * Bs + slack <= budget) {
+      na = 3;
+    } else if (2 * A + 2 * Bs + slack <= budget) {
+      na = 2;
+    } else {
+      continue;
+    }
+    nb = (int)((budget - slack - (size_t)(na + ns) * A) / Bs);
     if (nb > 8) nb = 8;
     p.na = na;
     p.nb = nb;
+    p.ns = ns;
     p.tiles_per_seq = ceil_div(d->t_out, p.MT * 128);
     p.total_tiles = p.tiles_per_seq * d->batch;
     const int cols = p.MT * d->cout;
@@ -597,7 +705,7 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     int alloc = 32;
     while (alloc < p.nacc * cols) alloc <<= 1;
     p.tmem_cols = alloc;
-    smem_bytes = (size_t)na * p.a_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4) + 16;
+    smem_bytes = (size_t)(na + ns) * p.a_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4) + 16;
     return 1;
   }
   return 0;
