@@ -77,9 +77,22 @@ __device__ __forceinline__ bool mbar_try(unsigned bar, unsigned parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_spin(unsigned bar, unsigned parity) {
+  unsigned n = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++n > SPIN_LIMIT) {
+      printf("pwgb conv1d_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+// Same with a sleep back-off: waiting warps must not steal issue slots from the working ones
+// (spin loops were 17% of all executed instructions in the first persistent version).
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   unsigned n = 0;
   while (!mbar_try(bar, parity)) {
+    if (n > 4) __nanosleep(n > 64 ? 200 : 40);
     if (++n > SPIN_LIMIT) {
       printf("pwgb conv1d_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);
@@ -282,6 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(raw_buf + (size_t)p.ns * p.a_bytes);
   const int nbar = 2 * p.na + 2 * p.nb + 4;
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + nbar);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // Cout floats (0 when bias == nullptr)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -319,6 +333,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = tid; i < p.Cout; i += TC_THREADS)
+    bias_s[i] = bias ? __ldg(bias + (p.shuffle > 1 ? (p.co_off + i) / p.shuffle : p.co_off + i)) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -360,8 +376,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           const float* src = ok ? xc + ts : xc;
           const unsigned nbytes = ok ? 4u : 0u;
+          unsigned dq = raw + (unsigned)r * 4u;
+          const unsigned dstep = (unsigned)p.R * 4u;
 #pragma unroll 8
-          for (int j = 0; j < KC; ++j) cp_async4(raw + (unsigned)(j * p.R + r) * 4u, src + (long long)j * p.T_in, nbytes);
+          for (int j = 0; j < KC; ++j, src += p.T_in, dq += dstep) cp_async4(dq, src, nbytes);
         }
       } else {
         const float* xc = x2 + ((long long)b * p.C2 + (long long)(c - p.nchunks) * KC) * p.T_out;
@@ -370,8 +388,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const bool ok = ts < p.T_out;
           const float* src = ok ? xc + ts : xc;
           const unsigned nbytes = ok ? 4u : 0u;
+          unsigned dq = raw + (unsigned)r * 4u;
+          const unsigned dstep = (unsigned)p.R * 4u;
 #pragma unroll 8
-          for (int j = 0; j < KC; ++j) cp_async4(raw + (unsigned)(j * p.R + r) * 4u, src + (long long)j * p.T_out, nbytes);
+          for (int j = 0; j < KC; ++j, src += p.T_out, dq += dstep) cp_async4(dq, src, nbytes);
         }
       }
       cp_async_commit();
@@ -459,20 +479,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(ACC_FULL(as), (it / p.nacc) & 1);
       tc_fence_after();
       const unsigned tacc = tmem_base + ((unsigned)(ew * 32) << 16) + (unsigned)(as * acc_cols);
+      const long long st = p.T_out;
       for (int mt = 0; mt < p.MT; ++mt) {
         const int t = t0 + mt * 128 + m;
         const bool tv = t < p.T_out;
-        for (int col = col_begin; col < col_end; col += 16) {
-          unsigned r[16];
-          tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
-          if (p.shuffle > 1) {
+        if (p.shuffle > 1) {
+          for (int col = col_begin; col < col_end; col += 16) {
+            unsigned r[16];
+            tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
             tc_wait_ld();
             if (tv) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int co = p.co_off + col + j;
                 const int cof = co / p.shuffle;
-                float v = __uint_as_float(r[j]) + (bias ? __ldg(bias + cof) : 0.f);
+                float v = __uint_as_float(r[j]) + bias_s[col + j];
                 if (p.post_act == PWGB_ACT_TANH)
                   v = tanhf(v);
                 else if (p.post_act == PWGB_ACT_LRELU)
@@ -482,50 +503,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                   y[(long long)b * p.ybs + (long long)cof * p.shuffle_tout + of] = v * p.out_scale;
               }
             }
-          } else if (p.wavenet) {
-            // WaveNet split epilogue (residual_block.py:131-138): columns [0, split) are the skip 1x1
-            // (accumulated into y2), columns [split, Cout) the residual 1x1: y = (v + x) * sqrt(0.5)
+          }
+        } else if (p.wavenet) {
+          // WaveNet split epilogue (residual_block.py:131-138): columns [0, split) are the skip 1x1
+          // (accumulated into y2), columns [split, Cout) the residual 1x1: y = (v + x) * sqrt(0.5)
+          for (int col = col_begin; col < col_end; col += 16) {
+            unsigned r[16];
+            tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
             const bool is_skip = col < p.split;
             const int ch = is_skip ? col : col - p.split;
             const int nch = is_skip ? p.split : p.Cout - p.split;
-            const long long off = ((long long)b * nch + ch) * p.T_out + t;
-            float rv[16], bv[16];
+            const long long off = ((long long)b * nch + ch) * st + t;
+            float rv[16];
+            if (tv) {
+              const float* rq = is_skip ? y2 + off : res + off;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              rv[j] = tv ? (is_skip ? y2[off + (long long)j * p.T_out] : __ldg(res + off + (long long)j * p.T_out)) : 0.f;
-              bv[j] = bias ? __ldg(bias + col + j) : 0.f;
+              for (int j = 0; j < 16; ++j, rq += st) rv[j] = is_skip ? *rq : __ldg(rq);
             }
             tc_wait_ld();
             if (tv) {
+              float* wq = is_skip ? y2 + off : y + off;
+              const float sc = is_skip ? 1.f : p.out_scale;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float v = __uint_as_float(r[j]) + bv[j];
-                if (is_skip)
-                  y2[off + (long long)j * p.T_out] = rv[j] + v;
-                else
-                  y[off + (long long)j * p.T_out] = (v + rv[j]) * p.out_scale;
+              for (int j = 0; j < 16; ++j, wq += st) *wq = (__uint_as_float(r[j]) + bias_s[col + j] + rv[j]) * sc;
+            }
+          }
+        } else {
+          // generic: running 64-bit pointers (2 integer instructions per element instead of a full
+          // address recomputation), every independent load of a 16-column group issued before use
+          float* yq = y + (long long)b * p.ybs + (long long)(p.co_off + col_begin) * st + t;
+          const float* rq = res ? res + (long long)b * p.rbs + (long long)(p.co_off + col_begin) * st + t : nullptr;
+          for (int col = col_begin; col < col_end; col += 16, yq += 16 * st) {
+            unsigned r[16];
+            tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
+            float rv[16];
+            if (rq) {
+              if (tv) {
+                const float* q = rq;
+#pragma unroll
+                for (int j = 0; j < 16; ++j, q += st) rv[j] = __ldg(q);
               }
-            }
-          } else {
-            // issue every independent global load of this 16-column group before touching the results
-            const long long off = (long long)(p.co_off + col) * p.T_out + t;
-            float rv[16], yv[16], bv[16];
+              rq += 16 * st;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              rv[j] = (res && tv) ? __ldg(res + (long long)b * p.rbs + off + (long long)j * p.T_out) : 0.f;
-              yv[j] = (p.accumulate && tv) ? y[(long long)b * p.ybs + off + (long long)j * p.T_out] : 0.f;
-              bv[j] = bias ? __ldg(bias + p.co_off + col + j) : 0.f;
+              for (int j = 0; j < 16; ++j) rv[j] = 0.f;
             }
             tc_wait_ld();
             if (tv) {
+              float* q = yq;
+              if (p.accumulate) {  // MRF sum (1 conv in 6): read-modify-write, loads batched first
+                float yv[16];
+                const float* q2 = yq;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float v = __uint_as_float(r[j]) + bv[j];
-                if (p.post_act == PWGB_ACT_TANH)
-                  v = tanhf(v);
-                else if (p.post_act == PWGB_ACT_LRELU)
-                  v = lrelu(v, p.post_slope);
-                y[(long long)b * p.ybs + off + (long long)j * p.T_out] = (v + rv[j]) * p.out_scale + yv[j];
+                for (int j = 0; j < 16; ++j, q2 += st) yv[j] = *q2;
+#pragma unroll
+                for (int j = 0; j < 16; ++j, q += st) {
+                  float v = __uint_as_float(r[j]) + bias_s[col + j];
+                  if (p.post_act != PWGB_ACT_NONE) v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
+                  *q = (v + rv[j]) * p.out_scale + yv[j];
+                }
+              } else if (p.post_act == PWGB_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j, q += st) *q = (__uint_as_float(r[j]) + bias_s[col + j] + rv[j]) * p.out_scale;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j, q += st) {
+                  float v = __uint_as_float(r[j]) + bias_s[col + j];
+                  v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
+                  *q = (v + rv[j]) * p.out_scale;
+                }
               }
             }
           }
@@ -564,17 +610,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       unsigned ca = 0, i = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int as = it % p.nacc;
-        mbar_wait(ACC_EMPTY(as), ((it / p.nacc) & 1) ^ 1);
+        mbar_wait_spin(ACC_EMPTY(as), ((it / p.nacc) & 1) ^ 1);
         tc_fence_after();
         const unsigned d_base = tmem_base + (unsigned)(as * acc_cols);
         for (int c = 0; c < nc_total; ++c, ++ca) {
           const int buf = ca % p.na;
-          mbar_wait(A_FULL(buf), (ca / p.na) & 1);
+          mbar_wait_spin(A_FULL(buf), (ca / p.na) & 1);
           const unsigned a16 = smem_u32(a_buf + (size_t)buf * p.a_bytes) >> 4;
           const int ntaps = c < p.nchunks ? p.K : 1;
           for (int k = 0; k < ntaps; ++k, ++i) {
             const int s = i % p.nb;
-            mbar_wait(B_FULL(s), (i / p.nb) & 1);
+            mbar_wait_spin(B_FULL(s), (i / p.nb) & 1);
             tc_fence_after();
             const unsigned b16 = smem_u32(b_buf + (size_t)s * p.b_bytes) >> 4;
             const unsigned tap_row = c < p.nchunks ? (unsigned)(p.win_mode ? k * TT : k * p.D) : 0u;
@@ -679,7 +725,7 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     p.a_bytes = 2 * (KC / 8) * p.R * 16;
     // shared-memory split: [na operand buffers][nb weight stages][ns raw staging buffers]
     int na = 0, nb = 0, ns = 0;
-    const size_t A = (size_t)p.a_bytes, Bs = (size_t)p.b_bytes, slack = 512;
+    const size_t A = (size_t)p.a_bytes, Bs = (size_t)p.b_bytes, slack = 2048;
     if (!d->pre_gate && 2 * A + 3 * A + 3 * Bs + slack <= budget) {
       ns = 2;
       na = 3;
@@ -705,7 +751,7 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     int alloc = 32;
     while (alloc < p.nacc * cols) alloc <<= 1;
     p.tmem_cols = alloc;
-    smem_bytes = (size_t)(na + ns) * p.a_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4) + 16;
+    smem_bytes = (size_t)(na + ns) * p.a_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4) + 16 + 4 * 256;
     return 1;
   }
   return 0;
