@@ -24,7 +24,8 @@
 
 namespace pwgb {
 
-constexpr int KC = 32;  // input channels per activation chunk / weight stage (2 UMMA K-steps)
+constexpr int KC = 16;  // input channels per activation chunk / weight stage (= one UMMA K-step):
+                        // small stages leave most of the shared memory to a deep weight (B) ring
 constexpr int NPROD = 256;  // producer threads (warps 0-7)
 constexpr int NEPI = 256;   // epilogue threads (warps 8-15)
 constexpr int TC_THREADS = NPROD + NEPI + 64;
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         for (int j = 0; j < per_tile; ++j, ++i) {
           const int s = i % p.nb;
-          mbar_wait(B_EMPTY(s), ((i / p.nb) & 1) ^ 1);
+          mbar_wait_spin(B_EMPTY(s), ((i / p.nb) & 1) ^ 1);
           if (elect_one()) {
             mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
             bulk_g2s(smem_u32(b_buf + (size_t)s * p.b_bytes), src + (size_t)j * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
@@ -740,7 +741,7 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
       continue;
     }
     nb = (int)((budget - slack - (size_t)(na + ns) * A) / Bs);
-    if (nb > 8) nb = 8;
+    if (nb > 24) nb = 24;
     p.na = na;
     p.nb = nb;
     p.ns = ns;
