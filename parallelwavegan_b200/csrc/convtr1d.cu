@@ -80,7 +80,7 @@ extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const 
   c.shuffle_pad = d->padding;
   c.shuffle_tout = d->t_out;
   // tcgen05 path: N (= cout*s virtual channels) in chunks of <= 256 accumulator columns
-  if (d->cin % 16 == 0 && c.cout % 16 == 0) {
+  if (d->cin % 32 == 0 && c.cout % 16 == 0) {
     int chunk = c.cout;
     if (chunk > 256) {
       chunk = 256;
