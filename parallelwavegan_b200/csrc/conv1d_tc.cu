@@ -144,6 +144,39 @@ __device__ __forceinline__ void tc_mma(unsigned d_tmem, unsigned long long adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// All bf16x3 passes of one (k-step, tap) for up to two 128-row m-tiles in ONE asm block: a single
+// elect.sync and descriptor arithmetic in PTX (u64 adds on the 14-bit start-address field) instead of
+// one elect + register->uniform moves per MMA.  d1 = d0 + dcol, a(mt=1) = a0 + 128 rows (8 units... 128
+// 16-byte units), lo images at +a_sub / +b_sub.
+__device__ __forceinline__ void tc_mma_x3(unsigned d0, unsigned long long a_hi, unsigned long long b_hi,
+                                          unsigned a_sub, unsigned b_sub, unsigned idesc, unsigned accumulate,
+                                          unsigned two_tiles, unsigned dcol) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pacc, p2;\n\t"
+      ".reg .b64 a_lo, b_lo, a1_hi, a1_lo, t64;\n\t"
+      ".reg .b32 d1;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pacc, %6, 0;\n\t"
+      "setp.ne.b32 p2, %7, 0;\n\t"
+      "and.pred p2, p2, pe;\n\t"
+      "cvt.u64.u32 t64, %3;\n\t"
+      "add.u64 a_lo, %1, t64;\n\t"
+      "cvt.u64.u32 t64, %4;\n\t"
+      "add.u64 b_lo, %2, t64;\n\t"
+      "add.u64 a1_hi, %1, 128;\n\t"
+      "add.u64 a1_lo, a_lo, 128;\n\t"
+      "add.u32 d1, %0, %8;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, pacc;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a_lo, %2, %5, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b_lo, %5, 1;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [d1], a1_hi, %2, %5, pacc;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [d1], a1_lo, %2, %5, 1;\n\t"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [d1], a1_hi, b_lo, %5, 1;\n\t"
+      "}" ::"r"(d0),
+      "l"(a_hi), "l"(b_hi), "r"(a_sub), "r"(b_sub), "r"(idesc), "r"(accumulate), "r"(two_tiles), "r"(dcol)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -628,17 +661,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks) {
               const unsigned bk = b16 + (unsigned)(2 * ks) * p.Cout;
+              const unsigned ak = a16 + (unsigned)(2 * ks) * p.R + tap_row;
               const unsigned long long b_hi = hi_const | (unsigned long long)(b_lo + bk);
-              const unsigned long long b_lo_img = hi_const | (unsigned long long)(b_lo + bk + b_sub);
-              for (int mt = 0; mt < p.MT; ++mt) {
-                const unsigned ak = a16 + (unsigned)(2 * ks) * p.R + (unsigned)(mt * 128) + tap_row;
-                const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + ak);
-                const unsigned long long a_lo_img = hi_const | (unsigned long long)(a_lo + ak + a_sub);
-                const unsigned d = d_base + (unsigned)(mt * p.Cout);
-                tc_mma(d, a_hi, b_hi, p.idesc, (c | k | ks) != 0 ? 1u : 0u);  // xh * wh
-                tc_mma(d, a_lo_img, b_hi, p.idesc, 1u);                       // xl * wh
-                tc_mma(d, a_hi, b_lo_img, p.idesc, 1u);                       // xh * wl
-              }
+              const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + ak);
+              tc_mma_x3(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, (c | k | ks) != 0 ? 1u : 0u,
+                        p.MT > 1 ? 1u : 0u, (unsigned)p.Cout);
             }
             tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
           }
