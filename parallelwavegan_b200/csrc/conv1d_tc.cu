@@ -26,8 +26,9 @@ namespace pwgb {
 
 constexpr int KC = 32;  // input channels per activation chunk / weight stage (2 UMMA K-steps).  KC = 16 was
                         // measured slower (22.3 vs 18.5 ms / step): the per-stage barrier round trip dominates
-constexpr int NPROD = 256;  // producer threads (warps 0-7)
-constexpr int NEPI = 256;   // epilogue threads (warps 8-15)
+constexpr int NPROD = 128;  // producer threads (warps 0-3)
+constexpr int NEPI = 256;   // epilogue threads (warps 4-11)
+constexpr int W_EPI0 = NPROD / 32, W_TMA = (NPROD + NEPI) / 32, W_MMA = W_TMA + 1;
 constexpr int TC_THREADS = NPROD + NEPI + 64;
 constexpr unsigned SPIN_LIMIT = 1u << 22;
 
@@ -114,7 +115,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void producer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(256) : "memory"); }
+__device__ __forceinline__ void producer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -175,6 +176,26 @@ __device__ __forceinline__ void tc_mma_x3(unsigned d0, unsigned long long a_hi, 
       "@p2 tcgen05.mma.cta_group::1.kind::f16 [d1], a1_hi, b_lo, %5, 1;\n\t"
       "}" ::"r"(d0),
       "l"(a_hi), "l"(b_hi), "r"(a_sub), "r"(b_sub), "r"(idesc), "r"(accumulate), "r"(two_tiles), "r"(dcol)
+      : "memory");
+}
+// single m-tile variant (Cout > 128: one 128-row tile per CTA item)
+__device__ __forceinline__ void tc_mma_x3_single(unsigned d0, unsigned long long a_hi, unsigned long long b_hi,
+                                                 unsigned a_sub, unsigned b_sub, unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pacc;\n\t"
+      ".reg .b64 a_lo, b_lo, t64;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pacc, %6, 0;\n\t"
+      "cvt.u64.u32 t64, %3;\n\t"
+      "add.u64 a_lo, %1, t64;\n\t"
+      "cvt.u64.u32 t64, %4;\n\t"
+      "add.u64 b_lo, %2, t64;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, pacc;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a_lo, %2, %5, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b_lo, %5, 1;\n\t"
+      "}" ::"r"(d0),
+      "l"(a_hi), "l"(b_hi), "r"(a_sub), "r"(b_sub), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&r)[16]) {
@@ -245,6 +266,57 @@ static void tc_pack_rows(const float* w, void* packed, int cin_real, int cin_pad
   if (blocks > 8192) blocks = 8192;
   if (blocks < 1) blocks = 1;
   tc_pack_weight_kernel<<<blocks, 128, 0, st>>>(w, (uint4*)packed, cin_real, cin_pad, rows, K, co_begin, cout_total);
+}
+
+// Generic epilogue for W (16 or 32) accumulator columns of one row: every independent global load
+// (residual, and the accumulate read-modify-write) is issued before the TMEM load is waited for, so
+// W (2W) requests per thread are in flight.
+template <int W>
+__device__ __forceinline__ void epi_generic(const TcK& p, unsigned taddr, const float* __restrict__ bias_s, int col,
+                                            const float* rq, float* yq, long long st, bool tv) {
+  unsigned r[W];
+  {
+    unsigned (&r0)[16] = *reinterpret_cast<unsigned (*)[16]>(&r[0]);
+    tc_ld16(taddr, r0);
+    if (W == 32) {
+      unsigned (&r1)[16] = *reinterpret_cast<unsigned (*)[16]>(&r[W == 32 ? 16 : 0]);
+      tc_ld16(taddr + 16, r1);
+    }
+  }
+  float rv[W];
+  if (rq && tv) {
+    const float* q = rq;
+#pragma unroll
+    for (int j = 0; j < W; ++j, q += st) rv[j] = __ldg(q);
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; ++j) rv[j] = 0.f;
+  }
+  tc_wait_ld();
+  if (!tv) return;
+  float* q = yq;
+  if (p.accumulate) {
+    float yv[W];
+    const float* q2 = yq;
+#pragma unroll
+    for (int j = 0; j < W; ++j, q2 += st) yv[j] = *q2;
+#pragma unroll
+    for (int j = 0; j < W; ++j, q += st) {
+      float v = __uint_as_float(r[j]) + bias_s[col + j];
+      if (p.post_act != PWGB_ACT_NONE) v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
+      *q = (v + rv[j]) * p.out_scale + yv[j];
+    }
+  } else if (p.post_act == PWGB_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < W; ++j, q += st) *q = (__uint_as_float(r[j]) + bias_s[col + j] + rv[j]) * p.out_scale;
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; ++j, q += st) {
+      float v = __uint_as_float(r[j]) + bias_s[col + j];
+      v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
+      *q = (v + rv[j]) * p.out_scale;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ main kernel
@@ -361,7 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 17) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((unsigned)p.tmem_cols)
                  : "memory");
@@ -374,7 +446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
 
-  if (warp < 8 && p.ns > 0) {
+  if (warp < W_EPI0 && p.ns > 0) {
     // ===================== A producers, cp.async-staged =====================
     // The raw fp32 chunk q+1 streams into shared memory (no registers held, any padding policy by
     // per-element addressing, zero-fill through src-size 0) while chunk q is converted to the bf16
@@ -462,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_arrive(A_FULL(buf));
       producer_barrier();  // raw[q % ns] may be overwritten by issue(q + 2)
     }
-  } else if (warp < 8) {
+  } else if (warp < W_EPI0) {
     // ===================== A producers, direct register path =====================
     unsigned ca = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -497,13 +569,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_arrive(A_FULL(buf));
       }
     }
-  } else if (warp < 16) {
+  } else if (warp < W_TMA) {
     // ===================== epilogue =====================
-    // 8 warps: lane quarter = warp % 4 (hardware TMEM access rule), column half = (warp - 8) / 4
+    // 8 warps: lane quarter = warp % 4 (hardware TMEM access rule), column half = (warp - W_EPI0) / 4
     const int ew = warp & 3;
     const int ngroups = p.Cout / 16;
-    const int col_begin = ((warp - 8) >> 2) ? (ngroups / 2) * 16 : 0;
-    const int col_end = ((warp - 8) >> 2) ? p.Cout : (ngroups / 2) * 16;
+    const int col_begin = ((warp - W_EPI0) >> 2) ? (ngroups / 2) * 16 : 0;
+    const int col_end = ((warp - W_EPI0) >> 2) ? p.Cout : (ngroups / 2) * 16;
     const int m = ew * 32 + lane;
     unsigned it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -567,54 +639,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           // address recomputation), every independent load of a 16-column group issued before use
           float* yq = y + (long long)b * p.ybs + (long long)(p.co_off + col_begin) * st + t;
           const float* rq = res ? res + (long long)b * p.rbs + (long long)(p.co_off + col_begin) * st + t : nullptr;
-          for (int col = col_begin; col < col_end; col += 16, yq += 16 * st) {
-            unsigned r[16];
-            tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
-            float rv[16];
-            if (rq) {
-              if (tv) {
-                const float* q = rq;
-#pragma unroll
-                for (int j = 0; j < 16; ++j, q += st) rv[j] = __ldg(q);
-              }
-              rq += 16 * st;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) rv[j] = 0.f;
-            }
-            tc_wait_ld();
-            if (tv) {
-              float* q = yq;
-              if (p.accumulate) {  // MRF sum (1 conv in 6): read-modify-write, loads batched first
-                float yv[16];
-                const float* q2 = yq;
-#pragma unroll
-                for (int j = 0; j < 16; ++j, q2 += st) yv[j] = *q2;
-#pragma unroll
-                for (int j = 0; j < 16; ++j, q += st) {
-                  float v = __uint_as_float(r[j]) + bias_s[col + j];
-                  if (p.post_act != PWGB_ACT_NONE) v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
-                  *q = (v + rv[j]) * p.out_scale + yv[j];
-                }
-              } else if (p.post_act == PWGB_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j, q += st) *q = (__uint_as_float(r[j]) + bias_s[col + j] + rv[j]) * p.out_scale;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j, q += st) {
-                  float v = __uint_as_float(r[j]) + bias_s[col + j];
-                  v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
-                  *q = (v + rv[j]) * p.out_scale;
-                }
-              }
-            }
+          int col = col_begin;
+          for (; col + 32 <= col_end; col += 32, yq += 32 * st) {
+            epi_generic<32>(p, tacc + (unsigned)(mt * p.Cout + col), bias_s, col, rq, yq, st, tv);
+            if (rq) rq += 32 * st;
+          }
+          for (; col < col_end; col += 16, yq += 16 * st) {
+            epi_generic<16>(p, tacc + (unsigned)(mt * p.Cout + col), bias_s, col, rq, yq, st, tv);
+            if (rq) rq += 16 * st;
           }
         }
       }
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(as));  // accumulator set drained: the MMA warp may overwrite it
     }
-  } else if (warp == 16) {
+  } else if (warp == W_TMA) {
     // ===================== B producer (TMA bulk copies of packed weight stages) =====================
     {
       const int per_tile = p.nchunks * p.K + p.nchunks2;
@@ -664,8 +703,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               const unsigned ak = a16 + (unsigned)(2 * ks) * p.R + tap_row;
               const unsigned long long b_hi = hi_const | (unsigned long long)(b_lo + bk);
               const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + ak);
-              tc_mma_x3(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, (c | k | ks) != 0 ? 1u : 0u,
-                        p.MT > 1 ? 1u : 0u, (unsigned)p.Cout);
+              if (p.MT > 1)
+                tc_mma_x3(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, (c | k | ks) != 0 ? 1u : 0u, 1u, (unsigned)p.Cout);
+              else
+                tc_mma_x3_single(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, (c | k | ks) != 0 ? 1u : 0u);
             }
             tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
           }
@@ -676,7 +717,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   }
   __syncthreads();
-  if (warp == 17) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols)
                  : "memory");
