@@ -26,8 +26,8 @@ namespace pwgb {
 
 constexpr int KC = 32;  // input channels per activation chunk / weight stage (2 UMMA K-steps).  KC = 16 was
                         // measured slower (22.3 vs 18.5 ms / step): the per-stage barrier round trip dominates
-constexpr int NPROD = 128;  // producer threads (warps 0-3)
-constexpr int NEPI = 256;   // epilogue threads (warps 4-11)
+constexpr int NPROD = 256;  // producer threads (warps 0-7); 4 warps measured slower (conversion-bound)
+constexpr int NEPI = 256;   // epilogue threads (warps 8-15)
 constexpr int W_EPI0 = NPROD / 32, W_TMA = (NPROD + NEPI) / 32, W_MMA = W_TMA + 1;
 constexpr int TC_THREADS = NPROD + NEPI + 64;
 constexpr unsigned SPIN_LIMIT = 1u << 22;
@@ -640,10 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           float* yq = y + (long long)b * p.ybs + (long long)(p.co_off + col_begin) * st + t;
           const float* rq = res ? res + (long long)b * p.rbs + (long long)(p.co_off + col_begin) * st + t : nullptr;
           int col = col_begin;
-          for (; col + 32 <= col_end; col += 32, yq += 32 * st) {
-            epi_generic<32>(p, tacc + (unsigned)(mt * p.Cout + col), bias_s, col, rq, yq, st, tv);
-            if (rq) rq += 32 * st;
-          }
+          // (32-column groups were tried: they spill at the 112-register budget of 576 threads)
           for (; col < col_end; col += 16, yq += 16 * st) {
             epi_generic<16>(p, tacc + (unsigned)(mt * p.Cout + col), bias_s, col, rq, yq, st, tv);
             if (rq) rq += 16 * st;
