@@ -97,9 +97,11 @@ PWGB_API int pwgb_conv1d_forward(const pwgb_conv1d_desc* d, const float* x, cons
  * pwgb_conv_transpose1d_workspace() bytes.  t_out = (t_in-1)*s - 2p + k + op.
  * ---------------------------------------------------------------------- */
 typedef struct pwgb_convtr1d_desc {
-  int32_t batch, cin, cout, t_in, t_out;
+  int32_t batch, cin, cout, t_in, t_out; /* t_in / t_out in rows (per period column) */
   int32_t kernel, stride, padding;
   float pre_slope;
+  int32_t groups; /* 0 or 1 = dense; w is (cin, cout/groups, kernel)                         */
+  int32_t period; /* 0 or 1 = plain; P > 1 = transposed Conv2d (k,1) on (B, C, rows, P) views  */
 } pwgb_convtr1d_desc;
 PWGB_API size_t pwgb_conv_transpose1d_workspace(const pwgb_convtr1d_desc* d);
 PWGB_API int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const float* x, const float* w, const float* bias,
@@ -193,6 +195,39 @@ PWGB_API int pwgb_reduce_mean_forward(int mode, const float* x, const float* y, 
                              int accumulate, float* out, float* ws, int ws_floats, void* stream);
 PWGB_API int pwgb_avg_pool1d_forward(const float* x, float* y, int rows, int t_in, int kernel, int stride, int padding,
                             int count_include_pad, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Backward building blocks of the train step (bin/train.py:287-288, 327-328 `loss.backward()`).
+ * Data gradients reuse the forward entry points: the dgrad of a stride-1 conv is the conv1d forward entry point (FFMA or tcgen05)
+ * with the transposed, tap-flipped weight; the dgrad of a strided / grouped / period conv is
+ * pwgb_conv_transpose1d_forward (groups / period fields); the dgrad of a conv-transpose is a strided
+ * pwgb_conv1d_forward.  New here:
+ *   pwgb_conv1d_wgrad: dw[co, ci, k] (+)= sum_{b,t} lrelu_g(gy[b,co,t]) * pre(x)[b, ci, t*stride + k*dil - pad]
+ *     for the conv described by `d` (same descriptor as the forward; d->pre_slope is applied to x,
+ *     g_slope to gy -- 1 except for the conv-transpose weight gradient); deterministic split reduce.
+ *   pwgb_act_backward:  out (+)= g * scale * f'(ref)   mode 0 LeakyReLU mask (ref > 0), 1 tanh (ref = output), 2 copy
+ *   pwgb_bias_grad:     db[c] (+)= sum_{b,t} g[b,c,t]
+ *   pwgb_reduce_mean_backward / pwgb_avg_pool1d_backward: adjoints of the forward entry points
+ *   pwgb_axpby:         y = a*x + b*y
+ * ---------------------------------------------------------------------- */
+PWGB_API size_t pwgb_conv1d_wgrad_workspace(const pwgb_conv1d_desc* d);
+PWGB_API int pwgb_conv1d_wgrad(const pwgb_conv1d_desc* d, const float* x, const float* gy, float g_slope, float* dw,
+                      int accumulate, void* ws, size_t ws_bytes, void* stream);
+PWGB_API int pwgb_act_backward(int mode, const float* g, const float* ref, float* out, long long n, float slope, float scale,
+                      int accumulate, void* stream);
+PWGB_API int pwgb_bias_grad(const float* g, float* db, int batch, int channels, long long len, int accumulate, void* stream);
+PWGB_API int pwgb_reduce_mean_backward(int mode, const float* x, const float* y, long long n, float c, float s, float weight,
+                              const float* gout, float* gx, int accumulate, void* stream);
+PWGB_API int pwgb_avg_pool1d_backward(const float* gy, float* gx, int rows, int t_in, int kernel, int stride, int padding,
+                             int count_include_pad, void* stream);
+PWGB_API int pwgb_axpby(long long n, float a, const float* x, float b, float* y, void* stream);
+/* adjoints of pwgb_stft_amplitude_forward (dx must be zero-initialised by the caller; frames overlap
+ * so it is accumulated with atomics) and of the loss branch of pwgb_mel_project_forward. */
+PWGB_API int pwgb_stft_amplitude_backward(const pwgb_stft_desc* d, const float* x, const float* window, const float* amp,
+                                 const float* damp, float* dx, void* stream);
+PWGB_API int pwgb_mel_project_backward(int batch, int frames, int bins, int n_mels, const float* amp_x, const float* amp_y,
+                              const float* melmat, float eps, float log_scale, const float* gout, float* damp_x,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,228 @@
+"""torch.autograd glue for the train step (bin/train.py:189-340): every Function's forward AND
+backward run libpwgb kernels.  Data gradients reuse the forward kernels (dgrad of a stride-1 conv =
+conv with the transposed, tap-flipped weight -> tcgen05 path; dgrad of a strided conv = poly-phase
+conv-transpose); weight gradients use pwgb_conv1d_wgrad.  Weight / spectral-norm
+re-parametrisation stays in PyTorch on the (tiny) weight tensors, so its backward is PyTorch's."""
+import ctypes as C
+
+import torch
+
+from . import capi, ops
+from .capi import PwgbError
+
+
+def _pair(p):
+    return (p, p) if isinstance(p, int) else (int(p[0]), int(p[1]))
+
+
+class Conv1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, residual, stride, padding, dilation, groups, pad_mode, pre_slope, post_act, post_slope,
+                out_scale, period):
+        if pad_mode != "zero":
+            raise PwgbError("training through reflect/replicate padded convs has no backward kernel yet")
+        y = ops.conv1d_raw(x, w, bias, stride=stride, padding=padding, dilation=dilation, groups=groups, pad_mode=pad_mode,
+                           pre_slope=pre_slope, post_act=post_act, post_slope=post_slope, residual=residual,
+                           out_scale=out_scale, period=period)
+        ctx.cfg = (stride, _pair(padding), dilation, groups, pre_slope, post_act, post_slope, out_scale, period)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.w3 = (w.shape[0], w.shape[1], w.shape[2])
+        ctx.w_shape = tuple(w.shape)
+        ctx.x_shape = tuple(x.shape)
+        ctx.save_for_backward(x, w, y if post_act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        stride, (pl, pr), dil, groups, pre_slope, post_act, post_slope, out_scale, P = ctx.cfg
+        gy = gy.contiguous()
+        need_x, need_w, need_b, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        g_res = None
+        if ctx.has_res and need_r:
+            g_res = gy if out_scale == 1.0 else ops.act_backward("scale", gy, scale=out_scale)
+        if post_act == "tanh":
+            gz = ops.act_backward("tanh", gy, y, scale=out_scale)
+        elif post_act == "lrelu":
+            gz = ops.act_backward("lrelu", gy, y, slope=post_slope, scale=out_scale)
+        elif out_scale != 1.0:
+            gz = ops.act_backward("scale", gy, scale=out_scale)
+        else:
+            gz = gy
+        cout, cin_g, K = ctx.w3
+        w3 = w.reshape(cout, cin_g, K)
+        gb = ops.bias_grad(gz, cout) if (ctx.has_bias and need_b) else None
+        gw = None
+        if need_w:
+            gw = ops.conv1d_wgrad(x, gz, ctx.w3, stride=stride, padding=pl, dilation=dil, groups=groups, x_slope=pre_slope, period=P)
+            gw = gw.reshape(ctx.w_shape)
+        gx = None
+        if need_x:
+            B, cin = x.shape[0], x.shape[1]
+            L = x.numel() // (B * cin)
+            t_in = (L + P - 1) // P
+            t_out = gz.numel() // (B * cout * P)
+            if stride == 1:
+                # dgrad = conv of gz with the transposed, tap-flipped weight (layout change on the weight only)
+                cout_g = cout // groups
+                wt = w3.detach().reshape(groups, cout_g, cin_g, K).transpose(1, 2).flip(-1).reshape(groups * cin_g, cout_g, K).contiguous()
+                pl2 = dil * (K - 1) - pl
+                pr2 = t_in - t_out - pl2 + dil * (K - 1)
+                gxe = ops.conv1d_raw(gz, wt, None, padding=(pl2, pr2), dilation=dil, groups=groups, period=P)
+            else:
+                if dil != 1 or pl != pr:
+                    raise PwgbError("backward of a strided conv with dilation / asymmetric padding is not supported")
+                op = t_in - ((t_out - 1) * stride - 2 * pl + K)
+                if not 0 <= op < stride:
+                    raise PwgbError("strided dgrad: inconsistent lengths")
+                gxe = ops.conv_transpose1d_raw(gz, w3.detach(), None, stride=stride, padding=pl, output_padding=op, groups=groups, period=P)
+            if pre_slope != 1.0:
+                if P > 1 and t_in * P != L:
+                    raise PwgbError("pre-activation on a reflect-extended period input is not supported")
+                ops.act_backward("lrelu", gxe, x, slope=pre_slope, out=gxe)
+            if P > 1 and t_in * P != L:
+                # first MPD layer: fold the reflect extension back (hifigan.py:365-369): x_ext[T+m] = x[T-2-m]
+                flat = gxe.reshape(B, cin, t_in * P)
+                gx = flat[:, :, :L].contiguous()
+                n_pad = t_in * P - L
+                idx = torch.arange(L - 2, L - 2 - n_pad, -1, device=gx.device)
+                gx[:, :, idx] += flat[:, :, L:]
+                gx = gx.reshape(ctx.x_shape)
+            else:
+                gx = gxe.reshape(ctx.x_shape)
+        return gx, gw, gb, g_res, None, None, None, None, None, None, None, None, None, None
+
+
+def conv1d(x, w, bias=None, *, stride=1, padding=0, dilation=1, groups=1, pad_mode="zero", pre_slope=1.0, pre_gate=False,
+           post_act=None, post_slope=0.0, residual=None, out_scale=1.0, out=None, accumulate=False, period=1):
+    if pre_gate or out is not None or accumulate:
+        raise PwgbError("gate / in-place accumulate variants are inference-only (no backward kernel)")
+    return Conv1dFn.apply(x, w, bias, residual, stride, padding, dilation, groups, pad_mode, float(pre_slope), post_act,
+                          float(post_slope), float(out_scale), int(period))
+
+
+class ConvTranspose1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, padding, output_padding, pre_slope):
+        y = ops.conv_transpose1d_raw(x, w, bias, stride=stride, padding=padding, output_padding=output_padding, pre_slope=pre_slope)
+        ctx.cfg = (stride, padding, output_padding, pre_slope)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding, _, pre_slope = ctx.cfg
+        gy = gy.contiguous()
+        cin, cout, K = w.shape
+        gb = ops.bias_grad(gy, cout) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            # dw[ci, co, k] = sum_t lrelu(x)[ci, t] * gy[co, t*s - p + k]: the conv wgrad with the roles of the
+            # two operands swapped ("x" = gy, gradient operand = pre-activated x)
+            gw = ops.conv1d_wgrad(gy, x, (cin, cout, K), stride=stride, padding=padding, g_slope=pre_slope)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.conv1d_raw(gy, w.detach(), None, stride=stride, padding=padding)  # (cin, cout, K) read as a conv weight
+            if gx.shape[-1] != x.shape[-1]:
+                raise PwgbError("conv_transpose dgrad: length mismatch")
+            if pre_slope != 1.0:
+                ops.act_backward("lrelu", gx, x, slope=pre_slope, out=gx)
+        return gx, gw, gb, None, None, None, None
+
+
+def conv_transpose1d(x, w, bias=None, *, stride, padding=0, output_padding=0, pre_slope=1.0, groups=1, period=1):
+    if groups != 1 or period != 1:
+        raise PwgbError("grouped / period conv_transpose is only used as a dgrad (no second-order support)")
+    return ConvTranspose1dFn.apply(x, w, bias, stride, padding, output_padding, float(pre_slope))
+
+
+class AvgPool1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel_size, stride, padding, count_include_pad):
+        ctx.cfg = (kernel_size, stride, padding, count_include_pad, x.shape)
+        return ops.avg_pool1d_raw(x, kernel_size, stride, padding, count_include_pad)
+
+    @staticmethod
+    def backward(ctx, gy):
+        k, s, p, inc, shape = ctx.cfg
+        gy = gy.contiguous()
+        gx = torch.empty(shape, device=gy.device, dtype=torch.float32)
+        rc = capi.lib().pwgb_avg_pool1d_backward(ops._p(gy), ops._p(gx), shape[0] * shape[1], shape[2], int(k), int(s), int(p),
+                                                 int(bool(inc)), ops._stream())
+        capi.check(rc, "pwgb_avg_pool1d_backward")
+        return gx, None, None, None, None
+
+
+class ReduceMeanFn(torch.autograd.Function):
+    """weight * mean f(x [, y]) as a 1-element tensor (GAN loss terms)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mode, c, s, weight):
+        ctx.cfg = (mode, c, s, weight)
+        ctx.save_for_backward(x, y)
+        return ops.reduce_mean_raw(mode, x, y, c, s, weight)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, y = ctx.saved_tensors
+        mode, c, s, weight = ctx.cfg
+        gout = gout.contiguous().reshape(1)
+        gx = torch.empty_like(x)
+        xc = x.contiguous()
+        rc = capi.lib().pwgb_reduce_mean_backward(ops._REDUCE[mode], ops._p(xc), ops._p(y.contiguous()) if y is not None else None,
+                                                  x.numel(), c, s, weight, ops._p(gout), ops._p(gx), 0, ops._stream())
+        capi.check(rc, "pwgb_reduce_mean_backward")
+        gy = None
+        if y is not None and ctx.needs_input_grad[1]:
+            gy = ops.act_backward("scale", gx, scale=-1.0)
+        return gx, gy, None, None, None, None
+
+
+class MelLossFn(torch.autograd.Function):
+    """MelSpectrogramLoss.forward (losses/mel_loss.py:150-165); gradient w.r.t. the generated signal only."""
+
+    @staticmethod
+    def forward(ctx, y_hat, y, melmat, window, fft_size, hop_size, win_length, eps, log_scale):
+        ax, ay = ops.stft_amplitude(y_hat, y, fft_size, hop_size, win_length, window, eps)
+        _, loss = ops.mel_project(ax, ay, melmat, eps, log_scale, want_mel=False, want_loss=True)
+        ctx.cfg = (fft_size, hop_size, win_length, eps, log_scale)
+        ctx.save_for_backward(y_hat, ax, ay, melmat, window)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        y_hat, ax, ay, melmat, window = ctx.saved_tensors
+        fft_size, hop_size, win_length, eps, log_scale = ctx.cfg
+        B, frames, bins = ax.shape
+        L = capi.lib()
+        gout = gout.contiguous().reshape(1)
+        dax = torch.empty_like(ax)
+        rc = L.pwgb_mel_project_backward(B, frames, bins, melmat.shape[1], ops._p(ax), ops._p(ay), ops._p(melmat), float(eps),
+                                         float(log_scale), ops._p(gout), ops._p(dax), ops._stream())
+        capi.check(rc, "pwgb_mel_project_backward")
+        d = capi.StftDesc(batch=B, t=y_hat.shape[1], n_fft=int(fft_size), hop=int(hop_size), win_length=int(win_length), clamp_eps=float(eps))
+        dx = torch.zeros_like(y_hat)
+        rc = L.pwgb_stft_amplitude_backward(C.byref(d), ops._p(y_hat), ops._p(window), ops._p(ax), ops._p(dax), ops._p(dx), ops._stream())
+        capi.check(rc, "pwgb_stft_amplitude_backward")
+        return dx, None, None, None, None, None, None, None, None
+
+
+class ScaledSumFn(torch.autograd.Function):
+    """sum_i a * x_i (the MRF average cs / num_blocks of hifigan.py:187-190) -- pwgb_axpby."""
+
+    @staticmethod
+    def forward(ctx, a, *xs):
+        ctx.a = a
+        ctx.n = len(xs)
+        out = torch.empty_like(xs[0])
+        for i, x in enumerate(xs):
+            ops.axpby(a, x, 0.0 if i == 0 else 1.0, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gs = ops.act_backward("scale", g.contiguous(), scale=ctx.a)
+        return (None,) + (gs,) * ctx.n

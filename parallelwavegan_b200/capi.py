@@ -29,6 +29,7 @@ class ConvTr1dDesc(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("t_in", C.c_int32), ("t_out", C.c_int32),
         ("kernel", C.c_int32), ("stride", C.c_int32), ("padding", C.c_int32), ("pre_slope", C.c_float),
+        ("groups", C.c_int32), ("period", C.c_int32),
     ]
 
 
@@ -102,6 +103,24 @@ def lib():
     L.pwgb_reduce_mean_forward.argtypes = [C.c_int, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, C.c_int, vp]
     L.pwgb_avg_pool1d_forward.restype = C.c_int
     L.pwgb_avg_pool1d_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.pwgb_conv1d_wgrad_workspace.restype = C.c_size_t
+    L.pwgb_conv1d_wgrad_workspace.argtypes = [C.POINTER(Conv1dDesc)]
+    L.pwgb_conv1d_wgrad.restype = C.c_int
+    L.pwgb_conv1d_wgrad.argtypes = [C.POINTER(Conv1dDesc), vp, vp, C.c_float, vp, C.c_int, vp, C.c_size_t, vp]
+    L.pwgb_act_backward.restype = C.c_int
+    L.pwgb_act_backward.argtypes = [C.c_int, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_int, vp]
+    L.pwgb_bias_grad.restype = C.c_int
+    L.pwgb_bias_grad.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, C.c_int, vp]
+    L.pwgb_reduce_mean_backward.restype = C.c_int
+    L.pwgb_reduce_mean_backward.argtypes = [C.c_int, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, vp, vp, C.c_int, vp]
+    L.pwgb_avg_pool1d_backward.restype = C.c_int
+    L.pwgb_avg_pool1d_backward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.pwgb_axpby.restype = C.c_int
+    L.pwgb_axpby.argtypes = [C.c_longlong, C.c_float, vp, C.c_float, vp, vp]
+    L.pwgb_stft_amplitude_backward.restype = C.c_int
+    L.pwgb_stft_amplitude_backward.argtypes = [C.POINTER(StftDesc), vp, vp, vp, vp, vp, vp]
+    L.pwgb_mel_project_backward.restype = C.c_int
+    L.pwgb_mel_project_backward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp]
     _lib = L
     return L
 
@@ -128,4 +147,7 @@ EXPORTED_SYMBOLS = [
     "pwgb_wavenet_pack", "pwgb_wavenet_layer_forward", "pwgb_upsample_fir_forward",
     "pwgb_mr_stft_loss_workspace", "pwgb_mr_stft_loss_forward", "pwgb_stft_amplitude_forward",
     "pwgb_mel_project_forward", "pwgb_reduce_mean_forward", "pwgb_avg_pool1d_forward",
+    "pwgb_conv1d_wgrad_workspace", "pwgb_conv1d_wgrad", "pwgb_act_backward", "pwgb_bias_grad",
+    "pwgb_reduce_mean_backward", "pwgb_avg_pool1d_backward", "pwgb_axpby",
+    "pwgb_stft_amplitude_backward", "pwgb_mel_project_backward",
 ]

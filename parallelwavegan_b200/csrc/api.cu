@@ -44,6 +44,6 @@ extern "C" int pwgb_conv1d_forward(const pwgb_conv1d_desc* d, const float* x, co
   const long long need = (long long)(d->t_out - 1) * d->stride + (long long)(d->kernel - 1) * d->dilation + 1 - d->pad_left;
   PWGB_CHECK_ARG(d->t_out == 0 || need <= (long long)d->t_in + (d->pad_mode == PWGB_PAD_ZERO ? (1LL << 30) : d->t_in - 1),
                  "conv1d: t_out too large for t_in");
-  PWGB_CHECK_ARG(d->shuffle <= 1 || (d->cout % d->shuffle == 0 && P == 1 && !residual), "conv1d: bad shuffle");
+  PWGB_CHECK_ARG(d->shuffle <= 1 || (d->cout % d->shuffle == 0 && !residual), "conv1d: bad shuffle");
   return conv1d_forward_simt(d, x, w, bias, residual, y, (cudaStream_t)stream);
 }

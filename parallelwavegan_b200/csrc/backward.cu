@@ -1,0 +1,325 @@
+// Backward building blocks for the train step (bin/train.py:189-340 calls loss.backward()):
+//   * wgrad of the generic fused Conv1d (any stride / dilation / groups / period view),
+//     deterministic two-stage split reduction;
+//   * data gradients reuse the FORWARD kernels (a stride-1 dgrad is a conv with the transposed,
+//     tap-flipped weight -> tcgen05 path; a strided dgrad is the poly-phase conv-transpose), so only
+//     the elementwise chain-rule pieces live here: activation masks, bias sums, loss / pooling grads.
+#include "common.cuh"
+
+namespace pwgb {
+
+// ------------------------------------------------------------------ wgrad
+struct WgK {
+  int B, Cin, Cout, Cin_g, Cout_g, groups;
+  int t_in, t_out, K, S, D, padL, pad_mode, P, t_valid;
+  int Lin, Lout;
+  float x_slope;   // LeakyReLU applied to x on load (the conv's fused pre-activation)
+  float g_slope;   // LeakyReLU applied to the gradient operand on load (conv-transpose wgrad)
+  long long xcs;
+  int nsplit, chunks_per_seq, XW, ci_tiles;
+};
+
+constexpr int WG_CO = 32, WG_CI = 8, WG_K = 8, WG_T = 128;
+
+// partial[split][co][ci_g][k] += sum over this split's (batch, chunk) items of g[co,o] * x~[ci, src(o,k)]
+__global__ void __launch_bounds__(256) conv1d_wgrad_kernel(const WgK p, const float* __restrict__ x,
+                                                            const float* __restrict__ gy, float* __restrict__ part) {
+  extern __shared__ float sm[];
+  float* gs = sm;                         // WG_CO x (WG_T + 1)
+  float* xs = gs + WG_CO * (WG_T + 1);    // WG_CI x XW
+  int* xoff = reinterpret_cast<int*>(xs + WG_CI * p.XW);  // WG_T
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_co = ceil_div(p.Cout_g, WG_CO);
+  const int g = blockIdx.x / (tiles_co * p.ci_tiles);
+  const int rem = blockIdx.x - g * tiles_co * p.ci_tiles;
+  const int co0 = g * p.Cout_g + (rem / p.ci_tiles) * WG_CO;
+  const int ci0 = (rem % p.ci_tiles) * WG_CI;  // within group
+  const int k0 = blockIdx.y * WG_K;
+  const int split = blockIdx.z;
+  const int co = co0 + lane;
+  const bool co_ok = co < (g + 1) * p.Cout_g;
+  const int ci = ci0 + warp;
+  const bool ci_ok = ci < p.Cin_g;
+  float acc[WG_K];
+#pragma unroll
+  for (int k = 0; k < WG_K; ++k) acc[k] = 0.f;
+  const int kdp = p.D * p.P;
+  const int total_items = p.B * p.chunks_per_seq;
+  for (int item = split; item < total_items; item += p.nsplit) {
+    const int b = item / p.chunks_per_seq;
+    const int o0 = (item - b * p.chunks_per_seq) * WG_T;
+    const int to0 = o0 / p.P;
+    const long long row0 = (long long)to0 * p.S + (long long)k0 * p.D - p.padL;
+    __syncthreads();
+    for (int idx = tid; idx < WG_CO * WG_T; idx += 256) {
+      const int c = idx / WG_T, o = idx - c * WG_T;
+      const int cc = co0 + c;
+      float v = 0.f;
+      if (cc < (g + 1) * p.Cout_g && o0 + o < p.Lout) v = lrelu(gy[((long long)b * p.Cout + cc) * p.Lout + o0 + o], p.g_slope);
+      gs[c * (WG_T + 1) + o] = v;
+    }
+    for (int o = tid; o < WG_T; o += 256) {
+      const int oo = min(o0 + o, p.Lout - 1);
+      const int to = oo / p.P;
+      xoff[o] = (to - to0) * p.S * p.P + (oo - to * p.P);
+    }
+    for (int idx = tid; idx < WG_CI * p.XW; idx += 256) {
+      const int c = idx / p.XW, r = idx - c * p.XW;
+      long long li = row0 * p.P + r;
+      float v = 0.f;
+      bool ok = ci0 + c < p.Cin_g;
+      if (ok && (li < 0 || li >= p.Lin)) {
+        if (p.pad_mode == PWGB_PAD_ZERO) {
+          ok = false;
+        } else if (p.pad_mode == PWGB_PAD_REFLECT) {
+          li = li < 0 ? -li : 2LL * (p.Lin - 1) - li;
+          li = li < 0 ? 0 : (li >= p.Lin ? p.Lin - 1 : li);
+        } else {
+          li = li < 0 ? 0 : p.Lin - 1;
+        }
+      }
+      if (ok) {
+        if (li >= p.t_valid) li = 2LL * (p.t_valid - 1) - li;
+        if (li < 0) li = 0;
+        v = lrelu(x[((long long)b * p.Cin + g * p.Cin_g + ci0 + c) * p.xcs + li], p.x_slope);
+      }
+      xs[idx] = v;
+    }
+    __syncthreads();
+    if (co_ok && ci_ok) {
+      const float* gr = gs + lane * (WG_T + 1);
+      const float* xr = xs + warp * p.XW;
+      const int nv = min(WG_T, p.Lout - o0);
+      for (int o = 0; o < nv; ++o) {
+        const float gv = gr[o];
+        const float* xq = xr + xoff[o];
+#pragma unroll
+        for (int k = 0; k < WG_K; ++k) acc[k] = fmaf(gv, xq[k * kdp], acc[k]);
+      }
+    }
+  }
+  if (co_ok && ci_ok) {
+    float* dst = part + (((long long)split * p.Cout + co) * p.Cin_g + ci) * p.K + k0;
+#pragma unroll
+    for (int k = 0; k < WG_K; ++k)
+      if (k0 + k < p.K) dst[k] = acc[k];
+  }
+}
+
+__global__ void split_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int nsplit,
+                                    int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < nsplit; ++s) a += part[(long long)s * n + i];
+    out[i] = accumulate ? out[i] + a : a;
+  }
+}
+
+// ------------------------------------------------------------------ elementwise chain rule
+// mode 0: out = g * scale * (ref > 0 ? 1 : slope)      (LeakyReLU, mask from the input OR the output)
+// mode 1: out = g * scale * (1 - ref^2)                (tanh, ref = output)
+// mode 2: out = g * scale                              (plain scale / copy)
+__global__ void act_backward_kernel(int mode, const float* __restrict__ g, const float* __restrict__ ref,
+                                    float* __restrict__ out, long long n, float slope, float scale, int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = g[i] * scale;
+    if (mode == 0)
+      v *= ref[i] > 0.f ? 1.f : slope;
+    else if (mode == 1)
+      v *= 1.f - ref[i] * ref[i];
+    out[i] = accumulate ? out[i] + v : v;
+  }
+}
+
+// db[c] = sum_{b, t} g[b, c, t]   (one CTA per channel, fixed order)
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ g, float* __restrict__ db, int B, int C,
+                                                         long long L, int accumulate) {
+  __shared__ double red[256];
+  const int c = blockIdx.x;
+  double a = 0;
+  for (int b = 0; b < B; ++b) {
+    const float* q = g + ((long long)b * C + c) * L;
+    for (long long i = threadIdx.x; i < L; i += 256) a += q[i];
+  }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) db[c] = (accumulate ? db[c] : 0.f) + (float)red[0];
+}
+
+// gradient of pwgb_reduce_mean_forward: gx = gout[0] * weight / n * f'(x [, y])  (+ optional gy = -gx for L1)
+__global__ void reduce_mean_backward_kernel(int mode, const float* __restrict__ x, const float* __restrict__ y, long long n,
+                                            float c, float s, float weight, const float* __restrict__ gout,
+                                            float* __restrict__ gx, int accumulate) {
+  const float go = gout[0] * weight / (float)n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    float d;
+    if (mode == 0)
+      d = 2.f * (v - c);
+    else if (mode == 1)
+      d = v > y[i] ? 1.f : (v < y[i] ? -1.f : 0.f);
+    else if (mode == 2)
+      d = (c - s * v) > 0.f ? -s : 0.f;
+    else
+      d = s;
+    gx[i] = (accumulate ? gx[i] : 0.f) + go * d;
+  }
+}
+
+// AvgPool1d backward: gx[r, i] = sum over windows o containing i of gy[r, o] / div(o)
+__global__ void avg_pool1d_backward_kernel(const float* __restrict__ gy, float* __restrict__ gx, int rows, int t_in,
+                                           int t_out, int k, int s, int pad, int include_pad) {
+  const int r = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t_in; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    // windows o with o*s - pad <= i < o*s - pad + k
+    int o_hi = (i + pad) / s;
+    int o_lo = (i + pad - k + s) / s;
+    if (i + pad - k + 1 <= 0) o_lo = 0;
+    if (o_lo < 0) o_lo = 0;
+    if (o_hi > t_out - 1) o_hi = t_out - 1;
+    for (int o = o_lo; o <= o_hi; ++o) {
+      const int start = o * s - pad;
+      if (i < start || i >= start + k) continue;
+      int div;
+      if (include_pad) {
+        div = min(start + k, t_in + pad) - start;
+      } else {
+        div = min(start + k, t_in) - max(start, 0);
+      }
+      acc += gy[(long long)r * t_out + o] / (float)div;
+    }
+    gx[(long long)r * t_in + i] = acc;
+  }
+}
+
+// y = a * x + b * y
+__global__ void axpby_kernel(long long n, float a, const float* __restrict__ x, float b, float* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
+}
+
+static int grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+}
+
+}  // namespace pwgb
+
+using namespace pwgb;
+
+static int wg_fill(const pwgb_conv1d_desc* d, WgK& p) {
+  if (!d || d->batch < 0 || d->cin <= 0 || d->cout <= 0 || d->groups <= 0 || d->cin % d->groups || d->cout % d->groups ||
+      d->kernel <= 0 || d->stride <= 0 || d->dilation <= 0 || d->t_in <= 0 || d->t_out < 0)
+    return 0;
+  p.B = d->batch;
+  p.Cin = d->cin;
+  p.Cout = d->cout;
+  p.groups = d->groups;
+  p.Cin_g = d->cin / d->groups;
+  p.Cout_g = d->cout / d->groups;
+  p.t_in = d->t_in;
+  p.t_out = d->t_out;
+  p.K = d->kernel;
+  p.S = d->stride;
+  p.D = d->dilation;
+  p.padL = d->pad_left;
+  p.pad_mode = d->pad_mode;
+  p.P = d->period < 1 ? 1 : d->period;
+  p.Lin = d->t_in * p.P;
+  p.Lout = d->t_out * p.P;
+  p.t_valid = d->t_valid > 0 ? d->t_valid : p.Lin;
+  p.xcs = p.t_valid;
+  p.x_slope = d->pre_slope;
+  p.g_slope = 1.f;
+  p.chunks_per_seq = ceil_div(p.Lout, WG_T);
+  const long long items = (long long)p.B * p.chunks_per_seq;
+  p.nsplit = (int)(items < 32 ? (items < 1 ? 1 : items) : 32);
+  const int nrows_out = (WG_T + p.P - 2) / p.P + 1;
+  const long long NR = (long long)(nrows_out - 1) * p.S + (long long)(WG_K - 1) * p.D + 1;
+  p.XW = (int)(NR * p.P);
+  p.ci_tiles = ceil_div(p.Cin_g, WG_CI);
+  return 1;
+}
+
+extern "C" size_t pwgb_conv1d_wgrad_workspace(const pwgb_conv1d_desc* d) {
+  WgK p;
+  if (!wg_fill(d, p)) return 0;
+  return (size_t)p.nsplit * d->cout * p.Cin_g * d->kernel * sizeof(float);
+}
+
+extern "C" int pwgb_conv1d_wgrad(const pwgb_conv1d_desc* d, const float* x, const float* gy, float g_slope, float* dw,
+                                 int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  PWGB_CHECK_ARG(d && x && gy && dw && ws, "conv1d_wgrad: null argument");
+  WgK p;
+  PWGB_CHECK_ARG(wg_fill(d, p), "conv1d_wgrad: bad descriptor");
+  PWGB_UNSUPPORTED_IF(d->pre_gate || d->shuffle > 1, "conv1d_wgrad: gate / shuffle variants are not supported");
+  p.g_slope = g_slope;
+  const size_t need = pwgb_conv1d_wgrad_workspace(d);
+  PWGB_CHECK_ARG(ws_bytes >= need, "conv1d_wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
+  const long long n = (long long)d->cout * p.Cin_g * d->kernel;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.B == 0 || p.Lout == 0) {
+    if (!accumulate) cudaMemsetAsync(dw, 0, n * sizeof(float), st);
+    return PWGB_OK;
+  }
+  const size_t smem = ((size_t)WG_CO * (WG_T + 1) + (size_t)WG_CI * p.XW + WG_T) * sizeof(float);
+  PWGB_UNSUPPORTED_IF(smem > 200 * 1024, "conv1d_wgrad: tile does not fit shared memory");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(conv1d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv1d_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PWGB_CUDA_ERROR;
+    }
+  }
+  dim3 grid(p.groups * ceil_div(p.Cout_g, WG_CO) * p.ci_tiles, ceil_div(p.K, WG_K), p.nsplit);
+  conv1d_wgrad_kernel<<<grid, 256, smem, st>>>(p, x, gy, (float*)ws);
+  int rc = check_launch("conv1d_wgrad_kernel");
+  if (rc) return rc;
+  split_reduce_kernel<<<grid_for(n), 256, 0, st>>>((const float*)ws, dw, n, p.nsplit, accumulate);
+  return check_launch("split_reduce_kernel");
+}
+
+extern "C" int pwgb_act_backward(int mode, const float* g, const float* ref, float* out, long long n, float slope,
+                                 float scale, int accumulate, void* stream) {
+  PWGB_CHECK_ARG(g && out && (ref || mode == 2) && n >= 0 && mode >= 0 && mode <= 2, "act_backward: bad arguments");
+  if (n == 0) return PWGB_OK;
+  act_backward_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(mode, g, ref, out, n, slope, scale, accumulate);
+  return check_launch("act_backward_kernel");
+}
+
+extern "C" int pwgb_bias_grad(const float* g, float* db, int batch, int channels, long long len, int accumulate,
+                              void* stream) {
+  PWGB_CHECK_ARG(g && db && batch >= 0 && channels > 0 && len >= 0, "bias_grad: bad arguments");
+  bias_grad_kernel<<<channels, 256, 0, (cudaStream_t)stream>>>(g, db, batch, channels, len, accumulate);
+  return check_launch("bias_grad_kernel");
+}
+
+extern "C" int pwgb_reduce_mean_backward(int mode, const float* x, const float* y, long long n, float c, float s,
+                                         float weight, const float* gout, float* gx, int accumulate, void* stream) {
+  PWGB_CHECK_ARG(x && gout && gx && n > 0 && mode >= 0 && mode <= 3 && (mode != 1 || y), "reduce_mean_backward: bad arguments");
+  reduce_mean_backward_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(mode, x, y, n, c, s, weight, gout, gx, accumulate);
+  return check_launch("reduce_mean_backward_kernel");
+}
+
+extern "C" int pwgb_avg_pool1d_backward(const float* gy, float* gx, int rows, int t_in, int kernel, int stride,
+                                        int padding, int count_include_pad, void* stream) {
+  PWGB_CHECK_ARG(gy && gx && rows >= 0 && t_in > 0 && kernel > 0 && stride > 0 && padding >= 0, "avg_pool1d_backward: bad arguments");
+  PWGB_UNSUPPORTED_IF(rows > 65535, "avg_pool1d_backward: too many rows");
+  if (rows == 0) return PWGB_OK;
+  const int t_out = (t_in + 2 * padding - kernel) / stride + 1;
+  dim3 grid(ceil_div(t_in, 256) < 64 ? ceil_div(t_in, 256) : 64, rows);
+  avg_pool1d_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gy, gx, rows, t_in, t_out, kernel, stride, padding, count_include_pad);
+  return check_launch("avg_pool1d_backward_kernel");
+}
+
+extern "C" int pwgb_axpby(long long n, float a, const float* x, float b, float* y, void* stream) {
+  PWGB_CHECK_ARG(x && y && n >= 0, "axpby: bad arguments");
+  if (n == 0) return PWGB_OK;
+  axpby_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
+  return check_launch("axpby_kernel");
+}

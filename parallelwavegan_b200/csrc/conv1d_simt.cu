@@ -175,9 +175,11 @@ __global__ void __launch_bounds__(256) conv1d_fwd_kernel(const ConvK p, const fl
       if (p.shuffle > 1) {
         const int cof = co / p.shuffle;
         const int ph = co - cof * p.shuffle;
-        const int of = o * p.shuffle + ph - p.shuffle_pad;
+        const int to = o / p.P;
+        const int jj = o - to * p.P;
+        const int of = to * p.shuffle + ph - p.shuffle_pad;  // output row
         if (of < 0 || of >= p.shuffle_tout) continue;
-        yi = (long long)b * p.ybs + (long long)cof * p.shuffle_tout + of;
+        yi = (long long)b * p.ybs + ((long long)cof * p.shuffle_tout + of) * p.P + jj;
       } else {
         yi = (long long)b * p.ybs + (long long)co * p.Lout + o;
       }
@@ -262,7 +264,7 @@ int conv1d_forward_simt(const pwgb_conv1d_desc* d, const float* x, const float* 
   p.xcs = p.t_valid;
   const long long cin_total = (long long)d->cin * (d->pre_gate ? 2 : 1);
   p.xbs = d->x_batch_stride ? d->x_batch_stride : cin_total * p.xcs;
-  const long long ylen = d->shuffle > 1 ? (long long)(d->cout / d->shuffle) * d->shuffle_tout : (long long)d->cout * p.Lout;
+  const long long ylen = d->shuffle > 1 ? (long long)(d->cout / d->shuffle) * d->shuffle_tout * p.P : (long long)d->cout * p.Lout;
   p.ybs = d->y_batch_stride ? d->y_batch_stride : ylen;
   p.rbs = d->r_batch_stride ? d->r_batch_stride : (long long)d->cout * p.Lout;
   if (p.B == 0 || p.Lout == 0) return PWGB_OK;

@@ -13,18 +13,21 @@ int conv1d_tc_chunk(const pwgb_conv1d_desc* d, int co_off, int cout_total, const
 int conv1d_tc_plan_ok(const pwgb_conv1d_desc* d);
 void tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, cudaStream_t st);
 
-// w: (cin, cout, K) -> wv: (cout*s, cin, M), wv[co*s+ph][ci][m'] = w[ci][co][ph + (M-1-m')*s]
+// w: (cin, cout/groups, K) -> wv: (cout*s, cin/groups, M),
+// wv[co*s+ph][ci_l][m'] = w[g*cin_g + ci_l][co_l][ph + (M-1-m')*s]   (co = g*cout_g + co_l)
 __global__ void convtr_weight_kernel(const float* __restrict__ w, float* __restrict__ wv, int cin, int cout, int K,
-                                     int s, int M) {
-  const long long n = (long long)cout * s * cin * M;
+                                     int s, int M, int groups) {
+  const int cin_g = cin / groups, cout_g = cout / groups;
+  const long long n = (long long)cout * s * cin_g * M;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int m = (int)(i % M);
     long long t = i / M;
-    int ci = (int)(t % cin);
-    int cv = (int)(t / cin);
+    int ci_l = (int)(t % cin_g);
+    int cv = (int)(t / cin_g);
     int co = cv / s, ph = cv - co * s;
+    int g = co / cout_g, co_l = co - g * cout_g;
     int k = ph + (M - 1 - m) * s;
-    wv[i] = k < K ? w[((long long)ci * cout + co) * K + k] : 0.f;
+    wv[i] = k < K ? w[((long long)(g * cin_g + ci_l) * cout_g + co_l) * K + k] : 0.f;
   }
 }
 
@@ -36,7 +39,8 @@ extern "C" size_t pwgb_conv_transpose1d_workspace(const pwgb_convtr1d_desc* d) {
   if (!d || d->stride <= 0) return 0;
   const int M = ceil_div(d->kernel, d->stride);
   // [virtual-conv fp32 weights][bf16 hi/lo operand image of the same weights for the tcgen05 path]
-  return 2 * (size_t)d->cout * d->stride * d->cin * M * sizeof(float);
+  const int G = d->groups > 1 ? d->groups : 1;
+  return 2 * (size_t)d->cout * d->stride * (d->cin / G) * M * sizeof(float);
 }
 
 extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const float* x, const float* w,
@@ -46,6 +50,8 @@ extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const 
                      d->padding >= 0,
                  "conv_transpose1d: bad descriptor");
   const int s = d->stride, K = d->kernel, M = ceil_div(K, s);
+  const int G = d->groups > 1 ? d->groups : 1, P = d->period > 1 ? d->period : 1;
+  PWGB_CHECK_ARG(d->cin % G == 0 && d->cout % G == 0, "conv_transpose1d: channels not divisible by groups");
   const int op = d->t_out - ((d->t_in - 1) * s - 2 * d->padding + K);
   PWGB_CHECK_ARG(op >= 0 && op < s, "conv_transpose1d: t_out=%d inconsistent with t_in=%d k=%d s=%d p=%d", d->t_out,
                  d->t_in, K, s, d->padding);
@@ -53,10 +59,10 @@ extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const 
   PWGB_CHECK_ARG(ws && ws_bytes >= need, "conv_transpose1d: workspace too small (%zu < %zu)", ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   float* wv = (float*)ws;
-  const long long n = (long long)d->cout * s * d->cin * M;
+  const long long n = (long long)d->cout * s * (d->cin / G) * M;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 4096) blocks = 4096;
-  convtr_weight_kernel<<<blocks, 256, 0, st>>>(w, wv, d->cin, d->cout, K, s, M);
+  convtr_weight_kernel<<<blocks, 256, 0, st>>>(w, wv, d->cin, d->cout, K, s, M, G);
   int rc = check_launch("convtr_weight_kernel");
   if (rc) return rc;
   pwgb_conv1d_desc c = {};
@@ -68,11 +74,11 @@ extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const 
   c.kernel = M;
   c.stride = 1;
   c.dilation = 1;
-  c.groups = 1;
+  c.groups = G;
   c.pad_left = M - 1;
   c.pad_mode = PWGB_PAD_ZERO;
-  c.period = 1;
-  c.t_valid = d->t_in;
+  c.period = P;
+  c.t_valid = d->t_in * P;
   c.pre_slope = d->pre_slope;
   c.post_act = PWGB_ACT_NONE;
   c.out_scale = 1.f;
@@ -80,7 +86,7 @@ extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const 
   c.shuffle_pad = d->padding;
   c.shuffle_tout = d->t_out;
   // tcgen05 path: N (= cout*s virtual channels) in chunks of <= 256 accumulator columns
-  if (d->cin % 32 == 0 && c.cout % 16 == 0) {
+  if (G == 1 && P == 1 && d->cin % 32 == 0 && c.cout % 16 == 0) {
     int chunk = c.cout;
     if (chunk > 256) {
       chunk = 256;

@@ -208,6 +208,129 @@ __global__ void sum_scale_kernel(const float* __restrict__ part, long long n, do
   if (threadIdx.x == 0) out[0] = (float)(red[0] * scale);
 }
 
+// ---------------------------------------------------------------- backward
+// dx += adjoint of (x -> amp): per frame, recompute X = FFT(w * frame), form
+// G[k] = damp[k] * X[k] / amp[k]  (0 where the clamp was active), zero-extend to n bins, inverse
+// transform (same butterflies, conjugate twiddles), dframe[j] = Re(z[j]), scatter w[j]*dframe[j]
+// back through the reflect-padded framing with atomics (frames overlap).
+__global__ void __launch_bounds__(256) stft_amp_backward_kernel(const StftK p, const float* __restrict__ x,
+                                                                 const float* __restrict__ window,
+                                                                 const float* __restrict__ amp,
+                                                                 const float* __restrict__ damp,
+                                                                 float* __restrict__ dx) {
+  extern __shared__ float2 sm[];
+  float2* z = sm;               // n
+  float2* g2 = sm + p.n;        // n
+  float2* tw = sm + 2 * p.n;    // n/2
+  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int n = p.n, half_n = n >> 1;
+  const int left = (n - p.win) >> 1;
+  const float* xb = x + (long long)b * p.T;
+  auto src_of = [&](int j) -> long long {
+    long long src = (long long)f * p.hop + j - half_n;
+    if (src < 0) src = -src;
+    if (src >= p.T) src = 2LL * (p.T - 1) - src;
+    return src < 0 ? 0 : (src >= p.T ? p.T - 1 : src);
+  };
+  for (int j = tid; j < half_n; j += 256) {
+    float s, c;
+    sincospif(-2.0f * (float)j / (float)n, &s, &c);
+    tw[j] = make_float2(c, s);
+  }
+  for (int j = tid; j < n; j += 256) {
+    float w = 0.f;
+    if (j >= left && j < left + p.win) w = __ldg(window + j - left);
+    z[bitrev((unsigned)j, p.log2n)] = make_float2(__ldg(xb + src_of(j)) * w, 0.f);
+  }
+  __syncthreads();
+  for (int s = 1; s <= p.log2n; ++s) {
+    const int half = 1 << (s - 1);
+    const int tstep = n >> s;
+    for (int t = tid; t < half_n; t += 256) {
+      const int pos = t & (half - 1);
+      const int i0 = ((t >> (s - 1)) << s) + pos;
+      const int i1 = i0 + half;
+      const float2 w = tw[pos * tstep];
+      const float2 a = z[i0], bb = z[i1];
+      const float2 m = make_float2(bb.x * w.x - bb.y * w.y, bb.x * w.y + bb.y * w.x);
+      z[i0] = make_float2(a.x + m.x, a.y + m.y);
+      z[i1] = make_float2(a.x - m.x, a.y - m.y);
+    }
+    __syncthreads();
+  }
+  const long long row = ((long long)b * p.frames + f) * p.bins;
+  for (int k = tid; k < n; k += 256) {
+    float2 gk = make_float2(0.f, 0.f);
+    if (k < p.bins) {
+      const float2 X = z[k];
+      const float pw = X.x * X.x + X.y * X.y;
+      if (pw > p.eps) {
+        const float sc = __ldg(damp + row + k) / __ldg(amp + row + k);
+        gk = make_float2(sc * X.x, sc * X.y);
+      }
+    }
+    g2[bitrev((unsigned)k, p.log2n)] = gk;
+  }
+  __syncthreads();
+  for (int s = 1; s <= p.log2n; ++s) {
+    const int half = 1 << (s - 1);
+    const int tstep = n >> s;
+    for (int t = tid; t < half_n; t += 256) {
+      const int pos = t & (half - 1);
+      const int i0 = ((t >> (s - 1)) << s) + pos;
+      const int i1 = i0 + half;
+      const float2 w = make_float2(tw[pos * tstep].x, -tw[pos * tstep].y);  // conjugate: e^{+i theta}
+      const float2 a = g2[i0], bb = g2[i1];
+      const float2 m = make_float2(bb.x * w.x - bb.y * w.y, bb.x * w.y + bb.y * w.x);
+      g2[i0] = make_float2(a.x + m.x, a.y + m.y);
+      g2[i1] = make_float2(a.x - m.x, a.y - m.y);
+    }
+    __syncthreads();
+  }
+  float* dxb = dx + (long long)b * p.T;
+  for (int j = tid; j < n; j += 256) {
+    if (j < left || j >= left + p.win) continue;
+    const float v = g2[j].x * __ldg(window + j - left);
+    if (v != 0.f) atomicAdd(dxb + src_of(j), v);
+  }
+}
+
+// dax[b,f,k] = sum_m melmat[k,m] * dmel[m],  dmel[m] = gout * scale * sign(lx-ly) * log_scale / mx * [mx > eps]
+__global__ void __launch_bounds__(128) mel_project_backward_kernel(int B, int frames, int bins, int n_mels,
+                                                                    const float* __restrict__ ax,
+                                                                    const float* __restrict__ ay,
+                                                                    const float* __restrict__ melmat, float eps,
+                                                                    float log_scale, const float* __restrict__ gout,
+                                                                    float scale, float* __restrict__ dax) {
+  extern __shared__ float sa[];  // 2*bins amps + n_mels dmel
+  float* dm = sa + 2 * bins;
+  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const long long row = ((long long)b * frames + f) * bins;
+  for (int k = tid; k < bins; k += 128) {
+    sa[k] = ax[row + k];
+    sa[bins + k] = ay[row + k];
+  }
+  __syncthreads();
+  const float go = gout[0] * scale;
+  for (int m = tid; m < n_mels; m += 128) {
+    float sx = 0.f, sy = 0.f;
+    for (int k = 0; k < bins; ++k) {
+      const float w = __ldg(melmat + (long long)k * n_mels + m);
+      sx = fmaf(sa[k], w, sx);
+      sy = fmaf(sa[bins + k], w, sy);
+    }
+    const float lx = logf(fmaxf(sx, eps)), ly = logf(fmaxf(sy, eps));
+    float d = lx > ly ? 1.f : (lx < ly ? -1.f : 0.f);
+    dm[m] = sx > eps ? go * d * log_scale / sx : 0.f;
+  }
+  __syncthreads();
+  for (int k = tid; k < bins; k += 128) {
+    float a = 0.f;
+    for (int m = 0; m < n_mels; ++m) a = fmaf(__ldg(melmat + (long long)k * n_mels + m), dm[m], a);
+    dax[row + k] = a;
+  }
+}
+
 static int fill(const pwgb_stft_desc* d, StftK& p) {
   if (!d || d->batch < 0 || d->t <= 0 || d->n_fft < 16 || d->n_fft > 4096 || (d->n_fft & (d->n_fft - 1)) ||
       d->hop <= 0 || d->win_length <= 0 || d->win_length > d->n_fft || d->t <= d->n_fft / 2)
@@ -298,4 +421,34 @@ extern "C" int pwgb_mel_project_forward(int batch, int frames, int bins, int n_m
   const long long n = (long long)batch * frames;
   sum_scale_kernel<<<1, 256, 0, st>>>(ws, n, 1.0 / ((double)n * n_mels), loss);
   return check_launch("sum_scale_kernel");
+}
+
+extern "C" int pwgb_stft_amplitude_backward(const pwgb_stft_desc* d, const float* x, const float* window, const float* amp,
+                                            const float* damp, float* dx, void* stream) {
+  PWGB_CHECK_ARG(d && x && window && amp && damp && dx, "stft_amplitude_backward: null argument");
+  StftK p;
+  PWGB_CHECK_ARG(fill(d, p), "stft_amplitude_backward: bad descriptor");
+  if (p.B == 0) return PWGB_OK;
+  const size_t smem = (size_t)(2 * p.n + p.n / 2) * sizeof(float2);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(stft_amp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("stft_amplitude_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PWGB_CUDA_ERROR;
+    }
+  }
+  stft_amp_backward_kernel<<<dim3(p.frames, p.B), 256, smem, (cudaStream_t)stream>>>(p, x, window, amp, damp, dx);
+  return check_launch("stft_amp_backward_kernel");
+}
+
+extern "C" int pwgb_mel_project_backward(int batch, int frames, int bins, int n_mels, const float* amp_x,
+                                         const float* amp_y, const float* melmat, float eps, float log_scale,
+                                         const float* gout, float* damp_x, void* stream) {
+  PWGB_CHECK_ARG(amp_x && amp_y && melmat && gout && damp_x, "mel_project_backward: null argument");
+  PWGB_CHECK_ARG(batch >= 0 && frames > 0 && bins > 0 && n_mels > 0 && batch <= 65535, "mel_project_backward: bad sizes");
+  if (batch == 0) return PWGB_OK;
+  const float scale = 1.0f / ((float)batch * (float)frames * (float)n_mels);
+  mel_project_backward_kernel<<<dim3(frames, batch), 128, (2 * (size_t)bins + n_mels) * sizeof(float), (cudaStream_t)stream>>>(
+      batch, frames, bins, n_mels, amp_x, amp_y, melmat, eps, log_scale, gout, scale, damp_x);
+  return check_launch("mel_project_backward_kernel");
 }

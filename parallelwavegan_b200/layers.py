@@ -108,7 +108,8 @@ class HiFiGANResidualBlock(torch.nn.Module):
                 ]
 
     def forward(self, x, out=None, accumulate=False, out_scale=1.0):
-        """Returns block(x); optionally ``out (+)= out_scale * block(x)`` fused into the last conv."""
+        """Returns block(x); optionally ``out (+)= out_scale * block(x)`` fused into the last conv
+        (inference only -- under autograd the caller sums the block outputs with ScaledSumFn)."""
         k = self.kernel_size
         n = len(self.dilations)
         for idx, d in enumerate(self.dilations):

@@ -169,6 +169,11 @@ class MelSpectrogramLoss(torch.nn.Module):
         if y_hat.dim() == 3:
             y_hat = y_hat.reshape(-1, y_hat.size(2))
             y = y.reshape(-1, y.size(2))
+        if torch.is_grad_enabled() and y_hat.requires_grad:
+            from .autograd import MelLossFn
+
+            return MelLossFn.apply(y_hat.contiguous(), y.contiguous(), m.melmat, m._window(y_hat), m.fft_size, m.hop_size,
+                                   m.win_length, m.eps, m._log_scale)[0]
         ax, ay = ops.stft_amplitude(y_hat, y, m.fft_size, m.hop_size, m.win_length, m._window(y_hat), m.eps)
         _, loss = ops.mel_project(ax, ay, m.melmat, m.eps, m._log_scale, want_mel=False, want_loss=True)
         return loss[0]
@@ -258,6 +263,6 @@ class FeatureMatchLoss(torch.nn.Module):
                 fh, f = fh[:-1], f[:-1]
             wl = 1.0 / len(f) if self.average_by_layers else 1.0
             for a, b in zip(fh, f):
-                out = ops.reduce_mean("l1", a, b, weight=wd * wl, out=out, accumulate=not first)
+                out = ops.reduce_mean("l1", a, b.detach(), weight=wd * wl, out=out, accumulate=not first)
                 first = False
         return out[0]

@@ -134,10 +134,15 @@ class HiFiGANGenerator(_GeneratorBase):
             s = self.upsample_scales[i]
             c = ops.conv_transpose1d(c, effective_weight(up), up.bias, stride=s, padding=s // 2 + s % 2,
                                      output_padding=s % 2, pre_slope=self.slope)
-            cs = torch.empty_like(c)
-            for j in range(nb):  # cs = sum_j block_j(c) / nb, fused into each block's last conv
-                self.blocks[i * nb + j](c, out=cs, accumulate=j > 0, out_scale=1.0 / nb)
-            c = cs
+            if torch.is_grad_enabled() and (c.requires_grad or next(self.parameters()).requires_grad):
+                from .autograd import ScaledSumFn  # training: differentiable MRF average
+
+                c = ScaledSumFn.apply(1.0 / nb, *[self.blocks[i * nb + j](c) for j in range(nb)])
+            else:
+                cs = torch.empty_like(c)
+                for j in range(nb):  # cs = sum_j block_j(c) / nb, fused into each block's last conv
+                    self.blocks[i * nb + j](c, out=cs, accumulate=j > 0, out_scale=1.0 / nb)
+                c = cs
         oc = self.output_conv[1]
         return ops.conv1d(c, effective_weight(oc), oc.bias, padding=pad, pre_slope=0.01, post_act="tanh")
 

@@ -82,7 +82,7 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def conv1d(
+def conv1d_raw(
     x,
     w,
     bias=None,
@@ -163,24 +163,28 @@ def conv1d(
     return out
 
 
-def conv_transpose1d(x, w, bias=None, *, stride, padding=0, output_padding=0, pre_slope=1.0):
+def conv_transpose1d_raw(x, w, bias=None, *, stride, padding=0, output_padding=0, pre_slope=1.0, groups=1, period=1):
     """ConvTranspose1d with fused pre-LeakyReLU -- pwgb_conv_transpose1d_forward.
     w is the reference layout (cin, cout, k)."""
     x = _dev(x, "x")
     w = _dev(w, "w")
-    B, cin, t_in = x.shape
+    if w.dim() == 4:
+        w = w.reshape(w.shape[0], w.shape[1], w.shape[2])
+    B, cin = x.shape[0], x.shape[1]
+    P = int(period)
+    t_in = x.numel() // max(B * cin * P, 1)
     if w.shape[0] != cin:
         raise PwgbError(f"conv_transpose1d: x has {cin} channels, weight expects {w.shape[0]}")
-    cout, K = w.shape[1], w.shape[2]
+    cout, K = w.shape[1] * groups, w.shape[2]
     t_out = (t_in - 1) * stride - 2 * padding + K + output_padding
     if bias is not None:
         bias = _dev(bias, "bias")
     d = capi.ConvTr1dDesc(batch=B, cin=cin, cout=cout, t_in=t_in, t_out=t_out, kernel=K, stride=stride,
-                          padding=padding, pre_slope=float(pre_slope))
+                          padding=padding, pre_slope=float(pre_slope), groups=int(groups), period=P)
     L = capi.lib()
     nbytes = L.pwgb_conv_transpose1d_workspace(C.byref(d))
     ws = torch.empty((nbytes + 3) // 4, device=x.device, dtype=torch.float32)
-    y = torch.empty((B, cout, t_out), device=x.device, dtype=torch.float32)
+    y = torch.empty((B, cout, t_out) if P == 1 else (B, cout, t_out, P), device=x.device, dtype=torch.float32)
     prof = _Prof("conv_transpose1d", 2.0 * B * cout * t_out * cin * ((K + stride - 1) // stride), 4.0 * (x.numel() + y.numel()),
                  f"B{B} cin{cin} cout{cout} k{K} s{stride} T{t_out}")
     rc = L.pwgb_conv_transpose1d_forward(C.byref(d), _p(x), _p(w), _p(bias), _p(y), _p(ws), C.c_size_t(nbytes), _stream())
@@ -329,7 +333,7 @@ def mel_project(ax, ay, melmat, eps, log_scale, want_mel=True, want_loss=False):
 _REDUCE = {"mse_const": 0, "l1": 1, "hinge": 2, "linear": 3}
 
 
-def reduce_mean(mode, x, y=None, c=0.0, s=1.0, weight=1.0, out=None, accumulate=False):
+def reduce_mean_raw(mode, x, y=None, c=0.0, s=1.0, weight=1.0, out=None, accumulate=False):
     """out[0] (+)= weight * mean(f(x[, y])) -- pwgb_reduce_mean_forward (deterministic)."""
     x = _dev(x, "x")
     if y is not None:
@@ -346,7 +350,7 @@ def reduce_mean(mode, x, y=None, c=0.0, s=1.0, weight=1.0, out=None, accumulate=
     return out
 
 
-def avg_pool1d(x, kernel_size, stride, padding=0, count_include_pad=True):
+def avg_pool1d_raw(x, kernel_size, stride, padding=0, count_include_pad=True):
     """torch.nn.AvgPool1d semantics on (B, C, T) -- pwgb_avg_pool1d_forward."""
     x = _dev(x, "x")
     B, Cc, T = x.shape
@@ -356,3 +360,101 @@ def avg_pool1d(x, kernel_size, stride, padding=0, count_include_pad=True):
                                             int(bool(count_include_pad)), _stream())
     capi.check(rc, "pwgb_avg_pool1d_forward")
     return y
+
+
+# --------------------------------------------------------------------------
+# backward building blocks (raw wrappers) and autograd-aware public entry points
+# --------------------------------------------------------------------------
+
+
+def conv1d_wgrad(x, gy, w_shape, *, stride=1, padding=0, dilation=1, groups=1, pad_mode="zero", x_slope=1.0, g_slope=1.0, period=1):
+    """dw of the conv described by the arguments -- pwgb_conv1d_wgrad (deterministic split reduce)."""
+    x = _dev(x, "x")
+    gy = _dev(gy, "gy")
+    cout, cin_g, K = w_shape[0], w_shape[1], w_shape[2]
+    B, cin = x.shape[0], x.shape[1]
+    P = int(period)
+    L = x.numel() // max(B * cin, 1)
+    t_in = (L + P - 1) // P
+    t_out = gy.numel() // max(B * cout * P, 1)
+    pl = padding if isinstance(padding, int) else padding[0]
+    d = capi.Conv1dDesc(batch=B, cin=cin, cout=cout, t_in=t_in, t_out=t_out, kernel=K, stride=stride, dilation=dilation,
+                        groups=groups, pad_left=pl, pad_mode=_PAD[pad_mode], period=P, t_valid=L, pre_slope=float(x_slope),
+                        out_scale=1.0)
+    Lb = capi.lib()
+    nbytes = Lb.pwgb_conv1d_wgrad_workspace(C.byref(d))
+    ws = torch.empty(max(nbytes // 4, 1), device=x.device, dtype=torch.float32)
+    dw = torch.empty((cout, cin_g, K), device=x.device, dtype=torch.float32)
+    prof = _Prof("conv1d_wgrad", 2.0 * B * cout * t_out * P * cin_g * K, 4.0 * (x.numel() + gy.numel()), f"B{B} cin{cin} cout{cout} k{K} T{t_out}")
+    rc = Lb.pwgb_conv1d_wgrad(C.byref(d), _p(x), _p(gy), float(g_slope), _p(dw), 0, _p(ws), C.c_size_t(nbytes), _stream())
+    capi.check(rc, "pwgb_conv1d_wgrad")
+    prof.done()
+    return dw
+
+
+def act_backward(mode, g, ref=None, slope=0.0, scale=1.0, out=None, accumulate=False):
+    """out (+)= g * scale * f'(ref); mode: "lrelu" (mask ref > 0), "tanh" (ref = output), "scale"."""
+    g = _dev(g, "g")
+    if ref is not None:
+        ref = _dev(ref, "ref")
+    if out is None:
+        out = torch.empty_like(g)
+    rc = capi.lib().pwgb_act_backward({"lrelu": 0, "tanh": 1, "scale": 2}[mode], _p(g), _p(ref), _p(out), g.numel(), float(slope),
+                                      float(scale), int(bool(accumulate)), _stream())
+    capi.check(rc, "pwgb_act_backward")
+    return out
+
+
+def bias_grad(g, channels):
+    g = _dev(g, "g")
+    B = g.shape[0]
+    db = torch.empty(channels, device=g.device, dtype=torch.float32)
+    rc = capi.lib().pwgb_bias_grad(_p(g), _p(db), B, channels, g.numel() // max(B * channels, 1), 0, _stream())
+    capi.check(rc, "pwgb_bias_grad")
+    return db
+
+
+def axpby(a, x, b, y):
+    """y = a*x + b*y in place on y."""
+    x = _dev(x, "x")
+    rc = capi.lib().pwgb_axpby(x.numel(), float(a), _p(x), float(b), _p(y), _stream())
+    capi.check(rc, "pwgb_axpby")
+    return y
+
+
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+
+def conv1d(x, w, bias=None, **kw):
+    """Fused conv (see conv1d_raw); differentiable through libpwgb backward kernels when any input requires grad."""
+    if _needs_grad(x, w, bias, kw.get("residual")):
+        from . import autograd as ag
+
+        return ag.conv1d(x, w, bias, **kw)
+    return conv1d_raw(x, w, bias, **kw)
+
+
+def conv_transpose1d(x, w, bias=None, **kw):
+    if _needs_grad(x, w, bias):
+        from . import autograd as ag
+
+        return ag.conv_transpose1d(x, w, bias, **kw)
+    return conv_transpose1d_raw(x, w, bias, **kw)
+
+
+def avg_pool1d(x, kernel_size, stride, padding=0, count_include_pad=True):
+    if _needs_grad(x):
+        from . import autograd as ag
+
+        return ag.AvgPool1dFn.apply(x, kernel_size, stride, padding, count_include_pad)
+    return avg_pool1d_raw(x, kernel_size, stride, padding, count_include_pad)
+
+
+def reduce_mean(mode, x, y=None, c=0.0, s=1.0, weight=1.0, out=None, accumulate=False):
+    if _needs_grad(x, y):
+        from . import autograd as ag
+
+        term = ag.ReduceMeanFn.apply(x, y, mode, float(c), float(s), float(weight))
+        return term if (out is None or not accumulate) else out + term
+    return reduce_mean_raw(mode, x, y, c, s, weight, out, accumulate)

@@ -1,0 +1,181 @@
+"""GPU gradient parity: autograd through the libpwgb backward kernels vs torch autograd on the CPU
+oracle (same weights / inputs).  Tolerance 1e-3 rel-L2 per gradient tensor (north_star bar)."""
+import json
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden_weights, load_golden, rel_l2
+from oracle import ref_ops, synth
+
+pytestmark = pytest.mark.gpu
+GTOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    import __graft_entry__
+
+    __graft_entry__.build()
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize(
+    "cin,cout,k,stride,dil,groups,pad,T,B,pre,post",
+    [
+        (8, 12, 3, 1, 1, 1, 1, 70, 2, 0.1, None),
+        (64, 64, 7, 1, 3, 1, 9, 300, 2, 0.1, None),
+        (32, 32, 11, 1, 5, 1, 25, 260, 1, 0.1, "tanh"),
+        (1, 16, 15, 1, 1, 1, 7, 200, 2, 1.0, "lrelu"),
+        (16, 16, 41, 4, 1, 4, 20, 515, 2, 1.0, "lrelu"),
+        (16, 32, 41, 2, 1, 16, 20, 300, 2, 1.0, "lrelu"),
+        (32, 1, 3, 1, 1, 1, 1, 64, 2, 1.0, None),
+    ],
+)
+def test_conv1d_gradients(dev, cin, cout, k, stride, dil, groups, pad, T, B, pre, post):
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((B, cin, T), 1)
+    w = synth.randn((cout, cin // groups, k), 2, 1.0 / (cin // groups * k) ** 0.5)
+    b = synth.randn((cout,), 3, 0.1)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    z = F.conv1d(F.leaky_relu(xr, pre) if pre != 1.0 else xr, wr, br, stride=stride, padding=pad, dilation=dil, groups=groups)
+    yr = torch.tanh(z) if post == "tanh" else (F.leaky_relu(z, 0.2) if post == "lrelu" else z)
+    res = synth.randn(yr.shape, 4)
+    rr = res.clone().requires_grad_(True)
+    out_r = (yr + rr) * 0.5
+    gout = synth.randn(out_r.shape, 5)
+    (out_r * gout).sum().backward()
+
+    xd, wd, bd, rd = (t.clone().to(dev).requires_grad_(True) for t in (x, w, b, res))
+    y = ops.conv1d(xd, wd, bd, stride=stride, padding=pad, dilation=dil, groups=groups, pre_slope=pre, post_act=post,
+                   post_slope=0.2, residual=rd, out_scale=0.5)
+    assert rel_l2(y.detach().cpu(), out_r.detach()) < GTOL
+    (y * gout.to(dev)).sum().backward()
+    for name, a, r in (("dx", xd.grad, xr.grad), ("dw", wd.grad, wr.grad), ("db", bd.grad, br.grad), ("dres", rd.grad, rr.grad)):
+        assert rel_l2(a.cpu(), r) < GTOL, name
+
+
+@pytest.mark.parametrize("cin,cout,s,T,B", [(16, 8, 8, 13, 2), (64, 32, 2, 50, 2), (12, 6, 5, 9, 1)])
+def test_conv_transpose_gradients(dev, cin, cout, s, T, B):
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((B, cin, T), 1)
+    w = synth.randn((cin, cout, 2 * s), 2, 0.2)
+    b = synth.randn((cout,), 3, 0.1)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    yr = F.conv_transpose1d(F.leaky_relu(xr, 0.1), wr, br, stride=s, padding=s // 2 + s % 2, output_padding=s % 2)
+    gout = synth.randn(yr.shape, 5)
+    (yr * gout).sum().backward()
+    xd, wd, bd = (t.clone().to(dev).requires_grad_(True) for t in (x, w, b))
+    y = ops.conv_transpose1d(xd, wd, bd, stride=s, padding=s // 2 + s % 2, output_padding=s % 2, pre_slope=0.1)
+    (y * gout.to(dev)).sum().backward()
+    for name, a, r in (("dx", xd.grad, xr.grad), ("dw", wd.grad, wr.grad), ("db", bd.grad, br.grad)):
+        assert rel_l2(a.cpu(), r) < GTOL, name
+
+
+@pytest.mark.parametrize("period", [2, 3, 7])
+def test_period_conv_gradients(dev, period):
+    """Two MPD layers incl. the reflect-extended first layer: gradients w.r.t. waveform and weights."""
+    from parallelwavegan_b200 import ops
+
+    B, T = 2, 301
+    x = synth.randn((B, 1, T), 11)
+    w1 = synth.randn((8, 1, 5, 1), 12, 0.4)
+    b1 = synth.randn((8,), 13, 0.1)
+    w2 = synth.randn((16, 8, 5, 1), 14, 0.15)
+    xr, w1r, b1r, w2r = (t.clone().requires_grad_(True) for t in (x, w1, b1, w2))
+    xe = F.pad(xr, (0, period - T % period), "reflect") if T % period else xr
+    h = F.leaky_relu(F.conv2d(xe.view(B, 1, -1, period), w1r, b1r, stride=(3, 1), padding=(2, 0)), 0.1)
+    o = F.conv2d(h, w2r, None, stride=(3, 1), padding=(2, 0))
+    gout = synth.randn(o.shape, 5)
+    (o * gout).sum().backward()
+    xd, w1d, b1d, w2d = (t.clone().to(dev).requires_grad_(True) for t in (x, w1, b1, w2))
+    hd = ops.conv1d(xd, w1d, b1d, stride=3, padding=2, period=period, post_act="lrelu", post_slope=0.1)
+    od = ops.conv1d(hd, w2d, None, stride=3, padding=2, period=period)
+    (od * gout.to(dev)).sum().backward()
+    for name, a, r in (("dx", xd.grad, xr.grad), ("dw1", w1d.grad, w1r.grad), ("db1", b1d.grad, b1r.grad), ("dw2", w2d.grad, w2r.grad)):
+        assert rel_l2(a.cpu(), r) < GTOL, name
+
+
+def test_hifigan_train_step_gradients(dev):
+    """One HiFi-GAN generator + discriminator loss evaluation with backward (train.py:200-335 logic on a small
+    config): every parameter gradient vs torch autograd through the CPU oracle."""
+    from parallelwavegan_b200 import losses, models
+
+    kw = dict(in_channels=80, out_channels=1, channels=64, kernel_size=7, upsample_scales=[8, 8, 2, 2],
+              upsample_kernel_sizes=[16, 16, 4, 4], resblock_kernel_sizes=[3, 7, 11],
+              resblock_dilations=[[1, 3, 5], [1, 3, 5], [1, 3, 5]])
+    g = models.HiFiGANGenerator(**kw)
+    spec = [(k, tuple(v.shape)) for k, v in g.state_dict().items()]
+    sd = synth.synth_state_dict(spec, 7, 1.15)
+    g.load_state_dict(sd)
+    dkw = dict(scales=2, periods=[2, 3], follow_official_norm=False,
+               scale_discriminator_params=dict(in_channels=1, out_channels=1, kernel_sizes=[15, 41, 5, 3], channels=16,
+                                               max_downsample_channels=64, max_groups=4, bias=True, downsample_scales=[2, 4, 1],
+                                               nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1}),
+               period_discriminator_params=dict(in_channels=1, out_channels=1, kernel_sizes=[5, 3], channels=4,
+                                                downsample_scales=[3, 3, 1], max_downsample_channels=32, bias=True,
+                                                nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
+                                                use_weight_norm=True, use_spectral_norm=False))
+    d = models.HiFiGANMultiScaleMultiPeriodDiscriminator(**dkw)
+    dspec = [(k, tuple(v.shape)) for k, v in d.state_dict().items()]
+    dsd = synth.synth_state_dict(dspec, 9, 1.4)
+    d.load_state_dict(dsd)
+    c = synth.randn((2, 80, 8), 21)
+    y = synth.randn((2, 1, 8 * 256), 22, 0.3)
+
+    # ---- CPU oracle with torch autograd (weights as leaf tensors in the reference layout)
+    leaf_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    leaf_d = {k: v.clone().requires_grad_(True) for k, v in dsd.items()}
+    wg = ref_ops.fold_weight_norm(leaf_g)
+    wd = ref_ops.fold_weight_norm(leaf_d)
+    y_ref = ref_ops.hifigan_generator(wg, c, dict(kw, negative_slope=0.1))
+    melmat = torch.from_numpy(ref_ops.slaney_mel_filterbank(22050, 1024, 80, 0, 11025).T.copy())
+    mel = ref_ops.mel_loss(y_ref, y, melmat, log_base=None)
+
+    def d_ref(x):
+        outs, xs = [], x
+        for i in range(2):
+            outs.append(ref_ops.hifigan_scale_discriminator(wd, f"msd.discriminators.{i}", xs, strides=(2, 4, 1), groups=(4, 4, 4)))
+            xs = F.avg_pool1d(xs, 4, 2, padding=2)
+        for i, p in enumerate((2, 3)):
+            outs.append(ref_ops.hifigan_period_discriminator(wd, f"mpd.discriminators.{i}", x, p, n_layers=3, strides=(3, 3, 1)))
+        return outs
+
+    p_hat = d_ref(y_ref)
+    with torch.no_grad():
+        p_real = d_ref(y)
+    adv = ref_ops.generator_adv_loss(p_hat)
+    fm = ref_ops.feature_match_loss(p_hat, p_real)
+    loss_ref = 45.0 * mel + adv + 2.0 * fm
+    loss_ref.backward()
+
+    # ---- ours
+    g = g.to(dev).train()
+    d = d.to(dev).train()
+    mel_fn = losses.MelSpectrogramLoss(fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80,
+                                       fmin=0, fmax=11025, log_base=None).to(dev)
+    y_hat = g(c.to(dev))
+    assert rel_l2(y_hat.detach().cpu(), y_ref.detach()) < GTOL
+    mel_o = mel_fn(y_hat, y.to(dev))
+    ph = d(y_hat)
+    with torch.no_grad():
+        pr = d(y.to(dev))
+    adv_o = losses.GeneratorAdversarialLoss()(ph)
+    fm_o = losses.FeatureMatchLoss()(ph, pr)
+    for name, a, r in (("mel", mel_o, mel), ("adv", adv_o, adv), ("fm", fm_o, fm)):
+        assert abs(float(a) - float(r)) <= GTOL * abs(float(r)), name
+    loss = 45.0 * mel_o + adv_o + 2.0 * fm_o
+    loss.backward()
+    worst = 0.0
+    for k, p in g.named_parameters():
+        e = rel_l2(p.grad.cpu(), leaf_g[k].grad)
+        worst = max(worst, e)
+        assert e < 5e-3, (k, e)
+    for k, p in d.named_parameters():
+        e = rel_l2(p.grad.cpu(), leaf_d[k].grad)
+        assert e < 5e-3, (k, e)
+    print("worst generator grad rel-L2", worst)
