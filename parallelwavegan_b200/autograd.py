@@ -30,7 +30,16 @@ class Conv1dFn(torch.autograd.Function):
         ctx.w3 = (w.shape[0], w.shape[1], w.shape[2])
         ctx.w_shape = tuple(w.shape)
         ctx.x_shape = tuple(x.shape)
-        ctx.save_for_backward(x, w, y if post_act else None)
+        act_out = None
+        if post_act:
+            act_out = y
+            if residual is not None or out_scale != 1.0:
+                # the activation derivative needs act(z) = y / out_scale - residual
+                act_out = torch.empty_like(y)
+                ops.axpby(1.0 / out_scale, y, 0.0, act_out)
+                if residual is not None:
+                    ops.axpby(-1.0, residual, 1.0, act_out)
+        ctx.save_for_backward(x, w, act_out)
         return y
 
     @staticmethod
