@@ -171,6 +171,52 @@ def run_reference(args, rank, world):
     }))
 
 
+def measure_train_step(dev, rank, local_rank, world, dist, steps=3, warmup=2):
+    """Secondary metric (BASELINE.json "train steps/sec"): HiFi-GAN v1 G + MSD/MPD full train step
+    (C5: per-GPU batch 16 x 8192 samples; mel + adversarial + feature-matching losses, Adam), forward and
+    backward on libpwgb kernels, DDP gradient all-reduce over NCCL when world > 1."""
+    from oracle import synth
+    from parallelwavegan_b200 import losses, models
+    from parallelwavegan_b200.train_step import GanTrainStep
+
+    g = models.HiFiGANGenerator(**CFG)
+    g.load_state_dict(synth.synth_state_dict([(k, tuple(v.shape)) for k, v in g.state_dict().items()], 1234, 1.15))
+    d = models.HiFiGANMultiScaleMultiPeriodDiscriminator()
+    d.load_state_dict(synth.synth_state_dict([(k, tuple(v.shape)) for k, v in d.state_dict().items()], 4321, 1.4))
+    g, d = g.to(dev).train(), d.to(dev).train()
+    if world > 1:
+        g = torch.nn.parallel.DistributedDataParallel(g, device_ids=[local_rank])
+        d = torch.nn.parallel.DistributedDataParallel(d, device_ids=[local_rank])
+    crit = {"mel": losses.MelSpectrogramLoss(fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80,
+                                             fmin=0, fmax=11025, log_base=None).to(dev),
+            "gen_adv": losses.GeneratorAdversarialLoss(), "dis_adv": losses.DiscriminatorAdversarialLoss(),
+            "feat_match": losses.FeatureMatchLoss()}
+    step = GanTrainStep(g, d, crit, torch.optim.Adam(g.parameters(), lr=2e-4, betas=(0.5, 0.9)),
+                        torch.optim.Adam(d.parameters(), lr=2e-4, betas=(0.5, 0.9)))
+    gen = torch.Generator().manual_seed(1000 + rank)
+    c = torch.randn(16, 80, 32, generator=gen).to(dev)
+    y = (torch.rand(16, 1, 8192, generator=gen) - 0.5).to(dev)
+    for _ in range(warmup):
+        st = step(c, y)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        st = step(c, y)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    return {"metric": "train_steps_per_sec", "value": 1e3 / ms, "ms_per_step": ms, "global_batch": 16 * world,
+            "workload": "HiFi-GAN v1 G + MSD/MPD train step, per-GPU batch 16 x 8192 samples (hifigan.v1.yaml losses, Adam)",
+            "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU",
+            "losses": {k: float(v) for k, v in st.items()}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +224,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -262,6 +309,13 @@ def main():
         prof = ops.PROFILE
         ops.PROFILE = None
 
+    train = None
+    if not args.no_train:
+        try:
+            train = measure_train_step(dev, rank, local_rank, world, dist)
+        except Exception as e:  # the headline line must survive a failure of the secondary measurement
+            train = {"error": repr(e)[:300]}
+
     from parallelwavegan_b200 import sharding
 
     local_samples = BATCH * FRAMES * HOP * args.steps
@@ -322,6 +376,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "train": train,
             "kernel_classes": {k: {"ms_per_step": v[2] / 3, "launches_per_step": v[3] / 3, "tflops": v[0] / (v[2] * 1e-3) / 1e12,
                                    "alg_GBps": v[1] / (v[2] * 1e-3) / 1e9} for k, v in agg.items()},
         }
