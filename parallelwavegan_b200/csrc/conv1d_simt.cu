@@ -232,6 +232,48 @@ static int launch_conv(ConvK p, const float* x, const float* w, const float* bia
   return check_launch("conv1d_fwd_kernel");
 }
 
+// Few output channels (logit convs of the discriminators, cin up to 1024 -> cout 1) with short
+// sequences: the generic tiling would launch a handful of CTAs.  Here one CTA = 32 output positions
+// x all (<= 4) output channels; its 8 warps split the input channels and reduce through shared memory.
+__global__ void __launch_bounds__(256) conv1d_small_cout_kernel(const ConvK p, const float* __restrict__ x,
+                                                                 const float* __restrict__ w,
+                                                                 const float* __restrict__ bias,
+                                                                 float* __restrict__ y) {
+  __shared__ float red[8][4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int o = blockIdx.x * 32 + lane;
+  const bool ov = o < p.Lout;
+  const int oc = ov ? o : 0;
+  const int to = oc / p.P, j = oc - to * p.P;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* xb = x + (long long)b * p.xbs;
+  for (int ci = warp; ci < p.Cin; ci += 8) {
+    const float* xc = xb + (long long)ci * p.xcs;
+    for (int k = 0; k < p.K; ++k) {
+      const long long row = (long long)to * p.S + (long long)k * p.D - p.padL;
+      float v = 0.f;
+      if (row >= 0 && row < p.t_in) {
+        long long li = row * p.P + j;
+        if (li >= p.t_valid) li = 2LL * (p.t_valid - 1) - li;
+        v = lrelu(__ldg(xc + (li < 0 ? 0 : li)), p.pre_slope);
+      }
+      for (int co = 0; co < p.Cout; ++co) acc[co] = fmaf(v, __ldg(w + ((long long)co * p.Cin + ci) * p.K + k), acc[co]);
+    }
+  }
+  for (int co = 0; co < 4; ++co) red[warp][co][lane] = acc[co];
+  __syncthreads();
+  if (warp < p.Cout && ov) {
+    float v = bias ? __ldg(bias + warp) : 0.f;
+    for (int i = 0; i < 8; ++i) v += red[i][warp][lane];
+    if (p.post_act == PWGB_ACT_TANH)
+      v = tanhf(v);
+    else if (p.post_act == PWGB_ACT_LRELU)
+      v = lrelu(v, p.post_slope);
+    y[(long long)b * p.ybs + (long long)warp * p.Lout + o] = v * p.out_scale;
+  }
+}
+
 int conv1d_forward_simt(const pwgb_conv1d_desc* d, const float* x, const float* w, const float* bias,
                         const float* residual, float* y, cudaStream_t st) {
   ConvK p;
@@ -268,6 +310,11 @@ int conv1d_forward_simt(const pwgb_conv1d_desc* d, const float* x, const float* 
   p.ybs = d->y_batch_stride ? d->y_batch_stride : ylen;
   p.rbs = d->r_batch_stride ? d->r_batch_stride : (long long)d->cout * p.Lout;
   if (p.B == 0 || p.Lout == 0) return PWGB_OK;
+  if (p.Cout <= 4 && p.groups == 1 && p.Cin >= 64 && p.pad_mode == PWGB_PAD_ZERO && !p.pre_gate && !residual &&
+      !p.accumulate && p.shuffle <= 1 && (long long)p.Lout * p.B <= 65536 && p.B <= 65535) {
+    conv1d_small_cout_kernel<<<dim3(ceil_div(p.Lout, 32), p.B), 256, 0, st>>>(p, x, w, bias, y);
+    return check_launch("conv1d_small_cout_kernel");
+  }
   const int cg = p.Cout_g;
   if (cg >= 64) return launch_conv<8, 8>(p, x, w, bias, residual, y, st);
   if (cg >= 32) return launch_conv<8, 4>(p, x, w, bias, residual, y, st);

@@ -878,6 +878,8 @@ void tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed,
 
 using namespace pwgb;
 
+static int tc_cout_chunk(int cout);
+
 extern "C" void pwgb_debug_set(int key, int value) {
   if (key == 1) g_tc_variant = value;
 }
@@ -890,24 +892,59 @@ extern "C" size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kern
 extern "C" int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream) {
   PWGB_CHECK_ARG(w && packed, "conv1d_tc_pack_weight: null argument");
   PWGB_CHECK_ARG(cin > 0 && cin % KC == 0 && cout > 0 && kernel > 0, "conv1d_tc_pack_weight: cin must be a multiple of %d", KC);
-  tc_pack_rows(w, packed, cin, cin, cout, kernel, 0, cout, (cudaStream_t)stream);
-  return check_launch("tc_pack_weight_kernel");
+  const int chunk = tc_cout_chunk(cout);
+  PWGB_CHECK_ARG(chunk > 0, "conv1d_tc_pack_weight: cout must be a multiple of 16");
+  const size_t img = (size_t)(cin / KC) * kernel * 2 * (KC / 8) * chunk * 16;
+  for (int co = 0; co < cout; co += chunk) {
+    tc_pack_rows(w + (size_t)co * cin * kernel, (unsigned char*)packed + (size_t)(co / chunk) * img, cin, cin, chunk, kernel, 0,
+                 chunk, (cudaStream_t)stream);
+    int rc = check_launch("tc_pack_weight_kernel");
+    if (rc) return rc;
+  }
+  return PWGB_OK;
+}
+
+// Output channels beyond the 256 accumulator columns of one launch are processed in column chunks
+// (one launch each, re-reading x): chunk = largest multiple of 16 that is <= 256 and divides cout.
+static int tc_cout_chunk(int cout) {
+  if (cout <= 256) return cout;
+  for (int c = 256; c >= 16; c -= 16)
+    if (cout % c == 0) return c;
+  return 0;
 }
 
 extern "C" int pwgb_conv1d_tc_supported(const pwgb_conv1d_desc* d) {
-  if (!d) return 0;
+  if (!d || d->cout <= 0) return 0;
+  const int chunk = tc_cout_chunk(d->cout);
+  if (!chunk) return 0;
+  if (chunk != d->cout && d->shuffle > 1) return 0;
+  pwgb_conv1d_desc c = *d;
+  c.cout = chunk;
   TcK p;
   size_t bytes;
-  return tc_plan(d, p, bytes);
+  return tc_plan(&c, p, bytes);
 }
 
 extern "C" int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x, const void* packed_w,
                                       const float* bias, const float* residual, float* y, void* stream) {
   PWGB_CHECK_ARG(d && x && packed_w && y, "conv1d_tc: null argument");
-  TcK p;
-  size_t bytes = 0;
-  PWGB_UNSUPPORTED_IF(!tc_plan(d, p, bytes), "conv1d_tc: configuration not supported by the tcgen05 path");
-  return tc_launch(p, bytes, x, packed_w, bias, residual, y, (cudaStream_t)stream);
+  PWGB_UNSUPPORTED_IF(!pwgb_conv1d_tc_supported(d), "conv1d_tc: configuration not supported by the tcgen05 path");
+  const int chunk = tc_cout_chunk(d->cout);
+  pwgb_conv1d_desc c = *d;
+  c.cout = chunk;
+  const size_t img = (size_t)(d->cin / KC) * d->kernel * 2 * (KC / 8) * chunk * 16;
+  for (int co = 0; co < d->cout; co += chunk) {
+    TcK p;
+    size_t bytes = 0;
+    tc_plan(&c, p, bytes);
+    p.co_off = co;
+    p.ybs = (long long)d->cout * d->t_out;
+    p.rbs = p.ybs;
+    int rc = tc_launch(p, bytes, x, (const unsigned char*)packed_w + (size_t)(co / chunk) * img, bias, residual, y,
+                       (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return PWGB_OK;
 }
 
 // ======================================================================================

@@ -118,8 +118,16 @@ def conv1d_raw(
     if cin_x != cin * (2 if pre_gate else 1):
         raise PwgbError(f"conv1d: x has {cin_x} channels, weight expects {cin}")
     P = int(period)
-    t_in = (L + P - 1) // P
     pl, pr = (padding, padding) if isinstance(padding, int) else padding
+    if P > 1 and stride == 1 and L % P == 0 and out is None and residual is None:
+        # a (k,1) Conv2d with stride 1 over the (rows, P) view IS a 1-D conv over the flat axis with
+        # dilation P and zero padding pad*P (rows outside [0, R) are flat indices outside [0, R*P)):
+        # this puts the wide 1024-channel period layers on the tcgen05 path
+        y = conv1d_raw(x.reshape(B, cin_x, L), w, bias, stride=1, padding=(pl * P, pr * P), dilation=dilation * P, groups=groups,
+                       pad_mode=pad_mode, pre_slope=pre_slope, pre_gate=pre_gate, post_act=post_act, post_slope=post_slope,
+                       out_scale=out_scale)
+        return y.reshape(B, cout, y.shape[-1] // P, P)
+    t_in = (L + P - 1) // P
     t_out = (t_in + pl + pr - dilation * (K - 1) - 1) // stride + 1
     if t_out < 0:
         raise PwgbError("conv1d: input shorter than the receptive field")

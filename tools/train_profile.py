@@ -1,0 +1,57 @@
+"""Top launches of one HiFi-GAN train step (CUDA events per libpwgb launch)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import collections
+
+import torch
+
+import bench
+from parallelwavegan_b200 import ops
+
+dev = torch.device("cuda:0")
+torch.cuda.set_device(0)
+# reuse the bench helper with instrumentation on
+import parallelwavegan_b200.train_step  # noqa: F401
+
+ops.PROFILE = None
+res = None
+orig = bench.measure_train_step
+
+
+def run():
+    from oracle import synth
+    from parallelwavegan_b200 import losses, models
+    from parallelwavegan_b200.train_step import GanTrainStep
+
+    g = models.HiFiGANGenerator(**bench.CFG)
+    g.load_state_dict(synth.synth_state_dict([(k, tuple(v.shape)) for k, v in g.state_dict().items()], 1234, 1.15))
+    d = models.HiFiGANMultiScaleMultiPeriodDiscriminator()
+    d.load_state_dict(synth.synth_state_dict([(k, tuple(v.shape)) for k, v in d.state_dict().items()], 4321, 1.4))
+    g, d = g.to(dev).train(), d.to(dev).train()
+    crit = {"mel": losses.MelSpectrogramLoss(fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80, fmin=0, fmax=11025, log_base=None).to(dev),
+            "gen_adv": losses.GeneratorAdversarialLoss(), "dis_adv": losses.DiscriminatorAdversarialLoss(), "feat_match": losses.FeatureMatchLoss()}
+    step = GanTrainStep(g, d, crit, torch.optim.Adam(g.parameters(), lr=2e-4, betas=(0.5, 0.9)), torch.optim.Adam(d.parameters(), lr=2e-4, betas=(0.5, 0.9)))
+    c = torch.randn(16, 80, 32, device=dev)
+    y = (torch.rand(16, 1, 8192, device=dev) - 0.5)
+    for _ in range(2):
+        step(c, y)
+    torch.cuda.synchronize()
+    ops.PROFILE = []
+    step(c, y)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    agg = collections.defaultdict(lambda: [0.0, 0, 0.0])
+    for name, fl, by, a, b, desc in prof:
+        k = f"{name:18s} {desc}"
+        agg[k][0] += a.elapsed_time(b)
+        agg[k][1] += 1
+        agg[k][2] += fl
+    tot = sum(v[0] for v in agg.values())
+    print("total instrumented ms", tot)
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+        print(f"{v[0]:8.2f} ms x{v[1]:3d} {v[2] / max(v[0], 1e-9) / 1e9:7.1f} TF  {k}")
+
+
+run()
