@@ -113,13 +113,17 @@ PWGB_API int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const fl
  * fp32 TMEM accumulation.  Weights are re-laid out once per weight update by
  * pwgb_conv1d_tc_pack_weight into a caller-owned buffer of
  * pwgb_conv1d_tc_packed_weight_bytes().  pwgb_conv1d_tc_supported() returns 1 when the
- * configuration can run here (stride 1, groups 1, cin % 32 == 0, cout % 16 == 0, cout <= 256,
- * halo fits shared memory); everything else stays on pwgb_conv1d_forward.
+ * configuration can run here (stride 1, cin/groups % 32 == 0, cout/groups % 16 == 0, halo fits shared
+ * memory; cout/groups > 256 and groups > 1 run as several launches); everything else stays on
+ * pwgb_conv1d_forward.
  * ---------------------------------------------------------------------- */
 /* bring-up aid (not part of the product contract): key 1 = tcgen05 descriptor variant */
 PWGB_API void pwgb_debug_set(int key, int value);
 PWGB_API size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kernel);
 PWGB_API int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream);
+/* grouped weights (cout, cin/groups, kernel): one image per (group, <=256-column chunk) */
+PWGB_API int pwgb_conv1d_tc_pack_weight_grouped(const float* w, int cin_per_group, int cout, int kernel, int groups, void* packed,
+                                       void* stream);
 PWGB_API int pwgb_conv1d_tc_supported(const pwgb_conv1d_desc* d);
 PWGB_API int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x, const void* packed_w, const float* bias,
                            const float* residual, float* y, void* stream);
@@ -213,6 +217,12 @@ PWGB_API int pwgb_avg_pool1d_forward(const float* x, float* y, int rows, int t_i
 PWGB_API size_t pwgb_conv1d_wgrad_workspace(const pwgb_conv1d_desc* d);
 PWGB_API int pwgb_conv1d_wgrad(const pwgb_conv1d_desc* d, const float* x, const float* gy, float g_slope, float* dw,
                       int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* tcgen05 variant (stride 1, groups 1, period 1, zero padding, cout % 128 == 0, cin % 32 == 0): the
+ * reduction over time is the MMA K dimension, both operands MN-major; same result contract. */
+PWGB_API int pwgb_conv1d_wgrad_tc_supported(const pwgb_conv1d_desc* d);
+PWGB_API size_t pwgb_conv1d_wgrad_tc_workspace(const pwgb_conv1d_desc* d);
+PWGB_API int pwgb_conv1d_wgrad_tc(const pwgb_conv1d_desc* d, const float* x, const float* gy, float g_slope, float* dw, void* ws,
+                         size_t ws_bytes, void* stream);
 PWGB_API int pwgb_act_backward(int mode, const float* g, const float* ref, float* out, long long n, float slope, float scale,
                       int accumulate, void* stream);
 PWGB_API int pwgb_bias_grad(const float* g, float* db, int batch, int channels, long long len, int accumulate, void* stream);

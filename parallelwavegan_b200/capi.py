@@ -75,6 +75,8 @@ def lib():
     L.pwgb_conv1d_tc_packed_weight_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     L.pwgb_conv1d_tc_pack_weight.restype = C.c_int
     L.pwgb_conv1d_tc_pack_weight.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.pwgb_conv1d_tc_pack_weight_grouped.restype = C.c_int
+    L.pwgb_conv1d_tc_pack_weight_grouped.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.pwgb_conv1d_tc_supported.restype = C.c_int
     L.pwgb_conv1d_tc_supported.argtypes = [C.POINTER(Conv1dDesc)]
     L.pwgb_conv1d_tc_forward.restype = C.c_int
@@ -107,6 +109,12 @@ def lib():
     L.pwgb_conv1d_wgrad_workspace.argtypes = [C.POINTER(Conv1dDesc)]
     L.pwgb_conv1d_wgrad.restype = C.c_int
     L.pwgb_conv1d_wgrad.argtypes = [C.POINTER(Conv1dDesc), vp, vp, C.c_float, vp, C.c_int, vp, C.c_size_t, vp]
+    L.pwgb_conv1d_wgrad_tc_supported.restype = C.c_int
+    L.pwgb_conv1d_wgrad_tc_supported.argtypes = [C.POINTER(Conv1dDesc)]
+    L.pwgb_conv1d_wgrad_tc_workspace.restype = C.c_size_t
+    L.pwgb_conv1d_wgrad_tc_workspace.argtypes = [C.POINTER(Conv1dDesc)]
+    L.pwgb_conv1d_wgrad_tc.restype = C.c_int
+    L.pwgb_conv1d_wgrad_tc.argtypes = [C.POINTER(Conv1dDesc), vp, vp, C.c_float, vp, vp, C.c_size_t, vp]
     L.pwgb_act_backward.restype = C.c_int
     L.pwgb_act_backward.argtypes = [C.c_int, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_int, vp]
     L.pwgb_bias_grad.restype = C.c_int
@@ -142,12 +150,14 @@ def reset_launch_count():
 EXPORTED_SYMBOLS = [
     "pwgb_last_error", "pwgb_version", "pwgb_compiled_arch", "pwgb_launch_count", "pwgb_reset_launch_count",
     "pwgb_conv1d_forward", "pwgb_conv_transpose1d_workspace", "pwgb_conv_transpose1d_forward",
-    "pwgb_conv1d_tc_packed_weight_bytes", "pwgb_conv1d_tc_pack_weight", "pwgb_conv1d_tc_supported",
+    "pwgb_conv1d_tc_packed_weight_bytes", "pwgb_conv1d_tc_pack_weight", "pwgb_conv1d_tc_pack_weight_grouped",
+    "pwgb_conv1d_tc_supported",
     "pwgb_conv1d_tc_forward", "pwgb_debug_set", "pwgb_wavenet_supported", "pwgb_wavenet_packed_bytes",
     "pwgb_wavenet_pack", "pwgb_wavenet_layer_forward", "pwgb_upsample_fir_forward",
     "pwgb_mr_stft_loss_workspace", "pwgb_mr_stft_loss_forward", "pwgb_stft_amplitude_forward",
     "pwgb_mel_project_forward", "pwgb_reduce_mean_forward", "pwgb_avg_pool1d_forward",
-    "pwgb_conv1d_wgrad_workspace", "pwgb_conv1d_wgrad", "pwgb_act_backward", "pwgb_bias_grad",
+    "pwgb_conv1d_wgrad_workspace", "pwgb_conv1d_wgrad", "pwgb_conv1d_wgrad_tc_supported",
+    "pwgb_conv1d_wgrad_tc_workspace", "pwgb_conv1d_wgrad_tc", "pwgb_act_backward", "pwgb_bias_grad",
     "pwgb_reduce_mean_backward", "pwgb_avg_pool1d_backward", "pwgb_axpby",
     "pwgb_stft_amplitude_backward", "pwgb_mel_project_backward",
 ]

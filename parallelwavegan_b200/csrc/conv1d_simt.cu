@@ -30,13 +30,12 @@ struct ConvK {
   int CI_T, XW, tiles_per_group;
 };
 
-template <int RCO, int WARPS_CO>
+template <int RCO, int WARPS_CO, int RT>
 __global__ void __launch_bounds__(256) conv1d_fwd_kernel(const ConvK p, const float* __restrict__ x,
                                                           const float* __restrict__ w,
                                                           const float* __restrict__ bias,
                                                           const float* __restrict__ res, float* __restrict__ y) {
   constexpr int WARPS_T = 8 / WARPS_CO;
-  constexpr int RT = 4;
   constexpr int CO_T = RCO * WARPS_CO;
   constexpr int TT = WARPS_T * 32 * RT;
   constexpr int WS = (CO_T % 4 == 0) ? CO_T + 4 : CO_T;
@@ -191,12 +190,12 @@ __global__ void __launch_bounds__(256) conv1d_fwd_kernel(const ConvK p, const fl
   }
 }
 
-template <int RCO, int WARPS_CO>
-static int launch_conv(ConvK p, const float* x, const float* w, const float* bias, const float* res, float* y,
+template <int RCO, int WARPS_CO, int RT>
+static int launch_conv_rt(ConvK p, const float* x, const float* w, const float* bias, const float* res, float* y,
                        cudaStream_t st) {
   constexpr int WARPS_T = 8 / WARPS_CO;
   constexpr int CO_T = RCO * WARPS_CO;
-  constexpr int TT = WARPS_T * 128;
+  constexpr int TT = WARPS_T * 32 * RT;
   constexpr int WS = (CO_T % 4 == 0) ? CO_T + 4 : CO_T;
   const int nrows_out = (TT + p.P - 2) / p.P + 1;
   const long long NR = (long long)(nrows_out - 1) * p.S + (long long)(p.K - 1) * p.D + 1;
@@ -215,7 +214,7 @@ static int launch_conv(ConvK p, const float* x, const float* w, const float* bia
   p.CI_T = ci_t;
   p.XW = (int)XW;
   p.tiles_per_group = ceil_div(p.Cout_g, CO_T);
-  auto kern = conv1d_fwd_kernel<RCO, WARPS_CO>;
+  auto kern = conv1d_fwd_kernel<RCO, WARPS_CO, RT>;
   if (bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
@@ -272,6 +271,15 @@ __global__ void __launch_bounds__(256) conv1d_small_cout_kernel(const ConvK p, c
       v = lrelu(v, p.post_slope);
     y[(long long)b * p.ybs + (long long)warp * p.Lout + o] = v * p.out_scale;
   }
+}
+
+// short sequences (discriminator tails, 10-50 positions per item): 1 position per lane instead of 4
+template <int RCO, int WARPS_CO>
+static int launch_conv(ConvK p, const float* x, const float* w, const float* bias, const float* res, float* y,
+                       cudaStream_t st) {
+  constexpr int WARPS_T = 8 / WARPS_CO;
+  if (p.Lout <= 40 * WARPS_T) return launch_conv_rt<RCO, WARPS_CO, 1>(p, x, w, bias, res, y, st);
+  return launch_conv_rt<RCO, WARPS_CO, 4>(p, x, w, bias, res, y, st);
 }
 
 int conv1d_forward_simt(const pwgb_conv1d_desc* d, const float* x, const float* w, const float* bias,

@@ -889,19 +889,27 @@ extern "C" size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kern
   return (size_t)(cin / KC) * kernel * 2 * (KC / 8) * cout * 16;
 }
 
-extern "C" int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream) {
+// w: (cout, cin_g, kernel) with cout = groups * cout_g.  One operand image per (group, column chunk),
+// chunk = tc_cout_chunk(cout / groups), laid out consecutively in row order.
+extern "C" int pwgb_conv1d_tc_pack_weight_grouped(const float* w, int cin_g, int cout, int kernel, int groups, void* packed,
+                                                  void* stream) {
   PWGB_CHECK_ARG(w && packed, "conv1d_tc_pack_weight: null argument");
-  PWGB_CHECK_ARG(cin > 0 && cin % KC == 0 && cout > 0 && kernel > 0, "conv1d_tc_pack_weight: cin must be a multiple of %d", KC);
-  const int chunk = tc_cout_chunk(cout);
-  PWGB_CHECK_ARG(chunk > 0, "conv1d_tc_pack_weight: cout must be a multiple of 16");
-  const size_t img = (size_t)(cin / KC) * kernel * 2 * (KC / 8) * chunk * 16;
+  PWGB_CHECK_ARG(cin_g > 0 && cin_g % KC == 0 && cout > 0 && kernel > 0 && groups > 0 && cout % groups == 0,
+                 "conv1d_tc_pack_weight: channels per group must be a multiple of %d", KC);
+  const int chunk = tc_cout_chunk(cout / groups);
+  PWGB_CHECK_ARG(chunk > 0, "conv1d_tc_pack_weight: cout / groups must be a multiple of 16");
+  const size_t img = (size_t)(cin_g / KC) * kernel * 2 * (KC / 8) * chunk * 16;
   for (int co = 0; co < cout; co += chunk) {
-    tc_pack_rows(w + (size_t)co * cin * kernel, (unsigned char*)packed + (size_t)(co / chunk) * img, cin, cin, chunk, kernel, 0,
-                 chunk, (cudaStream_t)stream);
+    tc_pack_rows(w + (size_t)co * cin_g * kernel, (unsigned char*)packed + (size_t)(co / chunk) * img, cin_g, cin_g, chunk, kernel,
+                 0, chunk, (cudaStream_t)stream);
     int rc = check_launch("tc_pack_weight_kernel");
     if (rc) return rc;
   }
   return PWGB_OK;
+}
+
+extern "C" int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream) {
+  return pwgb_conv1d_tc_pack_weight_grouped(w, cin, cout, kernel, 1, packed, stream);
 }
 
 // Output channels beyond the 256 accumulator columns of one launch are processed in column chunks
@@ -913,13 +921,19 @@ static int tc_cout_chunk(int cout) {
   return 0;
 }
 
+// Grouped convs run one launch per (group, column chunk): a group is an independent dense conv on a
+// channel slice (pointer offsets, batch strides of the full tensors).
 extern "C" int pwgb_conv1d_tc_supported(const pwgb_conv1d_desc* d) {
-  if (!d || d->cout <= 0) return 0;
-  const int chunk = tc_cout_chunk(d->cout);
+  if (!d || d->cout <= 0 || d->groups <= 0 || d->cin % d->groups || d->cout % d->groups) return 0;
+  const int G = d->groups;
+  if (G > 1 && (d->shuffle > 1 || d->pre_gate || G > 64)) return 0;
+  const int chunk = tc_cout_chunk(d->cout / G);
   if (!chunk) return 0;
   if (chunk != d->cout && d->shuffle > 1) return 0;
   pwgb_conv1d_desc c = *d;
   c.cout = chunk;
+  c.cin = d->cin / G;
+  c.groups = 1;
   TcK p;
   size_t bytes;
   return tc_plan(&c, p, bytes);
@@ -929,20 +943,27 @@ extern "C" int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x,
                                       const float* bias, const float* residual, float* y, void* stream) {
   PWGB_CHECK_ARG(d && x && packed_w && y, "conv1d_tc: null argument");
   PWGB_UNSUPPORTED_IF(!pwgb_conv1d_tc_supported(d), "conv1d_tc: configuration not supported by the tcgen05 path");
-  const int chunk = tc_cout_chunk(d->cout);
+  const int G = d->groups, cin_g = d->cin / G, cout_g = d->cout / G;
+  const int chunk = tc_cout_chunk(cout_g);
   pwgb_conv1d_desc c = *d;
   c.cout = chunk;
-  const size_t img = (size_t)(d->cin / KC) * d->kernel * 2 * (KC / 8) * chunk * 16;
-  for (int co = 0; co < d->cout; co += chunk) {
-    TcK p;
-    size_t bytes = 0;
-    tc_plan(&c, p, bytes);
-    p.co_off = co;
-    p.ybs = (long long)d->cout * d->t_out;
-    p.rbs = p.ybs;
-    int rc = tc_launch(p, bytes, x, (const unsigned char*)packed_w + (size_t)(co / chunk) * img, bias, residual, y,
-                       (cudaStream_t)stream);
-    if (rc) return rc;
+  c.cin = cin_g;
+  c.groups = 1;
+  const size_t img = (size_t)(cin_g / KC) * d->kernel * 2 * (KC / 8) * chunk * 16;
+  for (int g = 0; g < G; ++g) {
+    for (int co = 0; co < cout_g; co += chunk) {
+      TcK p;
+      size_t bytes = 0;
+      tc_plan(&c, p, bytes);
+      p.co_off = g * cout_g + co;
+      p.xbs = (long long)d->cin * (d->pre_gate ? 2 : 1) * d->t_in;
+      p.ybs = (long long)d->cout * d->t_out;
+      p.rbs = p.ybs;
+      const size_t iidx = (size_t)g * (cout_g / chunk) + co / chunk;
+      int rc = tc_launch(p, bytes, x + (size_t)g * cin_g * d->t_in, (const unsigned char*)packed_w + iidx * img, bias, residual,
+                         y, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
   }
   return PWGB_OK;
 }
@@ -1059,4 +1080,237 @@ extern "C" int pwgb_wavenet_layer_forward(const pwgb_wavenet_desc* d, const floa
   tc_plan(&c2, p, bytes, 0, d->skip_channels);
   const unsigned char* img2 = (const unsigned char*)packed + wn_image1_bytes(d) + wn_aux_bytes(d);
   return tc_launch(p, bytes, g_ws, img2, b_skip_out, x, x_out, st, nullptr, skips);
+}
+
+// ======================================================================================
+// Weight gradient on tcgen05:  dW[co, ci, k] = sum_{b,t} G[b,co,t] * X~[b,ci,t + k*D - pad]
+// is a GEMM whose reduction (MMA K) dimension is TIME.  Both operands are used MN-major: the same
+// [channel/8][time row][8 channels] shared-memory tile as the forward activation tile, read with the
+// roles of the two axes swapped (instruction descriptor a_major = b_major = MN), so a tap is again a
+// row offset in the descriptor.  M = 128 output channels (TMEM lanes), N = 32 input channels, one
+// accumulator column block per tap (<= 8 taps = 256 columns, 2 CTAs / SM), bf16x3 split, fp32
+// accumulation over the CTA's (batch, time-chunk) items; split partials are reduced deterministically.
+// ======================================================================================
+namespace pwgb {
+
+constexpr int WT_NC = 32;    // input channels per CTA (MMA N)
+constexpr int WT_TK = 128;   // time steps per item (8 MMA k-steps)
+constexpr int WT_TG = 8;     // taps per CTA
+constexpr int WT_THREADS = 160;
+
+struct WtK {
+  int B, Cin, Cout, T_in, T_out, K, D, padL;
+  float x_slope, g_slope;
+  int chunks_per_seq, nsplit, RX, ntg;
+  unsigned idesc;
+};
+
+__global__ void __launch_bounds__(WT_THREADS, 2)
+    wgrad_tc_kernel(const WtK p, const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // A (gradient) image: [hi|lo][16 co8][WT_TK rows][16 B];  B (activation) image: [hi|lo][4 ci8][RX rows][16 B]
+  unsigned char* a_buf = smem;
+  const int a_img = 16 * WT_TK * 16;
+  unsigned char* b_buf = smem + 2 * a_img;
+  const int b_img = (WT_NC / 8) * p.RX * 16;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(b_buf + 2 * b_img);
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int co0 = blockIdx.x * 128;
+  const int ci0 = (blockIdx.y / p.ntg) * WT_NC;
+  const int k0 = (blockIdx.y % p.ntg) * WT_TG;
+  const int ntap = min(WT_TG, p.K - k0);
+  const int split = blockIdx.z;
+  const unsigned bar0 = smem_u32(bars);
+  const unsigned FULL = bar0, EMPTY = bar0 + 8, ACC = bar0 + 16;
+  if (tid == 0) {
+    mbar_init(FULL, 128);
+    mbar_init(EMPTY, 1);
+    mbar_init(ACC, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+  const int total_items = p.B * p.chunks_per_seq;
+
+  if (warp < 4) {
+    unsigned n = 0;
+    for (int item = split; item < total_items; item += p.nsplit, ++n) {
+      const int b = item / p.chunks_per_seq;
+      const int t0 = (item - b * p.chunks_per_seq) * WT_TK;
+      mbar_wait(EMPTY, (n & 1) ^ 1);
+      // gradient tile: row = time, 8 output channels per 16 B
+      const float* gb = gy + ((long long)b * p.Cout + co0) * p.T_out;
+      for (int r = tid; r < WT_TK; r += 128) {
+        const int t = t0 + r;
+        const bool ok = t < p.T_out;
+#pragma unroll 4
+        for (int g = 0; g < 16; ++g) {
+          float u[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = ok ? lrelu(__ldg(gb + (long long)(g * 8 + j) * p.T_out + t), p.g_slope) : 0.f;
+          uint4 hi, lo;
+          split8(u, hi, lo);
+          *reinterpret_cast<uint4*>(a_buf + ((size_t)g * WT_TK + r) * 16) = hi;
+          *reinterpret_cast<uint4*>(a_buf + a_img + ((size_t)g * WT_TK + r) * 16) = lo;
+        }
+      }
+      // activation tile: rows t0 + k0*D - pad ... (+ RX)
+      const float* xb = x + ((long long)b * p.Cin + ci0) * p.T_in;
+      for (int r = tid; r < p.RX; r += 128) {
+        const long long ts = (long long)t0 + (long long)k0 * p.D - p.padL + r;
+        const bool ok = ts >= 0 && ts < p.T_in;
+#pragma unroll
+        for (int g = 0; g < WT_NC / 8; ++g) {
+          float u[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = ok ? lrelu(__ldg(xb + (long long)(g * 8 + j) * p.T_in + ts), p.x_slope) : 0.f;
+          uint4 hi, lo;
+          split8(u, hi, lo);
+          *reinterpret_cast<uint4*>(b_buf + ((size_t)g * p.RX + r) * 16) = hi;
+          *reinterpret_cast<uint4*>(b_buf + b_img + ((size_t)g * p.RX + r) * 16) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(FULL);
+    }
+    // ---- epilogue: lane = output channel, column = tap * WT_NC + ci
+    mbar_wait(ACC, 0);
+    tc_fence_after();
+    const int co = co0 + warp * 32 + lane;
+    float* dst = part + (((long long)split * p.Cout + co) * p.Cin + ci0) * p.K + k0;
+    for (int tp = 0; tp < ntap; ++tp) {
+      for (int c16 = 0; c16 < WT_NC; c16 += 16) {
+        unsigned r[16];
+        tc_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(tp * WT_NC + c16), r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[(long long)(c16 + j) * p.K + tp] = __uint_as_float(r[j]);
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---- MMA issuer (converged warp, elected lane)
+    const unsigned long long hi_const = ((unsigned long long)(1u << 14)) << 32;  // version = 1; SBO goes in per operand
+    const unsigned a16 = smem_u32(a_buf) >> 4, b16 = smem_u32(b_buf) >> 4;
+    // MN-major no-swizzle: LBO = 8-row K group stride (128 B = 8 units), SBO = MN 16 B-chunk stride (rows * 16 B)
+    const unsigned long long a_hi = ((unsigned long long)((unsigned)WT_TK & 0x3FFFu) << 32) | hi_const;
+    const unsigned long long b_hi = ((unsigned long long)((unsigned)p.RX & 0x3FFFu) << 32) | hi_const;
+    const unsigned lbo = 8u << 16;
+    const unsigned a_sub = (unsigned)(a_img >> 4), b_sub = (unsigned)(b_img >> 4);
+    unsigned n = 0;
+    for (int item = split; item < total_items; item += p.nsplit, ++n) {
+      mbar_wait_spin(FULL, n & 1);
+      tc_fence_after();
+      for (int ks = 0; ks < WT_TK / 16; ++ks) {
+        const unsigned long long ad = a_hi | (unsigned long long)(lbo + a16 + (unsigned)(ks * 16));
+        for (int tp = 0; tp < ntap; ++tp) {
+          const unsigned long long bd = b_hi | (unsigned long long)(lbo + b16 + (unsigned)(tp * p.D + ks * 16));
+          const unsigned acc = (n | (unsigned)ks) != 0 ? 1u : 0u;
+          tc_mma_x3_single(tmem_base + (unsigned)(tp * WT_NC), ad, bd, a_sub, b_sub, p.idesc, acc);
+        }
+      }
+      tc_commit(EMPTY);
+    }
+    tc_commit(ACC);
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+__global__ void wt_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int nsplit) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < nsplit; ++s) a += part[(long long)s * n + i];
+    out[i] = a;
+  }
+}
+
+static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
+  if (!d || d->stride != 1 || d->groups != 1 || (d->period > 1) || d->pre_gate || d->pad_mode != PWGB_PAD_ZERO) return 0;
+  if (d->cout % 128 != 0 || d->cin % WT_NC != 0 || d->kernel <= 0 || d->dilation <= 0) return 0;
+  if (d->t_valid > 0 && d->t_valid != d->t_in) return 0;
+  p.B = d->batch;
+  p.Cin = d->cin;
+  p.Cout = d->cout;
+  p.T_in = d->t_in;
+  p.T_out = d->t_out;
+  p.K = d->kernel;
+  p.D = d->dilation;
+  p.padL = d->pad_left;
+  p.x_slope = d->pre_slope;
+  p.g_slope = 1.f;
+  p.chunks_per_seq = ceil_div(d->t_out, WT_TK);
+  p.ntg = ceil_div(d->kernel, WT_TG);
+  const int tg = d->kernel < WT_TG ? d->kernel : WT_TG;
+  p.RX = WT_TK + (tg - 1) * d->dilation;
+  if ((size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (WT_NC / 8) * p.RX * 16 + 64 > 110 * 1024) return 0;
+  const long long items = (long long)p.B * p.chunks_per_seq;
+  const long long gxy = (long long)(d->cout / 128) * (d->cin / WT_NC) * p.ntg;
+  long long ns = (2 * 296 + gxy - 1) / gxy;
+  if (ns > items) ns = items;
+  if (ns > 64) ns = 64;
+  if (ns < 1) ns = 1;
+  p.nsplit = (int)ns;
+  // D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 @ 17, M >> 4 @ 24
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(WT_NC >> 3) << 17) | ((128u >> 4) << 24);
+  return 1;
+}
+
+}  // namespace pwgb
+
+extern "C" int pwgb_conv1d_wgrad_tc_supported(const pwgb_conv1d_desc* d) {
+  pwgb::WtK p;
+  return pwgb::wt_plan(d, p);
+}
+
+extern "C" size_t pwgb_conv1d_wgrad_tc_workspace(const pwgb_conv1d_desc* d) {
+  pwgb::WtK p;
+  if (!pwgb::wt_plan(d, p)) return 0;
+  return (size_t)p.nsplit * d->cout * d->cin * d->kernel * sizeof(float);
+}
+
+extern "C" int pwgb_conv1d_wgrad_tc(const pwgb_conv1d_desc* d, const float* x, const float* gy, float g_slope, float* dw,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  using namespace pwgb;
+  PWGB_CHECK_ARG(d && x && gy && dw && ws, "conv1d_wgrad_tc: null argument");
+  WtK p;
+  PWGB_UNSUPPORTED_IF(!wt_plan(d, p), "conv1d_wgrad_tc: configuration not supported by the tcgen05 path");
+  p.g_slope = g_slope;
+  const size_t need = pwgb_conv1d_wgrad_tc_workspace(d);
+  PWGB_CHECK_ARG(ws_bytes >= need, "conv1d_wgrad_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)d->cout * d->cin * d->kernel;
+  if (p.B == 0 || p.T_out == 0) {
+    cudaMemsetAsync(dw, 0, n * sizeof(float), st);
+    return PWGB_OK;
+  }
+  const size_t smem = (size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (WT_NC / 8) * p.RX * 16 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv1d_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PWGB_CUDA_ERROR;
+    }
+    attr_set = true;
+  }
+  dim3 grid(d->cout / 128, (d->cin / WT_NC) * p.ntg, p.nsplit);
+  wgrad_tc_kernel<<<grid, WT_THREADS, smem, st>>>(p, x, gy, (float*)ws);
+  int rc = check_launch("wgrad_tc_kernel");
+  if (rc) return rc;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  wt_reduce_kernel<<<blocks, 256, 0, st>>>((const float*)ws, dw, n, p.nsplit);
+  return check_launch("wt_reduce_kernel");
 }

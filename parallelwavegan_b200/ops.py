@@ -40,18 +40,18 @@ class _Prof:
 ENGINE = os.environ.get("PWGB_ENGINE", "auto")
 
 
-def packed_weight(w):
+def packed_weight(w, groups=1):
     """bf16 hi/lo operand image of a conv weight for the tcgen05 path, cached on the tensor
     object and invalidated by its version counter (in-place updates) -- a temporary such as a
     weight-norm product is simply re-packed every forward."""
     cache = getattr(w, "_pwgb_packed", None)
     if cache is not None and cache[0] == w._version and cache[1].device == w.device:
         return cache[1]
-    cout, cin, K = w.shape
+    cout, cin, K = w.shape  # cin = channels per group
     L = capi.lib()
     nbytes = L.pwgb_conv1d_tc_packed_weight_bytes(cin, cout, K)
     buf = torch.empty(nbytes // 4, device=w.device, dtype=torch.int32)
-    rc = L.pwgb_conv1d_tc_pack_weight(_p(w), cin, cout, K, _p(buf), _stream())
+    rc = L.pwgb_conv1d_tc_pack_weight_grouped(_p(w), cin, cout, K, int(groups), _p(buf), _stream())
     capi.check(rc, "pwgb_conv1d_tc_pack_weight")
     try:
         w._pwgb_packed = (w._version, buf)
@@ -160,7 +160,7 @@ def conv1d_raw(
                  f"B{B} cin{cin} cout{cout} k{K} d{dilation} s{stride} g{groups} T{t_out}" if PROFILE is not None else "")
     L = capi.lib()
     if ENGINE != "simt" and L.pwgb_conv1d_tc_supported(C.byref(d)):
-        pk = packed_weight(w)
+        pk = packed_weight(w, groups)
         prof.name = "conv1d_tc"
         rc = L.pwgb_conv1d_tc_forward(C.byref(d), _p(x), _p(pk), _p(bias), _p(residual), _p(out), _stream())
         capi.check(rc, "pwgb_conv1d_tc_forward")
@@ -390,6 +390,19 @@ def conv1d_wgrad(x, gy, w_shape, *, stride=1, padding=0, dilation=1, groups=1, p
                         groups=groups, pad_left=pl, pad_mode=_PAD[pad_mode], period=P, t_valid=L, pre_slope=float(x_slope),
                         out_scale=1.0)
     Lb = capi.lib()
+    if P > 1 and stride == 1 and L % P == 0:
+        # period conv with stride 1 == dilated 1-D conv over the flat axis (see conv1d_raw)
+        return conv1d_wgrad(x.reshape(B, cin, L), gy.reshape(B, cout, -1), w_shape, stride=1, padding=pl * P, dilation=dilation * P,
+                            groups=groups, pad_mode=pad_mode, x_slope=x_slope, g_slope=g_slope, period=1)
+    if ENGINE != "simt" and Lb.pwgb_conv1d_wgrad_tc_supported(C.byref(d)):
+        nbytes = Lb.pwgb_conv1d_wgrad_tc_workspace(C.byref(d))
+        ws = torch.empty(max(nbytes // 4, 1), device=x.device, dtype=torch.float32)
+        dw = torch.empty((cout, cin_g, K), device=x.device, dtype=torch.float32)
+        prof = _Prof("conv1d_wgrad_tc", 2.0 * B * cout * t_out * cin_g * K, 4.0 * (x.numel() + gy.numel()), f"B{B} cin{cin} cout{cout} k{K} d{dilation} T{t_out}")
+        rc = Lb.pwgb_conv1d_wgrad_tc(C.byref(d), _p(x), _p(gy), float(g_slope), _p(dw), _p(ws), C.c_size_t(nbytes), _stream())
+        capi.check(rc, "pwgb_conv1d_wgrad_tc")
+        prof.done()
+        return dw
     nbytes = Lb.pwgb_conv1d_wgrad_workspace(C.byref(d))
     ws = torch.empty(max(nbytes // 4, 1), device=x.device, dtype=torch.float32)
     dw = torch.empty((cout, cin_g, K), device=x.device, dtype=torch.float32)

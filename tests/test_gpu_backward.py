@@ -32,6 +32,10 @@ def dev():
         (16, 16, 41, 4, 1, 4, 20, 515, 2, 1.0, "lrelu"),
         (16, 32, 41, 2, 1, 16, 20, 300, 2, 1.0, "lrelu"),
         (32, 1, 3, 1, 1, 1, 1, 64, 2, 1.0, None),
+        (64, 128, 7, 1, 3, 1, 9, 300, 2, 0.1, None),       # tcgen05 wgrad (cout % 128 == 0)
+        (128, 256, 11, 1, 5, 1, 25, 517, 3, 0.1, None),    # two tap groups, several splits
+        (1024, 1024, 5, 1, 1, 1, 2, 40, 2, 1.0, "lrelu"),  # discriminator tail: column chunks + tcgen05 wgrad
+        (128, 128, 41, 1, 1, 4, 20, 200, 2, 1.0, "lrelu"), # grouped stride-1 conv on the tcgen05 path
     ],
 )
 def test_conv1d_gradients(dev, cin, cout, k, stride, dil, groups, pad, T, B, pre, post):
@@ -97,6 +101,26 @@ def test_period_conv_gradients(dev, period):
     od = ops.conv1d(hd, w2d, None, stride=3, padding=2, period=period)
     (od * gout.to(dev)).sum().backward()
     for name, a, r in (("dx", xd.grad, xr.grad), ("dw1", w1d.grad, w1r.grad), ("db1", b1d.grad, b1r.grad), ("dw2", w2d.grad, w2r.grad)):
+        assert rel_l2(a.cpu(), r) < GTOL, name
+
+
+def test_period_stride1_wide_gradients(dev):
+    """MPD tail layer (1024 -> 1024, (5,1), stride 1) as a dilated 1-D conv on the tcgen05 paths."""
+    from parallelwavegan_b200 import ops
+
+    B, R, P = 2, 9, 3
+    x = synth.randn((B, 256, R, P), 31)
+    w = synth.randn((256, 256, 5, 1), 32, 0.03)
+    b = synth.randn((256,), 33, 0.1)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    o = F.leaky_relu(F.conv2d(xr, wr, br, padding=(2, 0)), 0.1)
+    gout = synth.randn(o.shape, 5)
+    (o * gout).sum().backward()
+    xd, wd, bd = (t.clone().to(dev).requires_grad_(True) for t in (x, w, b))
+    od = ops.conv1d(xd, wd, bd, padding=2, period=P, post_act="lrelu", post_slope=0.1)
+    assert rel_l2(od.detach().cpu(), o.detach()) < GTOL
+    (od * gout.to(dev)).sum().backward()
+    for name, a, r in (("dx", xd.grad, xr.grad), ("dw", wd.grad, wr.grad), ("db", bd.grad, br.grad)):
         assert rel_l2(a.cpu(), r) < GTOL, name
 
 
