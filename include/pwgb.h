@@ -239,6 +239,19 @@ PWGB_API int pwgb_mel_project_backward(int batch, int frames, int bins, int n_me
                               const float* melmat, float eps, float log_scale, const float* gout, float* damp_x,
                               void* stream);
 
+/* Training pieces of the Parallel WaveGAN step (config C3): WaveNet gate and its adjoint, adjoint of
+ * pwgb_upsample_fir_forward (gx and/or the filter gradient), and the STFT loss on materialised
+ * magnitudes (terms: out2 (+)= weight * {sc, mag}, sums3 = {S1, S2, S3} kept for the adjoint;
+ * dmag: d loss / d xm given the upstream gradients gout2 = {g_sc, g_mag}). */
+PWGB_API int pwgb_gate_forward(const float* g, float* z, int batch, int half_channels, long long t, void* stream);
+PWGB_API int pwgb_gate_backward(const float* g, const float* gz, float* gg, int batch, int half_channels, long long t, void* stream);
+PWGB_API int pwgb_upsample_fir_backward(int rows, int rows_per_batch, int t_in, int scale, const float* x, const float* fir,
+                               const float* gy, long long gy_batch_stride, float* gx, float* dfir, void* stream);
+PWGB_API int pwgb_stft_loss_terms(const float* xm, const float* ym, long long n, float weight, int accumulate, float* out2,
+                         double* sums3, double* ws, int ws_doubles, void* stream);
+PWGB_API int pwgb_stft_loss_dmag(const float* xm, const float* ym, long long n, const double* sums3, const float* gout2,
+                        float weight, float* dxm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

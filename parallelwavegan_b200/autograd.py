@@ -235,3 +235,101 @@ class ScaledSumFn(torch.autograd.Function):
     def backward(ctx, g):
         gs = ops.act_backward("scale", g.contiguous(), scale=ctx.a)
         return (None,) + (gs,) * ctx.n
+
+
+# --------------------------------------------------------------------------
+# Parallel WaveGAN training pieces (config C3)
+# --------------------------------------------------------------------------
+
+
+class GateFn(torch.autograd.Function):
+    """z = tanh(g[:, :H]) * sigmoid(g[:, H:])  (layers/residual_block.py:128)."""
+
+    @staticmethod
+    def forward(ctx, g):
+        g = g.contiguous()
+        B, C2, T = g.shape
+        z = torch.empty((B, C2 // 2, T), device=g.device, dtype=torch.float32)
+        rc = capi.lib().pwgb_gate_forward(ops._p(g), ops._p(z), B, C2 // 2, T, ops._stream())
+        capi.check(rc, "pwgb_gate_forward")
+        ctx.save_for_backward(g)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        (g,) = ctx.saved_tensors
+        B, C2, T = g.shape
+        gg = torch.empty_like(g)
+        rc = capi.lib().pwgb_gate_backward(ops._p(g), ops._p(gz.contiguous()), ops._p(gg), B, C2 // 2, T, ops._stream())
+        capi.check(rc, "pwgb_gate_backward")
+        return gg
+
+
+class UpsampleFirFn(torch.autograd.Function):
+    """One stage of the conditioning upsampler (layers/upsample.py:122-128) with both adjoints."""
+
+    @staticmethod
+    def forward(ctx, x, fir, scale, out_channels):
+        y = ops.upsample_fir(x, fir, scale, out_channels=out_channels)
+        ctx.scale = scale
+        ctx.fir_shape = tuple(fir.shape)
+        ctx.save_for_backward(x, fir)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, fir = ctx.saved_tensors
+        B, Cc, T = x.shape
+        gy = gy.contiguous()
+        oc = gy.shape[1]
+        need_x, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx = torch.empty_like(x) if need_x else None
+        df = torch.empty(2 * ctx.scale + 1, device=x.device, dtype=torch.float32) if need_f else None
+        f1 = fir.detach().reshape(-1).contiguous()
+        rc = capi.lib().pwgb_upsample_fir_backward(B * Cc, Cc, T, int(ctx.scale), ops._p(x), ops._p(f1), ops._p(gy),
+                                                   oc * T * ctx.scale, ops._p(gx), ops._p(df), ops._stream())
+        capi.check(rc, "pwgb_upsample_fir_backward")
+        return gx, (df.reshape(ctx.fir_shape) if need_f else None), None, None
+
+
+class MrStftLossFn(torch.autograd.Function):
+    """MultiResolutionSTFTLoss.forward (losses/stft_loss.py:146-170) on materialised magnitudes, with the
+    gradient w.r.t. the predicted signal x.  Returns a 2-element tensor [sc, mag]."""
+
+    @staticmethod
+    def forward(ctx, x, y, fft_sizes, hop_sizes, win_lengths, *windows):
+        L = capi.lib()
+        n_res = len(fft_sizes)
+        out = torch.zeros(2, device=x.device, dtype=torch.float32)
+        saved = []
+        ws = torch.empty(3 * 1024, device=x.device, dtype=torch.float64)
+        for i, (f, h, wl, win) in enumerate(zip(fft_sizes, hop_sizes, win_lengths, windows)):
+            ax, ay = ops.stft_amplitude(x, y, f, h, wl, win, 1e-7)
+            sums = torch.empty(3, device=x.device, dtype=torch.float64)
+            rc = L.pwgb_stft_loss_terms(ops._p(ax), ops._p(ay), ax.numel(), 1.0 / n_res, int(i > 0), ops._p(out), ops._p(sums),
+                                        ops._p(ws), 3 * 1024, ops._stream())
+            capi.check(rc, "pwgb_stft_loss_terms")
+            saved += [ax, ay, sums]
+        ctx.cfg = (tuple(fft_sizes), tuple(hop_sizes), tuple(win_lengths))
+        ctx.save_for_backward(x, *windows, *saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        fft_sizes, hop_sizes, win_lengths = ctx.cfg
+        n_res = len(fft_sizes)
+        t = ctx.saved_tensors
+        x, windows, saved = t[0], t[1 : 1 + n_res], t[1 + n_res :]
+        gout = gout.contiguous()
+        L = capi.lib()
+        dx = torch.zeros_like(x)
+        for i in range(n_res):
+            ax, ay, sums = saved[3 * i : 3 * i + 3]
+            dax = torch.empty_like(ax)
+            rc = L.pwgb_stft_loss_dmag(ops._p(ax), ops._p(ay), ax.numel(), ops._p(sums), ops._p(gout), 1.0 / n_res, ops._p(dax), ops._stream())
+            capi.check(rc, "pwgb_stft_loss_dmag")
+            d = capi.StftDesc(batch=x.shape[0], t=x.shape[1], n_fft=int(fft_sizes[i]), hop=int(hop_sizes[i]),
+                              win_length=int(win_lengths[i]), clamp_eps=1e-7)
+            rc = L.pwgb_stft_amplitude_backward(C.byref(d), ops._p(x), ops._p(windows[i]), ops._p(ax), ops._p(dax), ops._p(dx), ops._stream())
+            capi.check(rc, "pwgb_stft_amplitude_backward")
+        return (dx, None, None, None, None) + (None,) * n_res

@@ -129,6 +129,16 @@ def lib():
     L.pwgb_stft_amplitude_backward.argtypes = [C.POINTER(StftDesc), vp, vp, vp, vp, vp, vp]
     L.pwgb_mel_project_backward.restype = C.c_int
     L.pwgb_mel_project_backward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp]
+    L.pwgb_gate_forward.restype = C.c_int
+    L.pwgb_gate_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
+    L.pwgb_gate_backward.restype = C.c_int
+    L.pwgb_gate_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
+    L.pwgb_upsample_fir_backward.restype = C.c_int
+    L.pwgb_upsample_fir_backward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_longlong, vp, vp, vp]
+    L.pwgb_stft_loss_terms.restype = C.c_int
+    L.pwgb_stft_loss_terms.argtypes = [vp, vp, C.c_longlong, C.c_float, C.c_int, vp, vp, vp, C.c_int, vp]
+    L.pwgb_stft_loss_dmag.restype = C.c_int
+    L.pwgb_stft_loss_dmag.argtypes = [vp, vp, C.c_longlong, vp, vp, C.c_float, vp, vp]
     _lib = L
     return L
 
@@ -159,5 +169,6 @@ EXPORTED_SYMBOLS = [
     "pwgb_conv1d_wgrad_workspace", "pwgb_conv1d_wgrad", "pwgb_conv1d_wgrad_tc_supported",
     "pwgb_conv1d_wgrad_tc_workspace", "pwgb_conv1d_wgrad_tc", "pwgb_act_backward", "pwgb_bias_grad",
     "pwgb_reduce_mean_backward", "pwgb_avg_pool1d_backward", "pwgb_axpby",
-    "pwgb_stft_amplitude_backward", "pwgb_mel_project_backward",
+    "pwgb_stft_amplitude_backward", "pwgb_mel_project_backward", "pwgb_gate_forward", "pwgb_gate_backward",
+    "pwgb_upsample_fir_backward", "pwgb_stft_loss_terms", "pwgb_stft_loss_dmag",
 ]

@@ -203,6 +203,81 @@ __global__ void axpby_kernel(long long n, float a, const float* __restrict__ x, 
     y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
 }
 
+// WaveNet gate (layers/residual_block.py:128): z[b,h,t] = tanh(g[b,h,t]) * sigmoid(g[b,H+h,t])
+__global__ void gate_forward_kernel(const float* __restrict__ g, float* __restrict__ z, int B, int H, long long T) {
+  const long long n = (long long)B * H * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i % T;
+    const long long bh = i / T;
+    const int h = (int)(bh % H);
+    const long long b = bh / H;
+    const float a = g[(b * 2 * H + h) * T + t];
+    const float s = g[(b * 2 * H + H + h) * T + t];
+    z[i] = tanhf(a) * sigmoidf_(s);
+  }
+}
+__global__ void gate_backward_kernel(const float* __restrict__ g, const float* __restrict__ gz, float* __restrict__ gg, int B,
+                                     int H, long long T) {
+  const long long n = (long long)B * H * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i % T;
+    const long long bh = i / T;
+    const int h = (int)(bh % H);
+    const long long b = bh / H;
+    const long long ia = (b * 2 * H + h) * T + t, is = (b * 2 * H + H + h) * T + t;
+    const float ta = tanhf(g[ia]);
+    const float sg = sigmoidf_(g[is]);
+    const float go = gz[i];
+    gg[ia] = go * sg * (1.f - ta * ta);
+    gg[is] = go * ta * sg * (1.f - sg);
+  }
+}
+
+// adjoints of upsample_fir_kernel: y[r,o] = sum_k f[k] x[r, (o+k-s)/s]
+__global__ void upsample_fir_backward_x_kernel(int t_in, int s, const float* __restrict__ gy, const float* __restrict__ fir,
+                                               float* __restrict__ gx, int rows_per_batch, long long gybs) {
+  extern __shared__ float f[];
+  for (int i = threadIdx.x; i < 2 * s + 1; i += blockDim.x) f[i] = fir[i];
+  __syncthreads();
+  const int r = blockIdx.y;
+  const int t_out = t_in * s;
+  const float* gr = gy + (long long)(r / rows_per_batch) * gybs + (long long)(r % rows_per_batch) * t_out;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t_in; i += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    // positions q = o + k - s with q / s == i  <=>  q in [i*s, i*s + s)
+    for (int q = i * s; q < i * s + s; ++q)
+      for (int k = 0; k <= 2 * s; ++k) {
+        const int o = q - k + s;
+        if (o >= 0 && o < t_out) acc = fmaf(f[k], gr[o], acc);
+      }
+    gx[(long long)r * t_in + i] = acc;
+  }
+}
+// df[k] = sum_{r,o} gy[r,o] * x[r,(o+k-s)/s]  -- one CTA per tap, fixed order
+__global__ void __launch_bounds__(256) upsample_fir_backward_f_kernel(int rows, int t_in, int s, const float* __restrict__ x,
+                                                                       const float* __restrict__ gy, float* __restrict__ df,
+                                                                       int rows_per_batch, long long gybs) {
+  __shared__ double red[256];
+  const int k = blockIdx.x;
+  const int t_out = t_in * s;
+  double a = 0;
+  for (int r = 0; r < rows; ++r) {
+    const float* gr = gy + (long long)(r / rows_per_batch) * gybs + (long long)(r % rows_per_batch) * t_out;
+    const float* xr = x + (long long)r * t_in;
+    for (int o = threadIdx.x; o < t_out; o += 256) {
+      const int q = o + k - s;
+      if (q >= 0 && q < t_out) a += (double)gr[o] * xr[q / s];
+    }
+  }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) df[k] = (float)red[0];
+}
+
 static int grid_for(long long n) {
   long long b = (n + 255) / 256;
   return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
@@ -322,4 +397,42 @@ extern "C" int pwgb_axpby(long long n, float a, const float* x, float b, float* 
   if (n == 0) return PWGB_OK;
   axpby_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
   return check_launch("axpby_kernel");
+}
+
+extern "C" int pwgb_gate_forward(const float* g, float* z, int batch, int half_channels, long long t, void* stream) {
+  PWGB_CHECK_ARG(g && z && batch >= 0 && half_channels > 0 && t >= 0, "gate_forward: bad arguments");
+  const long long n = (long long)batch * half_channels * t;
+  if (n == 0) return PWGB_OK;
+  gate_forward_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(g, z, batch, half_channels, t);
+  return check_launch("gate_forward_kernel");
+}
+
+extern "C" int pwgb_gate_backward(const float* g, const float* gz, float* gg, int batch, int half_channels, long long t,
+                                  void* stream) {
+  PWGB_CHECK_ARG(g && gz && gg && batch >= 0 && half_channels > 0 && t >= 0, "gate_backward: bad arguments");
+  const long long n = (long long)batch * half_channels * t;
+  if (n == 0) return PWGB_OK;
+  gate_backward_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(g, gz, gg, batch, half_channels, t);
+  return check_launch("gate_backward_kernel");
+}
+
+extern "C" int pwgb_upsample_fir_backward(int rows, int rows_per_batch, int t_in, int scale, const float* x, const float* fir,
+                                          const float* gy, long long gy_batch_stride, float* gx, float* dfir, void* stream) {
+  PWGB_CHECK_ARG(fir && gy && (gx || (dfir && x)), "upsample_fir_backward: null argument");
+  PWGB_CHECK_ARG(rows >= 0 && rows_per_batch > 0 && t_in > 0 && scale > 0 && rows % rows_per_batch == 0, "upsample_fir_backward: bad sizes");
+  PWGB_UNSUPPORTED_IF(rows > 65535, "upsample_fir_backward: too many rows");
+  if (rows == 0) return PWGB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long gybs = gy_batch_stride ? gy_batch_stride : (long long)rows_per_batch * t_in * scale;
+  if (gx) {
+    dim3 grid(ceil_div(t_in, 256) < 64 ? ceil_div(t_in, 256) : 64, rows);
+    upsample_fir_backward_x_kernel<<<grid, 256, (2 * scale + 1) * sizeof(float), st>>>(t_in, scale, gy, fir, gx, rows_per_batch, gybs);
+    int rc = check_launch("upsample_fir_backward_x_kernel");
+    if (rc) return rc;
+  }
+  if (dfir) {
+    upsample_fir_backward_f_kernel<<<2 * scale + 1, 256, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
+    return check_launch("upsample_fir_backward_f_kernel");
+  }
+  return PWGB_OK;
 }

@@ -331,6 +331,61 @@ __global__ void __launch_bounds__(128) mel_project_backward_kernel(int B, int fr
   }
 }
 
+// training form of the STFT loss on materialised magnitudes: three double sums, then d loss / d xm
+__global__ void __launch_bounds__(256) stft_loss_terms_kernel(const float* __restrict__ xm, const float* __restrict__ ym,
+                                                               long long n, double* __restrict__ sums) {
+  __shared__ double red[3][256];
+  double a = 0, b = 0, c = 0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float x = xm[i], y = ym[i];
+    const float d = y - x;
+    a += (double)d * d;
+    b += (double)y * y;
+    c += fabsf(logf(y) - logf(x));
+  }
+  red[0][threadIdx.x] = a;
+  red[1][threadIdx.x] = b;
+  red[2][threadIdx.x] = c;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int q = 0; q < 3; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) sums[blockIdx.x * 3 + threadIdx.x] = red[threadIdx.x][0];
+}
+__global__ void stft_loss_finish_kernel(const double* __restrict__ part, int nblocks, long long n, double* __restrict__ sums3,
+                                        float* __restrict__ out2, float weight, int accumulate) {
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int i = 0; i < nblocks; ++i) {
+      a += part[3 * i];
+      b += part[3 * i + 1];
+      c += part[3 * i + 2];
+    }
+    sums3[0] = a;
+    sums3[1] = b;
+    sums3[2] = c;
+    const float sc = (float)(sqrt(a) / sqrt(b)) * weight, mg = (float)(c / (double)n) * weight;
+    out2[0] = (accumulate ? out2[0] : 0.f) + sc;
+    out2[1] = (accumulate ? out2[1] : 0.f) + mg;
+  }
+}
+// dxm = g_sc * w * d sc/d xm + g_mag * w * d mag/d xm,  sc = sqrt(S1)/sqrt(S2), mag = S3 / n
+__global__ void stft_loss_dmag_kernel(const float* __restrict__ xm, const float* __restrict__ ym, long long n,
+                                      const double* __restrict__ sums3, const float* __restrict__ gout2, float weight,
+                                      float* __restrict__ dxm) {
+  const double s1 = sums3[0], s2 = sums3[1];
+  const float ksc = s1 > 0 ? (float)(gout2[0] * weight / (sqrt(s1) * sqrt(s2))) : 0.f;
+  const float kmg = gout2[1] * weight / (float)n;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float x = xm[i], y = ym[i];
+    const float dl = logf(y) - logf(x);
+    const float sg = dl > 0.f ? 1.f : (dl < 0.f ? -1.f : 0.f);
+    dxm[i] = -ksc * (y - x) - kmg * sg / x;
+  }
+}
+
 static int fill(const pwgb_stft_desc* d, StftK& p) {
   if (!d || d->batch < 0 || d->t <= 0 || d->n_fft < 16 || d->n_fft > 4096 || (d->n_fft & (d->n_fft - 1)) ||
       d->hop <= 0 || d->win_length <= 0 || d->win_length > d->n_fft || d->t <= d->n_fft / 2)
@@ -451,4 +506,27 @@ extern "C" int pwgb_mel_project_backward(int batch, int frames, int bins, int n_
   mel_project_backward_kernel<<<dim3(frames, batch), 128, (2 * (size_t)bins + n_mels) * sizeof(float), (cudaStream_t)stream>>>(
       batch, frames, bins, n_mels, amp_x, amp_y, melmat, eps, log_scale, gout, scale, damp_x);
   return check_launch("mel_project_backward_kernel");
+}
+
+extern "C" int pwgb_stft_loss_terms(const float* xm, const float* ym, long long n, float weight, int accumulate, float* out2,
+                                    double* sums3, double* ws, int ws_doubles, void* stream) {
+  PWGB_CHECK_ARG(xm && ym && out2 && sums3 && ws && n > 0 && ws_doubles >= 3, "stft_loss_terms: bad arguments");
+  int blocks = (int)((n + 4095) / 4096);
+  if (blocks > ws_doubles / 3) blocks = ws_doubles / 3;
+  if (blocks > 1024) blocks = 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  stft_loss_terms_kernel<<<blocks, 256, 0, st>>>(xm, ym, n, ws);
+  int rc = check_launch("stft_loss_terms_kernel");
+  if (rc) return rc;
+  stft_loss_finish_kernel<<<1, 32, 0, st>>>(ws, blocks, n, sums3, out2, weight, accumulate);
+  return check_launch("stft_loss_finish_kernel");
+}
+
+extern "C" int pwgb_stft_loss_dmag(const float* xm, const float* ym, long long n, const double* sums3, const float* gout2,
+                                   float weight, float* dxm, void* stream) {
+  PWGB_CHECK_ARG(xm && ym && sums3 && gout2 && dxm && n > 0, "stft_loss_dmag: bad arguments");
+  int blocks = (int)((n + 2047) / 2048);
+  if (blocks > 2368) blocks = 2368;
+  stft_loss_dmag_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(xm, ym, n, sums3, gout2, weight, dxm);
+  return check_launch("stft_loss_dmag_kernel");
 }

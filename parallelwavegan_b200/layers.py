@@ -275,6 +275,11 @@ class WaveNetResidualBlock(torch.nn.Module):
         if skips is None:
             skips = torch.zeros((x.shape[0], self.conv1x1_skip.out_channels, x.shape[2]), device=x.device, dtype=x.dtype)
         aux = self.conv1x1_aux
+        if torch.is_grad_enabled() and (x.requires_grad or next(self.parameters()).requires_grad):
+            xo, s = self._forward_train(x, c)
+            if skips is not None:
+                raise PwgbError("in-place skip accumulation is inference-only; use the returned skip tensor under autograd")
+            return xo, s
         x_out = ops.wavenet_layer(
             x, c,
             effective_weight(self.conv), self.conv.bias,
@@ -284,6 +289,27 @@ class WaveNetResidualBlock(torch.nn.Module):
             self.dilation, skips, self.aux_channels, cache=self._cache,
         )
         return x_out, skips
+
+
+def _wn_train(self, x, c):
+    """Differentiable composition of the layer (every op's forward and backward is a libpwgb kernel):
+    g = conv_dil(x) + W_aux c ; z = gate(g) ; s = W_skip z ; x' = (W_out z + x) * sqrt(0.5)."""
+    from .autograd import GateFn
+
+    k = self.conv.kernel_size[0]
+    g = ops.conv1d(x, effective_weight(self.conv), self.conv.bias, dilation=self.dilation, padding=(k - 1) // 2 * self.dilation)
+    if c is not None:
+        wa = effective_weight(self.conv1x1_aux)
+        if c.shape[1] != wa.shape[1]:  # conditioning stored channel-padded (zeros): pad the weight columns
+            wa = torch.nn.functional.pad(wa, (0, 0, 0, c.shape[1] - wa.shape[1]))
+        g = ops.conv1d(c, wa, None, residual=g)
+    z = GateFn.apply(g)
+    s = ops.conv1d(z, effective_weight(self.conv1x1_skip), self.conv1x1_skip.bias)
+    xo = ops.conv1d(z, effective_weight(self.conv1x1_out), self.conv1x1_out.bias, residual=x, out_scale=math.sqrt(0.5))
+    return xo, s
+
+
+WaveNetResidualBlock._forward_train = _wn_train
 
 
 class Stretch2d(torch.nn.Module):
@@ -325,7 +351,13 @@ class UpsampleNetwork(torch.nn.Module):
         n = len(self.upsample_scales)
         for i, s in enumerate(self.upsample_scales):
             fir = effective_weight(self.up_layers[2 * i + 1])
-            c = ops.upsample_fir(c, fir, s, out_channels=out_channels if i == n - 1 else None)
+            oc = out_channels if i == n - 1 else None
+            if torch.is_grad_enabled() and (c.requires_grad or fir.requires_grad):
+                from .autograd import UpsampleFirFn
+
+                c = UpsampleFirFn.apply(c, fir, s, oc)
+            else:
+                c = ops.upsample_fir(c, fir, s, out_channels=oc)
         return c
 
 

@@ -66,6 +66,16 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
 
     def forward(self, x, y):
         """x, y: (B, T) or (B, #subband, T) -> (sc_loss, mag_loss)."""
+        if torch.is_grad_enabled() and x.requires_grad:
+            from .autograd import MrStftLossFn
+
+            if x.dim() == 3:
+                x = x.reshape(-1, x.size(2))
+                y = y.reshape(-1, y.size(2))
+            out = MrStftLossFn.apply(x.contiguous(), y.contiguous(), [f.fft_size for f in self.stft_losses],
+                                     [f.shift_size for f in self.stft_losses], [f.win_length for f in self.stft_losses],
+                                     *[f.window for f in self.stft_losses])
+            return out[0], out[1]
         out = ops.mr_stft_loss(
             x, y,
             [f.fft_size for f in self.stft_losses],

@@ -370,6 +370,17 @@ class ParallelWaveGANGenerator(_GeneratorBase):
             c = cp
         fc = self.first_conv
         x = ops.conv1d(z, effective_weight(fc), fc.bias)
+        if torch.is_grad_enabled() and next(self.parameters()).requires_grad:
+            from .autograd import ScaledSumFn  # training: differentiable layer composition
+
+            hs = []
+            for f in self.conv_layers:
+                x, h = f._forward_train(x, c)
+                hs.append(h)
+            skips = ScaledSumFn.apply(self._skip_scale, *hs)
+            l1, l3 = self.last_conv_layers[1], self.last_conv_layers[3]
+            h = ops.conv1d(skips, effective_weight(l1), l1.bias, pre_slope=0.0)
+            return ops.conv1d(h, effective_weight(l3), l3.bias, pre_slope=0.0)
         skips = torch.zeros((x.shape[0], self.conv_layers[0].conv1x1_skip.out_channels, x.shape[2]), device=x.device, dtype=torch.float32)
         for f in self.conv_layers:
             x, _ = f(x, c, skips)
