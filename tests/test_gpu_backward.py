@@ -236,8 +236,8 @@ def test_pwg_train_step_gradients(dev):
     names = list(leaf_g)
 
     def grads_ref(loss):
-        gs = torch.autograd.grad(loss, [leaf_g[k] for k in names], retain_graph=True)
-        return dict(zip(names, gs))
+        gs = torch.autograd.grad(loss, [leaf_g[k] for k in names], retain_graph=True, allow_unused=True)
+        return {k: (v if v is not None else torch.zeros_like(leaf_g[k])) for k, v in zip(names, gs)}
 
     ref_terms = {"stft": grads_ref(sc + mag), "adv": grads_ref(adv), "out": grads_ref((y_ref * y).sum())}
 
@@ -255,14 +255,19 @@ def test_pwg_train_step_gradients(dev):
     params = dict(g.named_parameters())
 
     def grads_ours(loss):
-        gs = torch.autograd.grad(loss, [params[k] for k in names], retain_graph=True)
-        return dict(zip(names, gs))
+        gs = torch.autograd.grad(loss, [params[k] for k in names], retain_graph=True, allow_unused=True)
+        return {k: (v if v is not None else torch.zeros_like(params[k])) for k, v in zip(names, gs)}
 
     ours = {"stft": grads_ours(sc_o + mag_o), "adv": grads_ours(adv_o), "out": grads_ours((y_hat * y.to(dev)).sum())}
     bad = []
     for term in ("out", "adv", "stft"):
         for k in names:
-            e = rel_l2(ours[term][k].cpu(), ref_terms[term][k])
+            r = ref_terms[term][k]
+            if float(r.abs().max()) == 0.0:  # parameter without influence (last layer's residual 1x1)
+                assert float(ours[term][k].abs().max()) == 0.0, (term, k)
+                continue
+            e = rel_l2(ours[term][k].cpu(), r)
             if e >= 5e-3:
                 bad.append((term, k, round(e, 4)))
+    print("PWG-GRAD-BAD", len(bad), bad)
     assert not bad, bad[:12]
