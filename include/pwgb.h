@@ -217,7 +217,7 @@ PWGB_API int pwgb_avg_pool1d_forward(const float* x, float* y, int rows, int t_i
 PWGB_API size_t pwgb_conv1d_wgrad_workspace(const pwgb_conv1d_desc* d);
 PWGB_API int pwgb_conv1d_wgrad(const pwgb_conv1d_desc* d, const float* x, const float* gy, float g_slope, float* dw,
                       int accumulate, void* ws, size_t ws_bytes, void* stream);
-/* tcgen05 variant (stride 1, groups 1, period 1, zero padding, cout % 128 == 0, cin % 32 == 0): the
+/* tcgen05 variant (stride 1, groups 1, period 1, zero padding, cout % 8 == 0 (>= 32), cin % 32 == 0): the
  * reduction over time is the MMA K dimension, both operands MN-major; same result contract. */
 PWGB_API int pwgb_conv1d_wgrad_tc_supported(const pwgb_conv1d_desc* d);
 PWGB_API size_t pwgb_conv1d_wgrad_tc_workspace(const pwgb_conv1d_desc* d);

@@ -1154,8 +1154,9 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
 #pragma unroll 4
         for (int g = 0; g < 16; ++g) {
           float u[8];
+          const bool cok = ok && (co0 + g * 8 < p.Cout);  // Cout % 8 == 0: whole 8-channel groups are in or out
 #pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = ok ? lrelu(__ldg(gb + (long long)(g * 8 + j) * p.T_out + t), p.g_slope) : 0.f;
+          for (int j = 0; j < 8; ++j) u[j] = cok ? lrelu(__ldg(gb + (long long)(g * 8 + j) * p.T_out + t), p.g_slope) : 0.f;
           uint4 hi, lo;
           split8(u, hi, lo);
           *reinterpret_cast<uint4*>(a_buf + ((size_t)g * WT_TK + r) * 16) = hi;
@@ -1185,14 +1186,17 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
     mbar_wait(ACC, 0);
     tc_fence_after();
     const int co = co0 + warp * 32 + lane;
-    float* dst = part + (((long long)split * p.Cout + co) * p.Cin + ci0) * p.K + k0;
+    const bool co_ok = co < p.Cout;
+    float* dst = part + (((long long)split * p.Cout + (co_ok ? co : 0)) * p.Cin + ci0) * p.K + k0;
     for (int tp = 0; tp < ntap; ++tp) {
       for (int c16 = 0; c16 < WT_NC; c16 += 16) {
         unsigned r[16];
         tc_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(tp * WT_NC + c16), r);
         tc_wait_ld();
+        if (co_ok) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[(long long)(c16 + j) * p.K + tp] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) dst[(long long)(c16 + j) * p.K + tp] = __uint_as_float(r[j]);
+        }
       }
     }
     tc_fence_before();
@@ -1238,7 +1242,7 @@ __global__ void wt_reduce_kernel(const float* __restrict__ part, float* __restri
 
 static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
   if (!d || d->stride != 1 || d->groups != 1 || (d->period > 1) || d->pre_gate || d->pad_mode != PWGB_PAD_ZERO) return 0;
-  if (d->cout % 128 != 0 || d->cin % WT_NC != 0 || d->kernel <= 0 || d->dilation <= 0) return 0;
+  if (d->cout % 8 != 0 || d->cout < 32 || d->cin % WT_NC != 0 || d->kernel <= 0 || d->dilation <= 0) return 0;
   if (d->t_valid > 0 && d->t_valid != d->t_in) return 0;
   p.B = d->batch;
   p.Cin = d->cin;
@@ -1256,7 +1260,7 @@ static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
   p.RX = WT_TK + (tg - 1) * d->dilation;
   if ((size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (WT_NC / 8) * p.RX * 16 + 64 > 110 * 1024) return 0;
   const long long items = (long long)p.B * p.chunks_per_seq;
-  const long long gxy = (long long)(d->cout / 128) * (d->cin / WT_NC) * p.ntg;
+  const long long gxy = (long long)ceil_div(d->cout, 128) * (d->cin / WT_NC) * p.ntg;
   long long ns = (2 * 296 + gxy - 1) / gxy;
   if (ns > items) ns = items;
   if (ns > 64) ns = 64;
@@ -1305,7 +1309,7 @@ extern "C" int pwgb_conv1d_wgrad_tc(const pwgb_conv1d_desc* d, const float* x, c
     }
     attr_set = true;
   }
-  dim3 grid(d->cout / 128, (d->cin / WT_NC) * p.ntg, p.nsplit);
+  dim3 grid(ceil_div(d->cout, 128), (d->cin / WT_NC) * p.ntg, p.nsplit);
   wgrad_tc_kernel<<<grid, WT_THREADS, smem, st>>>(p, x, gy, (float*)ws);
   int rc = check_launch("wgrad_tc_kernel");
   if (rc) return rc;

@@ -36,6 +36,8 @@ def dev():
         (128, 256, 11, 1, 5, 1, 25, 517, 3, 0.1, None),    # two tap groups, several splits
         (1024, 1024, 5, 1, 1, 1, 2, 40, 2, 1.0, "lrelu"),  # discriminator tail: column chunks + tcgen05 wgrad
         (128, 128, 41, 1, 1, 4, 20, 200, 2, 1.0, "lrelu"), # grouped stride-1 conv on the tcgen05 path
+        (64, 64, 3, 1, 2, 1, 2, 1000, 2, 0.2, None),       # tcgen05 wgrad with a half-filled 128-row M tile
+        (32, 160, 1, 1, 1, 1, 0, 300, 2, 1.0, None),       # cout = 128 + 32
     ],
 )
 def test_conv1d_gradients(dev, cin, cout, k, stride, dil, groups, pad, T, B, pre, post):
