@@ -106,6 +106,40 @@ __global__ void __launch_bounds__(256) conv1d_wgrad_kernel(const WgK p, const fl
   }
 }
 
+// Narrow weight gradients (cin/groups <= 4 or cout <= 4: waveform-side and logit convs): few outputs,
+// very long reduction.  One CTA = one (batch item, 2048-position chunk); a warp owns one (co, ci, k)
+// output at a time with the time positions across its lanes (coalesced), shuffle-reduced.
+__global__ void __launch_bounds__(256) conv1d_wgrad_narrow_kernel(const WgK p, const float* __restrict__ x,
+                                                                   const float* __restrict__ gy, float* __restrict__ part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = 2048;
+  const int b = blockIdx.x / p.chunks_per_seq;
+  const int o0 = (blockIdx.x - b * p.chunks_per_seq) * chunk;
+  const int o1 = min(o0 + chunk, p.Lout);
+  const int nout = p.Cout * p.Cin_g * p.K;
+  float* dst = part + (long long)blockIdx.x * nout;
+  for (int q = warp; q < nout; q += 8) {
+    const int k = q % p.K;
+    const int ci = (q / p.K) % p.Cin_g;
+    const int co = q / (p.K * p.Cin_g);
+    const int g = co / p.Cout_g;
+    const float* gr = gy + ((long long)b * p.Cout + co) * p.Lout;
+    const float* xr = x + ((long long)b * p.Cin + g * p.Cin_g + ci) * p.xcs;
+    float acc = 0.f;
+    for (int o = o0 + lane; o < o1; o += 32) {
+      const int to = o / p.P, j = o - to * p.P;
+      const long long row = (long long)to * p.S + (long long)k * p.D - p.padL;
+      if (row < 0 || row >= p.t_in) continue;
+      long long li = row * p.P + j;
+      if (li >= p.t_valid) li = 2LL * (p.t_valid - 1) - li;
+      acc = fmaf(lrelu(__ldg(gr + o), p.g_slope), lrelu(__ldg(xr + (li < 0 ? 0 : li)), p.x_slope), acc);
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if (lane == 0) dst[q] = acc;
+  }
+}
+
 __global__ void split_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int nsplit,
                                     int accumulate) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -321,10 +355,22 @@ static int wg_fill(const pwgb_conv1d_desc* d, WgK& p) {
   return 1;
 }
 
+static size_t ws_bytes_narrow(const pwgb_conv1d_desc* d) {
+  const int P = d->period < 1 ? 1 : d->period;
+  const long long blocks = (long long)d->batch * ceil_div(d->t_out * P, 2048);
+  return (size_t)blocks * d->cout * (d->cin / d->groups) * d->kernel * sizeof(float);
+}
+
 extern "C" size_t pwgb_conv1d_wgrad_workspace(const pwgb_conv1d_desc* d) {
   WgK p;
   if (!wg_fill(d, p)) return 0;
-  return (size_t)p.nsplit * d->cout * p.Cin_g * d->kernel * sizeof(float);
+  size_t a = (size_t)p.nsplit * d->cout * p.Cin_g * d->kernel * sizeof(float);
+  const long long n = (long long)d->cout * p.Cin_g * d->kernel;
+  if ((p.Cin_g <= 4 || p.Cout <= 4) && n <= 4096) {
+    const size_t b = ws_bytes_narrow(d);
+    if (b > a && b <= (1ull << 31)) a = b;
+  }
+  return a;
 }
 
 extern "C" int pwgb_conv1d_wgrad(const pwgb_conv1d_desc* d, const float* x, const float* gy, float g_slope, float* dw,
@@ -341,6 +387,18 @@ extern "C" int pwgb_conv1d_wgrad(const pwgb_conv1d_desc* d, const float* x, cons
   if (p.B == 0 || p.Lout == 0) {
     if (!accumulate) cudaMemsetAsync(dw, 0, n * sizeof(float), st);
     return PWGB_OK;
+  }
+  if ((p.Cin_g <= 4 || p.Cout <= 4) && n <= 4096 && p.pad_mode == PWGB_PAD_ZERO) {
+    const int chunks = ceil_div(p.Lout, 2048);
+    const long long blocks = (long long)p.B * chunks;
+    if (ws_bytes_narrow(d) <= ws_bytes && blocks <= 0x7fffffffLL) {
+      p.chunks_per_seq = chunks;
+      conv1d_wgrad_narrow_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, x, gy, (float*)ws);
+      int rc = check_launch("conv1d_wgrad_narrow_kernel");
+      if (rc) return rc;
+      split_reduce_kernel<<<grid_for(n), 256, 0, st>>>((const float*)ws, dw, n, (int)blocks, accumulate);
+      return check_launch("split_reduce_kernel");
+    }
   }
   const size_t smem = ((size_t)WG_CO * (WG_T + 1) + (size_t)WG_CI * p.XW + WG_T) * sizeof(float);
   PWGB_UNSUPPORTED_IF(smem > 200 * 1024, "conv1d_wgrad: tile does not fit shared memory");
