@@ -1101,7 +1101,7 @@ constexpr int WT_THREADS = 160;
 struct WtK {
   int B, Cin, Cout, T_in, T_out, K, D, padL;
   float x_slope, g_slope;
-  int chunks_per_seq, nsplit, RX, ntg;
+  int chunks_per_seq, nsplit, RX, ntg, tg;  // tg = taps per CTA (<= WT_TG), ntg = tap groups
   unsigned idesc;
 };
 
@@ -1118,8 +1118,8 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int co0 = blockIdx.x * 128;
   const int ci0 = (blockIdx.y / p.ntg) * WT_NC;
-  const int k0 = (blockIdx.y % p.ntg) * WT_TG;
-  const int ntap = min(WT_TG, p.K - k0);
+  const int k0 = (blockIdx.y % p.ntg) * p.tg;
+  const int ntap = min(p.tg, p.K - k0);
   const int split = blockIdx.z;
   const unsigned bar0 = smem_u32(bars);
   const unsigned FULL = bar0, EMPTY = bar0 + 8, ACC = bar0 + 16;
@@ -1255,10 +1255,15 @@ static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
   p.x_slope = d->pre_slope;
   p.g_slope = 1.f;
   p.chunks_per_seq = ceil_div(d->t_out, WT_TK);
-  p.ntg = ceil_div(d->kernel, WT_TG);
-  const int tg = d->kernel < WT_TG ? d->kernel : WT_TG;
-  p.RX = WT_TK + (tg - 1) * d->dilation;
-  if ((size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (WT_NC / 8) * p.RX * 16 + 64 > 110 * 1024) return 0;
+  // taps per CTA: as many as fit (the activation window grows with (taps - 1) * dilation)
+  int tg = d->kernel < WT_TG ? d->kernel : WT_TG;
+  for (;; tg = (tg + 1) / 2) {
+    p.RX = WT_TK + (tg - 1) * d->dilation;
+    if ((size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (WT_NC / 8) * p.RX * 16 + 64 <= 110 * 1024) break;
+    if (tg == 1) return 0;
+  }
+  p.tg = tg;
+  p.ntg = ceil_div(d->kernel, tg);
   const long long items = (long long)p.B * p.chunks_per_seq;
   const long long gxy = (long long)ceil_div(d->cout, 128) * (d->cin / WT_NC) * p.ntg;
   long long ns = (2 * 296 + gxy - 1) / gxy;

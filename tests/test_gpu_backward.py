@@ -38,6 +38,7 @@ def dev():
         (128, 128, 41, 1, 1, 4, 20, 200, 2, 1.0, "lrelu"), # grouped stride-1 conv on the tcgen05 path
         (64, 64, 3, 1, 2, 1, 2, 1000, 2, 0.2, None),       # tcgen05 wgrad with a half-filled 128-row M tile
         (32, 160, 1, 1, 1, 1, 0, 300, 2, 1.0, None),       # cout = 128 + 32
+        (64, 128, 3, 1, 512, 1, 512, 1500, 1, 1.0, None),  # WaveNet-size dilation: one tap per CTA in the tcgen05 wgrad
     ],
 )
 def test_conv1d_gradients(dev, cin, cout, k, stride, dil, groups, pad, T, B, pre, post):

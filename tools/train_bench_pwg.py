@@ -101,5 +101,12 @@ if rank == 0:
             v[1] += 1
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             print(f"  {k:20s} {v[0] / args.steps:9.2f} ms/step {v[1] // args.steps:5d} launches/step")
+        agg2 = {}
+        for name, fl, by, a, b, desc in ops.PROFILE:
+            v = agg2.setdefault(name + " " + desc, [0.0, 0])
+            v[0] += a.elapsed_time(b)
+            v[1] += 1
+        for k, v in sorted(agg2.items(), key=lambda kv: -kv[1][0])[:12]:
+            print(f"    {v[0] / args.steps:9.2f} ms/step x{v[1] // args.steps:3d}  {k}")
 if world > 1:
     dist.destroy_process_group()
