@@ -217,6 +217,74 @@ def measure_train_step(dev, rank, local_rank, world, dist, steps=3, warmup=2):
             "losses": {k: float(v) for k, v in st.items()}}
 
 
+def measure_pwg_train_step(dev, rank, local_rank, world, dist, steps=2, warmup=1, batch=64):
+    """BASELINE.json configs[2]: Parallel WaveGAN v1 G + D train step (30-layer residual stack,
+    MultiResolutionSTFTLoss + adversarial loss, RAdam), per-GPU batch 64 x 25600 samples, DDP when world > 1."""
+    from oracle import synth
+    from parallelwavegan_b200 import losses, models
+
+    g = models.ParallelWaveGANGenerator()
+    g.load_state_dict(synth.synth_state_dict([(k, tuple(v.shape)) for k, v in g.state_dict().items()], 31, 1.0))
+    d = models.ParallelWaveGANDiscriminator()
+    d.load_state_dict(synth.synth_state_dict([(k, tuple(v.shape)) for k, v in d.state_dict().items()], 64, 1.4))
+    g, d = g.to(dev).train(), d.to(dev).train()
+    if world > 1:  # the last layer's residual 1x1 has no influence on the output (parallel_wavegan.py:161-166)
+        g = torch.nn.parallel.DistributedDataParallel(g, device_ids=[local_rank], find_unused_parameters=True)
+        d = torch.nn.parallel.DistributedDataParallel(d, device_ids=[local_rank])
+    mr = losses.MultiResolutionSTFTLoss().to(dev)
+    gen_adv, dis_adv = losses.GeneratorAdversarialLoss(), losses.DiscriminatorAdversarialLoss()
+    opt_g = torch.optim.RAdam(g.parameters(), lr=1e-4, eps=1e-6)
+    opt_d = torch.optim.RAdam(d.parameters(), lr=5e-5, eps=1e-6)
+    T = 25600
+    gen = torch.Generator().manual_seed(2000 + rank)
+    c = torch.randn(batch, 80, T // 256 + 4, generator=gen).to(dev)
+    y = (torch.rand(batch, 1, T, generator=gen) - 0.5).to(dev)
+    dpar = list((d.module if hasattr(d, "module") else d).parameters())
+
+    def step():
+        z = torch.randn(batch, 1, T, device=dev)
+        y_ = g(z, c)
+        sc, mag = mr(y_.squeeze(1), y.squeeze(1))
+        for p in dpar:
+            p.requires_grad_(False)
+        gen_loss = sc + mag + 4.0 * gen_adv(d(y_))
+        opt_g.zero_grad(set_to_none=True)
+        gen_loss.backward()
+        torch.nn.utils.clip_grad_norm_(g.parameters(), 10.0)
+        opt_g.step()
+        for p in dpar:
+            p.requires_grad_(True)
+        with torch.no_grad():
+            y_ = g(z, c)
+        real, fake = dis_adv(d(y_.detach()), d(y))
+        dis_loss = real + fake
+        opt_d.zero_grad(set_to_none=True)
+        dis_loss.backward()
+        torch.nn.utils.clip_grad_norm_(d.parameters(), 1.0)
+        opt_d.step()
+        return gen_loss.detach(), dis_loss.detach()
+
+    for _ in range(warmup):
+        st = step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        st = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    return {"metric": "train_steps_per_sec", "value": 1e3 / ms, "ms_per_step": ms, "global_batch": batch * world,
+            "workload": f"ParallelWaveGAN v1 G + D train step, per-GPU batch {batch} x {T} samples (parallel_wavegan.v1.yaml losses, RAdam)",
+            "parallelism": f"DDP x{world} (NCCL gradient all-reduce)" if world > 1 else "single GPU",
+            "losses": {"generator_loss": float(st[0]), "discriminator_loss": float(st[1])}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -309,12 +377,17 @@ def main():
         prof = ops.PROFILE
         ops.PROFILE = None
 
-    train = None
+    train = train_pwg = None
     if not args.no_train:
         try:
             train = measure_train_step(dev, rank, local_rank, world, dist)
         except Exception as e:  # the headline line must survive a failure of the secondary measurement
             train = {"error": repr(e)[:300]}
+        try:
+            train_pwg = measure_pwg_train_step(dev, rank, local_rank, world, dist)
+        except Exception as e:
+            train_pwg = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
 
     from parallelwavegan_b200 import sharding
 
@@ -377,6 +450,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "train": train,
+            "train_pwg": train_pwg,
             "kernel_classes": {k: {"ms_per_step": v[2] / 3, "launches_per_step": v[3] / 3, "tflops": v[0] / (v[2] * 1e-3) / 1e12,
                                    "alg_GBps": v[1] / (v[2] * 1e-3) / 1e9} for k, v in agg.items()},
         }
