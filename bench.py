@@ -383,10 +383,11 @@ def main():
             train = measure_train_step(dev, rank, local_rank, world, dist)
         except Exception as e:  # the headline line must survive a failure of the secondary measurement
             train = {"error": repr(e)[:300]}
-        try:
-            train_pwg = measure_pwg_train_step(dev, rank, local_rank, world, dist)
-        except Exception as e:
-            train_pwg = {"error": repr(e)[:300]}
+        if world == 1:  # the C3 step is reported single-GPU only (DDP run of it: tools/train_bench_pwg.py)
+            try:
+                train_pwg = measure_pwg_train_step(dev, rank, local_rank, world, dist)
+            except Exception as e:
+                train_pwg = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
 
     from parallelwavegan_b200 import sharding
@@ -454,7 +455,7 @@ def main():
             "kernel_classes": {k: {"ms_per_step": v[2] / 3, "launches_per_step": v[3] / 3, "tflops": v[0] / (v[2] * 1e-3) / 1e12,
                                    "alg_GBps": v[1] / (v[2] * 1e-3) / 1e9} for k, v in agg.items()},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
