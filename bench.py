@@ -316,6 +316,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     model, sd = synth_weights()
