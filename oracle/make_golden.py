@@ -286,6 +286,9 @@ def main():
     gen_melgan("mb_melgan_v2", mb, B=2, T=12, seed=21, gain=0.8, pqmf_subbands=4)
     mel_small = dict(in_channels=80, out_channels=1, kernel_size=7, channels=32, upsample_scales=[4, 4], stack_kernel_size=3, stacks=2, use_weight_norm=True, use_final_nonlinear_activation=False)
     gen_melgan("melgan_small", mel_small, B=2, T=20, seed=22, gain=1.2)
+    # causal variants (test/test_hifigan.py:198-226, test/test_melgan.py causal cases)
+    gen_hifigan("hifigan_causal", dict(small_hifi, use_causal_conv=True), B=2, T=16, seed=14, gain=1.15)
+    gen_melgan("melgan_causal", dict(mel_small, use_causal_conv=True, use_final_nonlinear_activation=True), B=2, T=20, seed=23, gain=1.2)
     # PWG v1 (egs/ljspeech/voc1/conf/parallel_wavegan.v1.yaml:28-46)
     pwg = dict(in_channels=1, out_channels=1, kernel_size=3, layers=30, stacks=3, residual_channels=64, gate_channels=128, skip_channels=64, aux_channels=80, aux_context_window=2, dropout=0.0, use_weight_norm=True, use_causal_conv=False, upsample_conditional_features=True, upsample_net="ConvInUpsampleNetwork", upsample_params={"upsample_scales": [4, 4, 4, 4]})
     gen_pwg("pwg_v1", pwg, B=1, frames=10, seed=31, gain=1.0)

@@ -123,9 +123,29 @@ HIFIGAN_V1 = dict(
 )
 
 
-def hifigan_resblock(w, prefix, x, kernel_size, dilations, use_additional_convs=True, slope=0.1):
+def causal_conv1d(x, weight, bias, dilation=1, mode="constant"):
+    """CausalConv1d.forward (layers/causal_conv.py:32-43): pad (k-1)*d on BOTH sides, conv, keep the first T."""
+    n = (weight.shape[-1] - 1) * dilation
+    xp = F.pad(x, (n, n), mode=mode) if n else x
+    return F.conv1d(xp, weight, bias, dilation=dilation)[:, :, : x.shape[2]]
+
+
+def causal_conv_transpose1d(x, weight, bias, stride):
+    """CausalConvTranspose1d.forward (layers/causal_conv.py:68-79): replicate-pad one frame on the
+    left, transposed conv without padding, drop ``stride`` samples on each side."""
+    xp = F.pad(x, (1, 0), mode="replicate")
+    return F.conv_transpose1d(xp, weight, bias, stride=stride)[:, :, stride:-stride]
+
+
+def hifigan_resblock(w, prefix, x, kernel_size, dilations, use_additional_convs=True, slope=0.1, causal=False):
     """HiFiGANResidualBlock.forward (layers/residual_block.py:243-258)."""
     for idx, d in enumerate(dilations):
+        if causal:  # residual_block.py:194-209, 227-241: Sequential(act, CausalConv1d)
+            xt = causal_conv1d(F.leaky_relu(x, slope), w[f"{prefix}.convs1.{idx}.1.conv.weight"], w.get(f"{prefix}.convs1.{idx}.1.conv.bias"), d)
+            if use_additional_convs:
+                xt = causal_conv1d(F.leaky_relu(xt, slope), w[f"{prefix}.convs2.{idx}.1.conv.weight"], w.get(f"{prefix}.convs2.{idx}.1.conv.bias"), 1)
+            x = xt + x
+            continue
         xt = F.conv1d(
             F.leaky_relu(x, slope),
             w[f"{prefix}.convs1.{idx}.1.weight"],
@@ -145,21 +165,29 @@ def hifigan_resblock(w, prefix, x, kernel_size, dilations, use_additional_convs=
 
 
 def hifigan_generator(w, c, cfg=HIFIGAN_V1):
-    """HiFiGANGenerator.forward (models/hifigan.py:173-192), non-causal."""
+    """HiFiGANGenerator.forward (models/hifigan.py:173-192); ``use_causal_conv`` selects the
+    CausalConv1d / CausalConvTranspose1d wiring (hifigan.py:80-91, 108-121, 143-158)."""
     ks = cfg["kernel_size"]
     slope = cfg.get("negative_slope", 0.1)
     nb = len(cfg["resblock_kernel_sizes"])
-    c = F.conv1d(c, w["input_conv.weight"], w.get("input_conv.bias"), padding=(ks - 1) // 2)
+    causal = bool(cfg.get("use_causal_conv", False))
+    if causal:
+        c = causal_conv1d(c, w["input_conv.conv.weight"], w.get("input_conv.conv.bias"))
+    else:
+        c = F.conv1d(c, w["input_conv.weight"], w.get("input_conv.bias"), padding=(ks - 1) // 2)
     for i, s in enumerate(cfg["upsample_scales"]):
-        # hifigan.py:94-107: LeakyReLU -> ConvTranspose1d(k=2s, stride s, pad s//2+s%2, out_pad s%2)
-        c = F.conv_transpose1d(
-            F.leaky_relu(c, slope),
-            w[f"upsamples.{i}.1.weight"],
-            w.get(f"upsamples.{i}.1.bias"),
-            stride=s,
-            padding=s // 2 + s % 2,
-            output_padding=s % 2,
-        )
+        if causal:
+            c = causal_conv_transpose1d(F.leaky_relu(c, slope), w[f"upsamples.{i}.1.deconv.weight"], w.get(f"upsamples.{i}.1.deconv.bias"), s)
+        else:
+            # hifigan.py:94-107: LeakyReLU -> ConvTranspose1d(k=2s, stride s, pad s//2+s%2, out_pad s%2)
+            c = F.conv_transpose1d(
+                F.leaky_relu(c, slope),
+                w[f"upsamples.{i}.1.weight"],
+                w.get(f"upsamples.{i}.1.bias"),
+                stride=s,
+                padding=s // 2 + s % 2,
+                output_padding=s % 2,
+            )
         cs = 0.0
         for j in range(nb):
             cs = cs + hifigan_resblock(
@@ -170,9 +198,12 @@ def hifigan_generator(w, c, cfg=HIFIGAN_V1):
                 cfg["resblock_dilations"][j],
                 cfg.get("use_additional_convs", True),
                 slope,
+                causal,
             )
         c = cs / nb
     # hifigan.py:139-151: LeakyReLU() with the *default* slope 0.01, conv k, tanh
+    if causal:
+        return torch.tanh(causal_conv1d(F.leaky_relu(c, 0.01), w["output_conv.1.conv.weight"], w.get("output_conv.1.conv.bias")))
     c = F.conv1d(F.leaky_relu(c, 0.01), w["output_conv.1.weight"], w.get("output_conv.1.bias"), padding=(ks - 1) // 2)
     return torch.tanh(c)
 
@@ -199,21 +230,31 @@ def melgan_layer_index(cfg):
     (melgan.py:68-156): returns a list of ("conv"|"convt"|"stack"|"final", idx, meta)."""
     plan = []
     idx = 0
-    plan.append(("conv_in", idx + 1, None))  # [ReflectionPad, Conv1d]
-    idx += 2
+    causal = bool(cfg.get("use_causal_conv", False))
+    if causal:
+        plan.append(("conv_in", idx, None))  # [CausalConv1d]
+        idx += 1
+    else:
+        plan.append(("conv_in", idx + 1, None))  # [ReflectionPad, Conv1d]
+        idx += 2
     for i, s in enumerate(cfg["upsample_scales"]):
-        plan.append(("convt", idx + 1, (i, s)))  # [act, ConvTranspose1d]
+        plan.append(("convt", idx + 1, (i, s)))  # [act, ConvTranspose1d | CausalConvTranspose1d]
         idx += 2
         for j in range(cfg["stacks"]):
             plan.append(("stack", idx, (i, j)))
             idx += 1
-    plan.append(("conv_out", idx + 2, None))  # [act, pad, conv, (tanh)]
+    plan.append(("conv_out", idx + (1 if causal else 2), None))  # [act, (pad,) conv, (tanh)]
     return plan
 
 
-def melgan_residual_stack(w, prefix, c, kernel_size, dilation, slope):
-    """ResidualStack.forward (layers/residual_stack.py:75-85)."""
+def melgan_residual_stack(w, prefix, c, kernel_size, dilation, slope, causal=False):
+    """ResidualStack.forward (layers/residual_stack.py:75-85; causal wiring :56-70)."""
     h = F.leaky_relu(c, slope)
+    if causal:
+        h = causal_conv1d(h, w[f"{prefix}.stack.1.conv.weight"], w.get(f"{prefix}.stack.1.conv.bias"), dilation, mode="reflect")
+        h = F.leaky_relu(h, slope)
+        h = F.conv1d(h, w[f"{prefix}.stack.3.weight"], w.get(f"{prefix}.stack.3.bias"))
+        return h + F.conv1d(c, w[f"{prefix}.skip_layer.weight"], w.get(f"{prefix}.skip_layer.bias"))
     h = F.pad(h, ((kernel_size - 1) // 2 * dilation,) * 2, mode="reflect")
     h = F.conv1d(h, w[f"{prefix}.stack.2.weight"], w.get(f"{prefix}.stack.2.bias"), dilation=dilation)
     h = F.leaky_relu(h, slope)
@@ -226,9 +267,18 @@ def melgan_generator(w, c, cfg=MB_MELGAN_V2):
     ks = cfg["kernel_size"]
     slope = cfg.get("negative_slope", 0.2)
     sk = cfg.get("stack_kernel_size", 3)
+    causal = bool(cfg.get("use_causal_conv", False))
     for kind, idx, meta in melgan_layer_index(cfg):
         p = f"melgan.{idx}"
-        if kind == "conv_in":
+        if causal and kind == "conv_in":
+            c = causal_conv1d(c, w[p + ".conv.weight"], w.get(p + ".conv.bias"), mode="reflect")
+        elif causal and kind == "convt":
+            c = causal_conv_transpose1d(F.leaky_relu(c, slope), w[p + ".deconv.weight"], w.get(p + ".deconv.bias"), meta[1])
+        elif causal and kind == "conv_out":
+            c = causal_conv1d(F.leaky_relu(c, slope), w[p + ".conv.weight"], w.get(p + ".conv.bias"), mode="reflect")
+            if cfg.get("use_final_nonlinear_activation", True):
+                c = torch.tanh(c)
+        elif kind == "conv_in":
             c = F.conv1d(F.pad(c, ((ks - 1) // 2,) * 2, mode="reflect"), w[p + ".weight"], w.get(p + ".bias"))
         elif kind == "convt":
             _, s = meta
@@ -242,7 +292,7 @@ def melgan_generator(w, c, cfg=MB_MELGAN_V2):
             )
         elif kind == "stack":
             _, j = meta
-            c = melgan_residual_stack(w, p, c, sk, sk**j, slope)
+            c = melgan_residual_stack(w, p, c, sk, sk**j, slope, causal)
         else:
             c = F.leaky_relu(c, slope)
             c = F.conv1d(F.pad(c, ((ks - 1) // 2,) * 2, mode="reflect"), w[p + ".weight"], w.get(p + ".bias"))

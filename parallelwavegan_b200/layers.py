@@ -66,6 +66,46 @@ class Conv1d1x1(Conv1d):
         super().__init__(in_channels, out_channels, kernel_size=1, padding=0, dilation=1, bias=bias)
 
 
+class CausalConv1d(torch.nn.Module):
+    """layers/causal_conv.py:12-43.  Container with the reference's ``pad`` / ``conv`` children;
+    the forward is ONE conv launch with left-only padding ``(k - 1) * d`` (the reference pads both
+    sides and crops the tail, which never reads the right padding)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, dilation=1, bias=True,
+                 pad="ConstantPad1d", pad_params={"value": 0.0}):
+        super().__init__()
+        self.pad = getattr(torch.nn, pad)((kernel_size - 1) * dilation, **pad_params)
+        self.conv = torch.nn.Conv1d(in_channels, out_channels, kernel_size, dilation=dilation, bias=bias)
+        self.pad_mode = pad_mode_of(pad, pad_params)
+        self.left = (kernel_size - 1) * dilation
+        self.dilation = dilation
+
+    def forward(self, x, **fuse):
+        return ops.conv1d(x, effective_weight(self.conv), self.conv.bias, dilation=self.dilation,
+                          padding=(self.left, 0), pad_mode=self.pad_mode, **fuse)
+
+
+class CausalConvTranspose1d(torch.nn.Module):
+    """layers/causal_conv.py:46-79: ``deconv(pad_left_1(x))[:, :, stride:-stride]``.  The crop of
+    ``stride`` samples per side is the transposed conv's own ``padding=stride``, so the forward is the
+    one-frame left pad (a copy) plus ONE poly-phase launch."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, bias=True,
+                 pad="ReplicationPad1d", pad_params={}):
+        super().__init__()
+        if pad not in ("ReplicationPad1d", "ConstantPad1d", "ReflectionPad1d"):
+            raise PwgbError(f"CausalConvTranspose1d: pad={pad!r} has no sm_100a kernel")
+        self.pad = getattr(torch.nn, pad)((1, 0), **pad_params)
+        self.deconv = torch.nn.ConvTranspose1d(in_channels, out_channels, kernel_size, stride, bias=bias)
+        self.stride = stride
+
+    def forward(self, x, pre_slope=1.0):
+        # the pending activation commutes with every supported pad (lrelu(0) == 0), so it stays fused
+        x = self.pad(x)  # (B, C, T + 1): data movement only
+        return ops.conv_transpose1d(x.contiguous(), effective_weight(self.deconv), self.deconv.bias,
+                                    stride=self.stride, padding=self.stride, pre_slope=pre_slope)
+
+
 class HiFiGANResidualBlock(torch.nn.Module):
     """layers/residual_block.py:143-258: 3 x [LReLU -> conv(k, d) -> LReLU -> conv(k, 1)] + x."""
 
@@ -81,9 +121,8 @@ class HiFiGANResidualBlock(torch.nn.Module):
         use_causal_conv=False,
     ):
         super().__init__()
-        if use_causal_conv:
-            raise PwgbError("use_causal_conv=True has no sm_100a kernel yet")
         assert kernel_size % 2 == 1, "Kernel size must be odd number."
+        self.use_causal_conv = use_causal_conv
         self.kernel_size = kernel_size
         self.dilations = tuple(dilations)
         self.use_additional_convs = use_additional_convs
@@ -93,19 +132,17 @@ class HiFiGANResidualBlock(torch.nn.Module):
         if use_additional_convs:
             self.convs2 = torch.nn.ModuleList()
         for d in dilations:
-            self.convs1 += [
-                torch.nn.Sequential(
-                    act(**nonlinear_activation_params),
-                    torch.nn.Conv1d(channels, channels, kernel_size, 1, dilation=d, bias=bias, padding=(kernel_size - 1) // 2 * d),
-                )
-            ]
+            if use_causal_conv:
+                conv1 = CausalConv1d(channels, channels, kernel_size, dilation=d, bias=bias)
+            else:
+                conv1 = torch.nn.Conv1d(channels, channels, kernel_size, 1, dilation=d, bias=bias, padding=(kernel_size - 1) // 2 * d)
+            self.convs1 += [torch.nn.Sequential(act(**nonlinear_activation_params), conv1)]
             if use_additional_convs:
-                self.convs2 += [
-                    torch.nn.Sequential(
-                        act(**nonlinear_activation_params),
-                        torch.nn.Conv1d(channels, channels, kernel_size, dilation=1, bias=bias, padding=(kernel_size - 1) // 2),
-                    )
-                ]
+                if use_causal_conv:
+                    conv2 = CausalConv1d(channels, channels, kernel_size, dilation=1, bias=bias)
+                else:
+                    conv2 = torch.nn.Conv1d(channels, channels, kernel_size, dilation=1, bias=bias, padding=(kernel_size - 1) // 2)
+                self.convs2 += [torch.nn.Sequential(act(**nonlinear_activation_params), conv2)]
 
     def forward(self, x, out=None, accumulate=False, out_scale=1.0):
         """Returns block(x); optionally ``out (+)= out_scale * block(x)`` fused into the last conv
@@ -116,7 +153,13 @@ class HiFiGANResidualBlock(torch.nn.Module):
             last = idx == n - 1
             c1 = self.convs1[idx][1]
             tail = dict(out=out, accumulate=accumulate, out_scale=out_scale) if last else {}
-            if self.use_additional_convs:
+            if self.use_causal_conv:
+                if self.use_additional_convs:
+                    xt = c1(x, pre_slope=self.slope)
+                    x = self.convs2[idx][1](xt, pre_slope=self.slope, residual=x, **tail)
+                else:
+                    x = c1(x, pre_slope=self.slope, residual=x, **tail)
+            elif self.use_additional_convs:
                 xt = ops.conv1d(x, effective_weight(c1), c1.bias, dilation=d, padding=(k - 1) // 2 * d, pre_slope=self.slope)
                 c2 = self.convs2[idx][1]
                 x = ops.conv1d(xt, effective_weight(c2), c2.bias, padding=(k - 1) // 2, pre_slope=self.slope, residual=x, **tail)
@@ -141,27 +184,40 @@ class ResidualStack(torch.nn.Module):
         use_causal_conv=False,
     ):
         super().__init__()
-        if use_causal_conv:
-            raise PwgbError("use_causal_conv=True has no sm_100a kernel yet")
-        assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
+        self.use_causal_conv = use_causal_conv
+        if not use_causal_conv:
+            assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
         self.pad_mode = pad_mode_of(pad, pad_params)
         self.kernel_size = kernel_size
         self.dilation = dilation
         self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
         act = getattr(torch.nn, nonlinear_activation)
-        self.stack = torch.nn.Sequential(
-            act(**nonlinear_activation_params),
-            getattr(torch.nn, pad)((kernel_size - 1) // 2 * dilation, **pad_params),
-            torch.nn.Conv1d(channels, channels, kernel_size, dilation=dilation, bias=bias),
-            act(**nonlinear_activation_params),
-            torch.nn.Conv1d(channels, channels, 1, bias=bias),
-        )
+        if not use_causal_conv:
+            self.stack = torch.nn.Sequential(
+                act(**nonlinear_activation_params),
+                getattr(torch.nn, pad)((kernel_size - 1) // 2 * dilation, **pad_params),
+                torch.nn.Conv1d(channels, channels, kernel_size, dilation=dilation, bias=bias),
+                act(**nonlinear_activation_params),
+                torch.nn.Conv1d(channels, channels, 1, bias=bias),
+            )
+        else:
+            self.stack = torch.nn.Sequential(
+                act(**nonlinear_activation_params),
+                CausalConv1d(channels, channels, kernel_size, dilation=dilation, bias=bias, pad=pad, pad_params=pad_params),
+                act(**nonlinear_activation_params),
+                torch.nn.Conv1d(channels, channels, 1, bias=bias),
+            )
         self.skip_layer = torch.nn.Conv1d(channels, channels, 1, bias=bias)
 
     def forward(self, c):
         k, d = self.kernel_size, self.dilation
-        c1, c2, sk = self.stack[2], self.stack[4], self.skip_layer
-        h = ops.conv1d(c, effective_weight(c1), c1.bias, dilation=d, padding=(k - 1) // 2 * d, pad_mode=self.pad_mode, pre_slope=self.slope)
+        sk = self.skip_layer
+        if self.use_causal_conv:
+            c2 = self.stack[3]
+            h = self.stack[1](c, pre_slope=self.slope)
+        else:
+            c1, c2 = self.stack[2], self.stack[4]
+            h = ops.conv1d(c, effective_weight(c1), c1.bias, dilation=d, padding=(k - 1) // 2 * d, pad_mode=self.pad_mode, pre_slope=self.slope)
         s = ops.conv1d(c, effective_weight(sk), sk.bias)
         return ops.conv1d(h, effective_weight(c2), c2.bias, pre_slope=self.slope, residual=s)
 

@@ -12,7 +12,7 @@ import torch
 from . import ops
 from .capi import PwgbError
 from .layers import HiFiGANResidualBlock as ResidualBlock
-from .layers import ResidualStack, activation_slope, effective_weight, pad_mode_of
+from .layers import CausalConv1d, CausalConvTranspose1d, ResidualStack, activation_slope, effective_weight, pad_mode_of
 
 
 def _read_stats(stats):
@@ -74,8 +74,6 @@ class HiFiGANGenerator(_GeneratorBase):
         use_weight_norm=True,
     ):
         super().__init__()
-        if use_causal_conv:
-            raise PwgbError("HiFiGANGenerator(use_causal_conv=True) has no sm_100a kernel yet")
         assert kernel_size % 2 == 1, "Kernel size must be odd number."
         assert len(upsample_scales) == len(upsample_kernel_sizes)
         assert len(resblock_dilations) == len(resblock_kernel_sizes)
@@ -86,21 +84,23 @@ class HiFiGANGenerator(_GeneratorBase):
         self.upsample_scales = tuple(upsample_scales)
         self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
         act = getattr(torch.nn, nonlinear_activation)
-        self.input_conv = torch.nn.Conv1d(in_channels, channels, kernel_size, bias=bias, padding=(kernel_size - 1) // 2)
+        if use_causal_conv:
+            self.input_conv = CausalConv1d(in_channels, channels, kernel_size, bias=bias)
+        else:
+            self.input_conv = torch.nn.Conv1d(in_channels, channels, kernel_size, bias=bias, padding=(kernel_size - 1) // 2)
         self.upsamples = torch.nn.ModuleList()
         self.blocks = torch.nn.ModuleList()
         for i in range(len(upsample_kernel_sizes)):
             assert upsample_kernel_sizes[i] == 2 * upsample_scales[i]
             s = upsample_scales[i]
-            self.upsamples += [
-                torch.nn.Sequential(
-                    act(**nonlinear_activation_params),
-                    torch.nn.ConvTranspose1d(
-                        channels // (2**i), channels // (2 ** (i + 1)), upsample_kernel_sizes[i], s,
-                        padding=s // 2 + s % 2, output_padding=s % 2, bias=bias,
-                    ),
+            if use_causal_conv:
+                up = CausalConvTranspose1d(channels // (2**i), channels // (2 ** (i + 1)), upsample_kernel_sizes[i], s, bias=bias)
+            else:
+                up = torch.nn.ConvTranspose1d(
+                    channels // (2**i), channels // (2 ** (i + 1)), upsample_kernel_sizes[i], s,
+                    padding=s // 2 + s % 2, output_padding=s % 2, bias=bias,
                 )
-            ]
+            self.upsamples += [torch.nn.Sequential(act(**nonlinear_activation_params), up)]
             for j in range(len(resblock_kernel_sizes)):
                 self.blocks += [
                     ResidualBlock(
@@ -116,7 +116,9 @@ class HiFiGANGenerator(_GeneratorBase):
                 ]
         self.output_conv = torch.nn.Sequential(
             torch.nn.LeakyReLU(),  # default slope 0.01 (hifigan.py:139-142)
-            torch.nn.Conv1d(channels // (2 ** (i + 1)), out_channels, kernel_size, bias=bias, padding=(kernel_size - 1) // 2),
+            CausalConv1d(channels // (2 ** (i + 1)), out_channels, kernel_size, bias=bias)
+            if use_causal_conv
+            else torch.nn.Conv1d(channels // (2 ** (i + 1)), out_channels, kernel_size, bias=bias, padding=(kernel_size - 1) // 2),
             torch.nn.Tanh(),
         )
         if use_weight_norm:
@@ -127,13 +129,17 @@ class HiFiGANGenerator(_GeneratorBase):
         """(B, in_channels, T) -> (B, out_channels, T * prod(upsample_scales))  (hifigan.py:173-192)."""
         pad = (self.kernel_size - 1) // 2
         ic = self.input_conv
-        c = ops.conv1d(c, effective_weight(ic), ic.bias, padding=pad)
+        causal = self.use_causal_conv
+        c = ic(c) if causal else ops.conv1d(c, effective_weight(ic), ic.bias, padding=pad)
         nb = self.num_blocks
         for i in range(self.num_upsamples):
             up = self.upsamples[i][1]
             s = self.upsample_scales[i]
-            c = ops.conv_transpose1d(c, effective_weight(up), up.bias, stride=s, padding=s // 2 + s % 2,
-                                     output_padding=s % 2, pre_slope=self.slope)
+            if causal:
+                c = up(c, pre_slope=self.slope)
+            else:
+                c = ops.conv_transpose1d(c, effective_weight(up), up.bias, stride=s, padding=s // 2 + s % 2,
+                                         output_padding=s % 2, pre_slope=self.slope)
             if torch.is_grad_enabled() and (c.requires_grad or next(self.parameters()).requires_grad):
                 from .autograd import ScaledSumFn  # training: differentiable MRF average
 
@@ -144,6 +150,8 @@ class HiFiGANGenerator(_GeneratorBase):
                     self.blocks[i * nb + j](c, out=cs, accumulate=j > 0, out_scale=1.0 / nb)
                 c = cs
         oc = self.output_conv[1]
+        if causal:
+            return oc(c, pre_slope=0.01, post_act="tanh")
         return ops.conv1d(c, effective_weight(oc), oc.bias, padding=pad, pre_slope=0.01, post_act="tanh")
 
     def reset_parameters(self):
@@ -188,23 +196,28 @@ class MelGANGenerator(_GeneratorBase):
         use_causal_conv=False,
     ):
         super().__init__()
-        if use_causal_conv:
-            raise PwgbError("MelGANGenerator(use_causal_conv=True) has no sm_100a kernel yet")
         assert channels >= np.prod(upsample_scales)
         assert channels % (2 ** len(upsample_scales)) == 0
-        assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
+        if not use_causal_conv:
+            assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
         self.kernel_size = kernel_size
         self.slope = activation_slope(nonlinear_activation, nonlinear_activation_params)
         self.pad_mode = pad_mode_of(pad, pad_params)
         self.use_final_nonlinear_activation = use_final_nonlinear_activation
         act = getattr(torch.nn, nonlinear_activation)
-        layers = [getattr(torch.nn, pad)((kernel_size - 1) // 2, **pad_params), torch.nn.Conv1d(in_channels, channels, kernel_size, bias=bias)]
+        if use_causal_conv:
+            layers = [CausalConv1d(in_channels, channels, kernel_size, bias=bias, pad=pad, pad_params=pad_params)]
+        else:
+            layers = [getattr(torch.nn, pad)((kernel_size - 1) // 2, **pad_params), torch.nn.Conv1d(in_channels, channels, kernel_size, bias=bias)]
         for i, s in enumerate(upsample_scales):
             layers += [act(**nonlinear_activation_params)]
-            layers += [
-                torch.nn.ConvTranspose1d(channels // (2**i), channels // (2 ** (i + 1)), s * 2, stride=s,
-                                         padding=s // 2 + s % 2, output_padding=s % 2, bias=bias)
-            ]
+            if use_causal_conv:
+                layers += [CausalConvTranspose1d(channels // (2**i), channels // (2 ** (i + 1)), s * 2, stride=s, bias=bias)]
+            else:
+                layers += [
+                    torch.nn.ConvTranspose1d(channels // (2**i), channels // (2 ** (i + 1)), s * 2, stride=s,
+                                             padding=s // 2 + s % 2, output_padding=s % 2, bias=bias)
+                ]
             for j in range(stacks):
                 layers += [
                     ResidualStack(
@@ -220,7 +233,10 @@ class MelGANGenerator(_GeneratorBase):
                     )
                 ]
         layers += [act(**nonlinear_activation_params)]
-        layers += [getattr(torch.nn, pad)((kernel_size - 1) // 2, **pad_params), torch.nn.Conv1d(channels // (2 ** (i + 1)), out_channels, kernel_size, bias=bias)]
+        if use_causal_conv:
+            layers += [CausalConv1d(channels // (2 ** (i + 1)), out_channels, kernel_size, bias=bias, pad=pad, pad_params=pad_params)]
+        else:
+            layers += [getattr(torch.nn, pad)((kernel_size - 1) // 2, **pad_params), torch.nn.Conv1d(channels // (2 ** (i + 1)), out_channels, kernel_size, bias=bias)]
         if use_final_nonlinear_activation:
             layers += [torch.nn.Tanh()]
         self.melgan = torch.nn.Sequential(*layers)
@@ -238,7 +254,14 @@ class MelGANGenerator(_GeneratorBase):
         idx = 0
         while idx < n:
             m = mods[idx]
-            if isinstance(m, torch.nn.ConvTranspose1d):
+            if isinstance(m, CausalConvTranspose1d):
+                c = m(c, pre_slope=pre)
+                pre = 1.0
+            elif isinstance(m, CausalConv1d):
+                final = idx >= n - 2
+                c = m(c, pre_slope=pre, post_act="tanh" if (final and self.use_final_nonlinear_activation) else None)
+                pre = 1.0
+            elif isinstance(m, torch.nn.ConvTranspose1d):
                 s = m.stride[0]
                 c = ops.conv_transpose1d(c, effective_weight(m), m.bias, stride=s, padding=m.padding[0],
                                          output_padding=m.output_padding[0], pre_slope=pre)

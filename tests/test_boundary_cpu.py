@@ -47,7 +47,7 @@ def _mirror(kind, kwargs):
     return cls(**json.loads(json.dumps(kwargs)))
 
 
-@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd", "mb_melgan_v2", "melgan_small", "pwg_v1", "pwg_small"])
+@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd", "hifigan_causal", "mb_melgan_v2", "melgan_small", "melgan_causal", "pwg_v1", "pwg_small"])
 def test_state_dict_layout_matches_reference(name, built_lib):
     meta, _ = load_golden(name)
     m = _mirror(meta["kind"], meta["kwargs"])

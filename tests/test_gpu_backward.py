@@ -208,6 +208,38 @@ def test_hifigan_train_step_gradients(dev):
     print("worst generator grad rel-L2", worst)
 
 
+def test_causal_hifigan_gradients(dev):
+    """Causal HiFi-GAN generator (layers/causal_conv.py wiring) + mel loss: parameter and input
+    gradients vs torch autograd through the CPU oracle."""
+    from parallelwavegan_b200 import losses, models
+
+    kw = dict(in_channels=80, out_channels=1, channels=64, kernel_size=7, upsample_scales=[8, 4, 2],
+              upsample_kernel_sizes=[16, 8, 4], resblock_kernel_sizes=[3, 7], resblock_dilations=[[1, 3, 5], [1, 3]],
+              use_causal_conv=True)
+    g = models.HiFiGANGenerator(**kw)
+    sd = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in g.state_dict().items()], 17, 1.15)
+    g.load_state_dict(sd)
+    c = synth.randn((2, 80, 32), 23)
+    y = synth.randn((2, 1, 32 * 64), 24, 0.3)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    c_ref = c.clone().requires_grad_(True)
+    y_ref = ref_ops.hifigan_generator(ref_ops.fold_weight_norm(leaf), c_ref, dict(kw, negative_slope=0.1))
+    melmat = torch.from_numpy(ref_ops.slaney_mel_filterbank(22050, 1024, 80, 0, 11025).T.copy())
+    ref_ops.mel_loss(y_ref, y, melmat, log_base=None).backward()
+
+    g = g.to(dev).train()
+    mel_fn = losses.MelSpectrogramLoss(fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80,
+                                       fmin=0, fmax=11025, log_base=None).to(dev)
+    c_o = c.to(dev).requires_grad_(True)
+    y_hat = g(c_o)
+    assert rel_l2(y_hat.detach().cpu(), y_ref.detach()) < GTOL
+    mel_fn(y_hat, y.to(dev)).backward()
+    assert rel_l2(c_o.grad.cpu(), c_ref.grad) < 5e-3
+    for k, p in g.named_parameters():
+        e = rel_l2(p.grad.cpu(), leaf[k].grad)
+        assert e < 5e-3, (k, e)
+
+
 def test_pwg_train_step_gradients(dev):
     """Parallel WaveGAN generator + MR-STFT + adversarial loss (train.py:200-295 logic, reduced depth):
     parameter gradients vs torch autograd through the CPU oracle."""

@@ -122,7 +122,7 @@ def _load_mirror(name, dev):
     return meta, g, m.eval().to(dev)
 
 
-@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd"])
+@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd", "hifigan_causal"])
 @pytest.mark.parametrize("weight_norm", [True, False])
 def test_hifigan_generator_vs_reference(dev, name, weight_norm):
     meta, g, m = _load_mirror(name, dev)
@@ -141,7 +141,7 @@ def test_hifigan_generator_vs_reference(dev, name, weight_norm):
     assert rel_l2(y.cpu(), ref) < REL_TOL
 
 
-@pytest.mark.parametrize("name", ["mb_melgan_v2", "melgan_small"])
+@pytest.mark.parametrize("name", ["mb_melgan_v2", "melgan_small", "melgan_causal"])
 def test_melgan_generator_vs_reference(dev, name):
     from parallelwavegan_b200.layers import PQMF
 
@@ -158,6 +158,23 @@ def test_melgan_generator_vs_reference(dev, name):
             y_inf = m.inference(c[0].t())
         assert rel_l2(yp.cpu(), g["y_pqmf"]) < REL_TOL
         assert rel_l2(y_inf.cpu(), g["y_inf"]) < REL_TOL
+
+
+@pytest.mark.parametrize("name", ["hifigan_causal", "melgan_causal"])
+def test_causal_generators_are_causal(dev, name):
+    """test/test_hifigan.py:198-226, test/test_melgan.py (causal): perturbing the second half of the
+    conditioning leaves the first half of the waveform bit-identical."""
+    meta, g, m = _load_mirror(name, dev)
+    B, C, T = 2, meta["c_shape"][1], 32
+    c = synth.randn((B, C, T), 77).to(dev)
+    c2 = c.clone()
+    c2[..., T // 2:] = synth.randn((B, C, T - T // 2), 78).to(dev)
+    with torch.no_grad():
+        y, y2 = m(c), m(c2)
+    hop = y.shape[-1] // T
+    assert y.shape[-1] == T * hop
+    assert torch.equal(y[..., : T // 2 * hop], y2[..., : T // 2 * hop])
+    assert not torch.equal(y[..., T // 2 * hop:], y2[..., T // 2 * hop:])
 
 
 @pytest.mark.parametrize("n", [2, 3, 4, 8])

@@ -9,7 +9,7 @@ from helpers import ORACLE_TOL, golden_effective_weights, load_golden, rel_l2
 from oracle import ref_ops, synth
 
 
-@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd"])
+@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd", "hifigan_causal"])
 def test_hifigan_generator(name):
     meta, g = load_golden(name)
     w = golden_effective_weights(meta)
@@ -22,7 +22,7 @@ def test_hifigan_generator(name):
     assert rel_l2(y[0].t(), g["y_inf"]) < ORACLE_TOL
 
 
-@pytest.mark.parametrize("name", ["mb_melgan_v2", "melgan_small"])
+@pytest.mark.parametrize("name", ["mb_melgan_v2", "melgan_small", "melgan_causal"])
 def test_melgan_generator(name):
     meta, g = load_golden(name)
     w = golden_effective_weights(meta)
