@@ -231,6 +231,14 @@ PWGB_API int pwgb_reduce_mean_backward(int mode, const float* x, const float* y,
 PWGB_API int pwgb_avg_pool1d_backward(const float* gy, float* gx, int rows, int t_in, int kernel, int stride, int padding,
                              int count_include_pad, void* stream);
 PWGB_API int pwgb_axpby(long long n, float a, const float* x, float b, float* y, void* stream);
+/* Explicit ReflectionPad1d / ReplicationPad1d (melgan.py:70-72, residual_stack.py:49) of rows x t -> rows x
+ * (pad_left + t + pad_right) and its adjoint (gather form, deterministic).  The forward convs fuse the
+ * padding into their loaders; the train step materialises it once per layer so the weight / data
+ * gradients run on the zero-padding kernels.  pad_mode: PWGB_PAD_REFLECT or PWGB_PAD_REPLICATE. */
+PWGB_API int pwgb_pad1d_forward(const float* x, float* xp, long long rows, long long t, int pad_left, int pad_right,
+                       int pad_mode, void* stream);
+PWGB_API int pwgb_pad1d_backward(const float* gxp, float* gx, long long rows, long long t, int pad_left, int pad_right,
+                        int pad_mode, void* stream);
 /* adjoints of pwgb_stft_amplitude_forward (dx must be zero-initialised by the caller; frames overlap
  * so it is accumulated with atomics) and of the loss branch of pwgb_mel_project_forward. */
 PWGB_API int pwgb_stft_amplitude_backward(const pwgb_stft_desc* d, const float* x, const float* window, const float* amp,

@@ -19,12 +19,13 @@ class Conv1dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, residual, stride, padding, dilation, groups, pad_mode, pre_slope, post_act, post_slope,
                 out_scale, period):
-        if pad_mode != "zero":
-            raise PwgbError("training through reflect/replicate padded convs has no backward kernel yet")
+        if pad_mode != "zero" and (stride != 1 or period != 1):
+            raise PwgbError("training through strided / period convs with reflect or replicate padding is not supported")
         y = ops.conv1d_raw(x, w, bias, stride=stride, padding=padding, dilation=dilation, groups=groups, pad_mode=pad_mode,
                            pre_slope=pre_slope, post_act=post_act, post_slope=post_slope, residual=residual,
                            out_scale=out_scale, period=period)
         ctx.cfg = (stride, _pair(padding), dilation, groups, pre_slope, post_act, post_slope, out_scale, period)
+        ctx.pad_mode = pad_mode
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
         ctx.w3 = (w.shape[0], w.shape[1], w.shape[2])
@@ -63,6 +64,24 @@ class Conv1dFn(torch.autograd.Function):
         w3 = w.reshape(cout, cin_g, K)
         gb = ops.bias_grad(gz, cout) if (ctx.has_bias and need_b) else None
         gw = None
+        if ctx.pad_mode != "zero" and (pl or pr):
+            # reflect / replicate padding: the gradients are those of a *valid* conv over the explicitly
+            # padded signal, folded back through the adjoint of the padding (stride 1, period 1 only)
+            T = x.shape[2]
+            if need_w:
+                xp = ops.pad1d(x, pl, pr, ctx.pad_mode)
+                gw = ops.conv1d_wgrad(xp, gz, ctx.w3, stride=1, padding=0, dilation=dil, groups=groups, x_slope=pre_slope).reshape(ctx.w_shape)
+                del xp
+            gx = None
+            if need_x:
+                cout_g = cout // groups
+                wt = w3.detach().reshape(groups, cout_g, cin_g, K).transpose(1, 2).flip(-1).reshape(groups * cin_g, cout_g, K).contiguous()
+                full = dil * (K - 1)
+                gxp = ops.conv1d_raw(gz, wt, None, padding=(full, full), dilation=dil, groups=groups)
+                gx = ops.pad1d_backward(gxp, T, pl, pr, ctx.pad_mode)
+                if pre_slope != 1.0:
+                    ops.act_backward("lrelu", gx, x, slope=pre_slope, out=gx)
+            return gx, gw, gb, g_res, None, None, None, None, None, None, None, None, None, None
         if need_w:
             gw = ops.conv1d_wgrad(x, gz, ctx.w3, stride=stride, padding=pl, dilation=dil, groups=groups, x_slope=pre_slope, period=P)
             gw = gw.reshape(ctx.w_shape)

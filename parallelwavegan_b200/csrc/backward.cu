@@ -237,6 +237,46 @@ __global__ void axpby_kernel(long long n, float a, const float* __restrict__ x, 
     y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
 }
 
+// Explicit reflect / replicate padding (torch.nn.ReflectionPad1d / ReplicationPad1d in front of the MelGAN
+// convs, melgan.py:70-72, residual_stack.py:49) and its adjoint.  mode: PWGB_PAD_*.
+__device__ __forceinline__ long long pad_src(long long e, long long T, int pl, int mode) {
+  long long t = e - pl;
+  if (mode == PWGB_PAD_REFLECT) {
+    if (t < 0) t = -t;
+    if (t >= T) t = 2 * (T - 1) - t;
+  } else {
+    t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+  }
+  return t;
+}
+__global__ void pad1d_forward_kernel(const float* __restrict__ x, float* __restrict__ xp, long long rows, long long T, int pl,
+                                     int pr, int mode) {
+  const long long Te = T + pl + pr, n = rows * Te;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Te, e = i % Te;
+    xp[i] = x[r * T + pad_src(e, T, pl, mode)];
+  }
+}
+// gx[r, t] = sum over extended positions e with pad_src(e) == t of gxp[r, e]   (gather form, deterministic)
+__global__ void pad1d_backward_kernel(const float* __restrict__ gxp, float* __restrict__ gx, long long rows, long long T, int pl,
+                                      int pr, int mode) {
+  const long long Te = T + pl + pr, n = rows * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / T, t = i % T;
+    const float* g = gxp + r * Te;
+    float acc = g[pl + t];
+    if (mode == PWGB_PAD_REFLECT) {
+      if (t >= 1 && t <= pl) acc += g[pl - t];                  // left extension e = pl - t
+      const long long m = T - 2 - t;                            // right extension e = pl + T + m
+      if (m >= 0 && m < pr) acc += g[pl + T + m];
+    } else {
+      if (t == 0) for (int e = 0; e < pl; ++e) acc += g[e];
+      if (t == T - 1) for (int m = 0; m < pr; ++m) acc += g[pl + T + m];
+    }
+    gx[i] = acc;
+  }
+}
+
 // WaveNet gate (layers/residual_block.py:128): z[b,h,t] = tanh(g[b,h,t]) * sigmoid(g[b,H+h,t])
 __global__ void gate_forward_kernel(const float* __restrict__ g, float* __restrict__ z, int B, int H, long long T) {
   const long long n = (long long)B * H * T;
@@ -455,6 +495,28 @@ extern "C" int pwgb_axpby(long long n, float a, const float* x, float b, float* 
   if (n == 0) return PWGB_OK;
   axpby_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
   return check_launch("axpby_kernel");
+}
+
+extern "C" int pwgb_pad1d_forward(const float* x, float* xp, long long rows, long long t, int pad_left, int pad_right,
+                                  int pad_mode, void* stream) {
+  PWGB_CHECK_ARG(x && xp && rows >= 0 && t > 0 && pad_left >= 0 && pad_right >= 0, "pad1d_forward: bad arguments");
+  PWGB_CHECK_ARG(pad_mode == PWGB_PAD_REFLECT || pad_mode == PWGB_PAD_REPLICATE, "pad1d_forward: pad_mode must be reflect or replicate");
+  PWGB_CHECK_ARG(pad_mode != PWGB_PAD_REFLECT || (pad_left < t && pad_right < t), "pad1d_forward: reflect padding must be < t");
+  const long long n = rows * (t + pad_left + pad_right);
+  if (n == 0) return PWGB_OK;
+  pad1d_forward_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, xp, rows, t, pad_left, pad_right, pad_mode);
+  return check_launch("pad1d_forward_kernel");
+}
+
+extern "C" int pwgb_pad1d_backward(const float* gxp, float* gx, long long rows, long long t, int pad_left, int pad_right,
+                                   int pad_mode, void* stream) {
+  PWGB_CHECK_ARG(gxp && gx && rows >= 0 && t > 0 && pad_left >= 0 && pad_right >= 0, "pad1d_backward: bad arguments");
+  PWGB_CHECK_ARG(pad_mode == PWGB_PAD_REFLECT || pad_mode == PWGB_PAD_REPLICATE, "pad1d_backward: pad_mode must be reflect or replicate");
+  PWGB_CHECK_ARG(pad_mode != PWGB_PAD_REFLECT || (pad_left < t && pad_right < t), "pad1d_backward: reflect padding must be < t");
+  const long long n = rows * t;
+  if (n == 0) return PWGB_OK;
+  pad1d_backward_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(gxp, gx, rows, t, pad_left, pad_right, pad_mode);
+  return check_launch("pad1d_backward_kernel");
 }
 
 extern "C" int pwgb_gate_forward(const float* g, float* z, int batch, int half_channels, long long t, void* stream) {

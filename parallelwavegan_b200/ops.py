@@ -443,6 +443,28 @@ def axpby(a, x, b, y):
     return y
 
 
+def pad1d(x, pad_left, pad_right, mode):
+    """Materialised ReflectionPad1d / ReplicationPad1d of (B, C, T) (train-step helper)."""
+    x = _dev(x, "x")
+    B, Cc, T = x.shape
+    xp = torch.empty(B, Cc, T + pad_left + pad_right, device=x.device, dtype=torch.float32)
+    rc = capi.lib().pwgb_pad1d_forward(_p(x), _p(xp), B * Cc, T, int(pad_left), int(pad_right), _PAD[mode], _stream())
+    capi.check(rc, "pwgb_pad1d_forward")
+    return xp
+
+
+def pad1d_backward(gxp, t, pad_left, pad_right, mode):
+    """Adjoint of pad1d: (B, C, pad_left + t + pad_right) -> (B, C, t)."""
+    gxp = _dev(gxp, "gxp")
+    B, Cc, Te = gxp.shape
+    if Te != t + pad_left + pad_right:
+        raise PwgbError("pad1d_backward: length mismatch")
+    gx = torch.empty(B, Cc, t, device=gxp.device, dtype=torch.float32)
+    rc = capi.lib().pwgb_pad1d_backward(_p(gxp), _p(gx), B * Cc, t, int(pad_left), int(pad_right), _PAD[mode], _stream())
+    capi.check(rc, "pwgb_pad1d_backward")
+    return gx
+
+
 def _needs_grad(*ts):
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
 

@@ -208,6 +208,83 @@ def test_hifigan_train_step_gradients(dev):
     print("worst generator grad rel-L2", worst)
 
 
+@pytest.mark.parametrize("mode", ["reflect", "replicate"])
+@pytest.mark.parametrize("cin,cout,k,dil,pad,T,pre", [(1, 16, 15, 1, (7, 7), 90, 1.0), (32, 32, 3, 9, (9, 9), 120, 0.2),
+                                                        (64, 128, 7, 1, (6, 0), 300, 0.2)])
+def test_conv1d_gradients_reflect_replicate(dev, mode, cin, cout, k, dil, pad, T, pre):
+    """ReflectionPad1d / ReplicationPad1d + conv (melgan.py:70-72, residual_stack.py:49, causal_conv.py:27)."""
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((2, cin, T), 1)
+    w = synth.randn((cout, cin, k), 2, 1.0 / (cin * k) ** 0.5)
+    b = synth.randn((cout,), 3, 0.1)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    z = F.conv1d(F.pad(F.leaky_relu(xr, pre) if pre != 1.0 else xr, pad, mode=mode), wr, br, dilation=dil)
+    gout = synth.randn(z.shape, 5)
+    (z * gout).sum().backward()
+    xd, wd, bd = (t.clone().to(dev).requires_grad_(True) for t in (x, w, b))
+    y = ops.conv1d(xd, wd, bd, padding=pad, dilation=dil, pad_mode=mode, pre_slope=pre)
+    assert rel_l2(y.detach().cpu(), z.detach()) < GTOL
+    (y * gout.to(dev)).sum().backward()
+    for name, a, r in (("dx", xd.grad, xr.grad), ("dw", wd.grad, wr.grad), ("db", bd.grad, br.grad)):
+        assert rel_l2(a.cpu(), r) < GTOL, name
+
+
+def test_mb_melgan_train_step_gradients(dev):
+    """Multi-band MelGAN generator -> PQMF synthesis -> mel loss + MelGAN multi-scale discriminator
+    (adversarial + feature matching): gradients vs torch autograd through the CPU oracle."""
+    from parallelwavegan_b200 import layers, losses, models
+
+    kw = dict(in_channels=80, out_channels=4, kernel_size=7, channels=64, upsample_scales=[4, 2], stack_kernel_size=3, stacks=2)
+    g = models.MelGANGenerator(**kw)
+    sd = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in g.state_dict().items()], 71, 1.0)
+    g.load_state_dict(sd)
+    dkw = dict(scales=2, downsample_scales=[4, 4], max_downsample_channels=64, channels=16)
+    d = models.MelGANMultiScaleDiscriminator(**dkw)
+    dsd = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in d.state_dict().items()], 72, 1.4)
+    d.load_state_dict(dsd)
+    c = synth.randn((2, 80, 64), 73)
+    y = synth.randn((2, 1, 64 * 32), 74, 0.3)
+
+    leaf_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    leaf_d = {k: v.clone().requires_grad_(True) for k, v in dsd.items()}
+    wg, wd = ref_ops.fold_weight_norm(leaf_g), ref_ops.fold_weight_norm(leaf_d)
+    _, syn = ref_ops.pqmf_filters(4)
+    y_mb = ref_ops.melgan_generator(wg, c, dict(kw, negative_slope=0.2))
+    y_ref = ref_ops.pqmf_synthesis(y_mb, syn)
+    melmat = torch.from_numpy(ref_ops.slaney_mel_filterbank(22050, 512, 40, 0, 11025).T.copy())
+    mel = ref_ops.mel_loss(y_ref, y, melmat, fft_size=512, hop_size=128, log_base=None)
+    d_ref = lambda x: ref_ops.melgan_msd(wd, x, scales=2, downsample_scales=(4, 4), channels=16, max_ch=64)
+    p_hat = d_ref(y_ref)
+    with torch.no_grad():
+        p_real = d_ref(y)
+    adv = ref_ops.generator_adv_loss(p_hat)
+    fm = ref_ops.feature_match_loss(p_hat, p_real)
+    (10.0 * mel + adv + 2.0 * fm).backward()
+
+    g, d = g.to(dev).train(), d.to(dev).train()
+    pq = layers.PQMF(4).to(dev)
+    mel_fn = losses.MelSpectrogramLoss(fs=22050, fft_size=512, hop_size=128, win_length=None, window="hann", num_mels=40,
+                                       fmin=0, fmax=11025, log_base=None).to(dev)
+    y_hat = pq.synthesis(g(c.to(dev)))
+    assert rel_l2(y_hat.detach().cpu(), y_ref.detach()) < GTOL
+    mel_o = mel_fn(y_hat, y.to(dev))
+    ph = d(y_hat)
+    with torch.no_grad():
+        pr = d(y.to(dev))
+    adv_o = losses.GeneratorAdversarialLoss()(ph)
+    fm_o = losses.FeatureMatchLoss()(ph, pr)
+    for name, a, r in (("mel", mel_o, mel), ("adv", adv_o, adv), ("fm", fm_o, fm)):
+        assert abs(float(a) - float(r)) <= GTOL * abs(float(r)), name
+    (10.0 * mel_o + adv_o + 2.0 * fm_o).backward()
+    for k, p in g.named_parameters():
+        e = rel_l2(p.grad.cpu(), leaf_g[k].grad)
+        assert e < 5e-3, (k, e)
+    for k, p in d.named_parameters():
+        e = rel_l2(p.grad.cpu(), leaf_d[k].grad)
+        assert e < 5e-3, (k, e)
+
+
 def test_causal_hifigan_gradients(dev):
     """Causal HiFi-GAN generator (layers/causal_conv.py wiring) + mel loss: parameter and input
     gradients vs torch autograd through the CPU oracle."""
