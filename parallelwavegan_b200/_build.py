@@ -29,7 +29,7 @@ def _digest():
     h = hashlib.sha256()
     for f in sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + [
         os.path.join(ROOT, "include", "pwgb.h"), os.path.abspath(__file__)]:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())  # path-independent: the stamp built here stays valid on the GPU box
         with open(f, "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()

@@ -28,8 +28,10 @@ constexpr int KC = 32;  // input channels per activation chunk / weight stage (2
                         // measured slower (22.3 vs 18.5 ms / step): the per-stage barrier round trip dominates
 constexpr int NPROD = 256;  // producer threads (warps 0-7); 4 warps measured slower (conversion-bound)
 constexpr int NEPI = 256;   // epilogue threads (warps 8-15)
-constexpr int W_EPI0 = NPROD / 32, W_TMA = (NPROD + NEPI) / 32, W_MMA = W_TMA + 1;
-constexpr int TC_THREADS = NPROD + NEPI + 64;
+// warp roles after the producers / epilogue: weight TMA, MMA issuer(s), activation TMA
+constexpr int W_EPI0 = NPROD / 32, W_TMA = (NPROD + NEPI) / 32, W_MMA = W_TMA + 1, W_MMA1 = W_TMA + 2, W_LDA = W_TMA + 3;
+constexpr int TC_THREADS = NPROD + NEPI + 128;
+constexpr int NS_MAX = 4;  // raw activation stages
 constexpr unsigned SPIN_LIMIT = 1u << 22;
 
 struct TcK {
@@ -41,7 +43,10 @@ struct TcK {
   int accumulate;
   int shuffle, shuffle_pad, shuffle_tout;
   int MT, R, nchunks, tiles_per_seq, nb, na, nacc, total_tiles;
-  int ns;                // raw fp32 cp.async staging buffers for the activation chunks (0 = direct register path)
+  int ns;                // raw fp32 staging buffers for the activation chunks (0 = direct register path)
+  int R4, raw_bytes;     // raw stage: KC rows of R4 floats (R4 = R + alignment slack, multiple of 4)
+  int tma_act;           // 1: raw stages are filled by cp.async.bulk row copies (warp W_LDA), 0: by cp.async (producers)
+  int nmma;              // MMA issuer warps: 2 = one per 128-row m-tile (MT == 2)
   long long xbs, ybs, rbs;
   unsigned idesc;
   int tmem_cols;
@@ -206,6 +211,7 @@ __device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -394,12 +400,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                      const uint4* __restrict__ wpk, const float* __restrict__ bias, const float* __restrict__ res,
                      float* __restrict__ y, float* __restrict__ y2) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: A[na] | B[nb] | raw staging[ns] | barriers | tmem ptr
+  // layout: A[na] | B[nb] | raw staging[ns] | barriers | tmem ptr | bias
   unsigned char* a_buf = smem;
   unsigned char* b_buf = smem + (size_t)p.na * p.a_bytes;
   unsigned char* raw_buf = b_buf + (size_t)p.nb * p.b_bytes;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(raw_buf + (size_t)p.ns * p.a_bytes);
-  const int nbar = 2 * p.na + 2 * p.nb + 4;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(raw_buf + (size_t)p.ns * p.raw_bytes);
+  const int nbar = 2 * p.na + 2 * p.nb + 4 + 2 * NS_MAX;
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + nbar);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // Cout floats (0 when bias == nullptr)
 
@@ -417,19 +423,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   auto B_EMPTY = [&](int i) { return bar0 + 8u * (2 * p.na + p.nb + i); };
   auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * p.na + 2 * p.nb + i); };
   auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * p.na + 2 * p.nb + 2 + i); };
+  auto RAW_FULL = [&](int i) { return bar0 + 8u * (2 * p.na + 2 * p.nb + 4 + i); };
+  auto RAW_EMPTY = [&](int i) { return bar0 + 8u * (2 * p.na + 2 * p.nb + 4 + NS_MAX + i); };
 
   if (tid == 0) {
     for (int i = 0; i < p.na; ++i) {
       mbar_init(A_FULL(i), NPROD);
-      mbar_init(A_EMPTY(i), 1);
+      mbar_init(A_EMPTY(i), p.nmma);
     }
     for (int i = 0; i < p.nb; ++i) {
       mbar_init(B_FULL(i), 1);
-      mbar_init(B_EMPTY(i), 1);
+      mbar_init(B_EMPTY(i), p.nmma);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(ACC_FULL(i), 1);
+      mbar_init(ACC_FULL(i), p.nmma);
       mbar_init(ACC_EMPTY(i), NEPI);
+    }
+    for (int i = 0; i < NS_MAX; ++i) {
+      mbar_init(RAW_FULL(i), 1);
+      mbar_init(RAW_EMPTY(i), NPROD);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -446,7 +458,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
 
-  if (warp < W_EPI0 && p.ns > 0) {
+  if (warp < W_EPI0 && p.tma_act) {
+    // ===================== A producers, TMA-staged =====================
+    // Warp W_LDA streams the raw fp32 rows of chunk q + ns - 1 into shared memory with bulk copies
+    // (no LSU instructions, no registers); these 8 warps only convert landed stages to the bf16 hi/lo
+    // operand image.  Stages start at a 16-byte aligned sample, `shift` re-aligns the rows; samples
+    // outside [0, T) are never copied and are masked here (zero padding).
+    int s = 0, sph = 0, buf = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_seq;
+      const int t0 = (tile - b * p.tiles_per_seq) * TT;
+      const int ts_first = t0 - p.padL;
+      const int shift = ts_first - (ts_first & ~3);
+      for (int c = 0; c < nc_total; ++c) {
+        mbar_wait(RAW_FULL(s), sph);
+        mbar_wait(A_EMPTY(buf), aph ^ 1);
+        unsigned char* dst = a_buf + (size_t)buf * p.a_bytes;
+        const float* raw = reinterpret_cast<const float*>(raw_buf + (size_t)s * p.raw_bytes);
+        const bool main_chunk = c < p.nchunks;
+        const int rows = main_chunk ? p.R : TT;
+        const int sh = main_chunk ? shift : 0;
+        const int tbase = main_chunk ? ts_first : t0;
+        const unsigned tlim = (unsigned)(main_chunk ? p.T_in : p.T_out);
+        const float slope = main_chunk ? p.pre_slope : 1.f;
+        for (int r = tid; r < rows; r += NPROD) {
+          const bool ok = (unsigned)(tbase + r) < tlim;
+          const float* rr = raw + r + sh;
+#pragma unroll
+          for (int g = 0; g < KC / 8; ++g) {
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = ok ? lrelu(rr[(g * 8 + j) * p.R4], slope) : 0.f;
+            uint4 hi, lo;
+            split8(u, hi, lo);
+            *reinterpret_cast<uint4*>(dst + ((size_t)g * p.R + r) * 16) = hi;
+            *reinterpret_cast<uint4*>(dst + ((size_t)(KC / 8 + g) * p.R + r) * 16) = lo;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(A_FULL(buf));
+        mbar_arrive(RAW_EMPTY(s));
+        if (++s == p.ns) { s = 0; sph ^= 1; }
+        if (++buf == p.na) { buf = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp < W_EPI0 && p.ns > 0) {
     // ===================== A producers, cp.async-staged =====================
     // The raw fp32 chunk q+1 streams into shared memory (no registers held, any padding policy by
     // per-element addressing, zero-fill through src-size 0) while chunk q is converted to the bf16
@@ -458,7 +514,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int c = q % nc_total;
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile - b * p.tiles_per_seq) * TT;
-      const unsigned raw = smem_u32(raw_buf + (size_t)(q % p.ns) * p.a_bytes);
+      const unsigned raw = smem_u32(raw_buf + (size_t)(q % p.ns) * p.raw_bytes);
       if (c < p.nchunks) {
         const float* xc = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in;
         for (int r = tid; r < p.R; r += NPROD) {
@@ -515,7 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int buf = q % p.na;
       mbar_wait(A_EMPTY(buf), ((q / p.na) & 1) ^ 1);
       unsigned char* dst = a_buf + (size_t)buf * p.a_bytes;
-      const float* raw = reinterpret_cast<const float*>(raw_buf + (size_t)(q % p.ns) * p.a_bytes);
+      const float* raw = reinterpret_cast<const float*>(raw_buf + (size_t)(q % p.ns) * p.raw_bytes);
       const int rows = c < p.nchunks ? p.R : TT;
       const float slope = c < p.nchunks ? p.pre_slope : 1.f;
       for (int r = tid; r < rows; r += NPROD) {
@@ -577,15 +633,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int col_begin = ((warp - W_EPI0) >> 2) ? (ngroups / 2) * 16 : 0;
     const int col_end = ((warp - W_EPI0) >> 2) ? p.Cout : (ngroups / 2) * 16;
     const int m = ew * 32 + lane;
-    unsigned it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const bool generic = !(p.shuffle > 1) && !p.wavenet;
+    const long long st = p.T_out;
+    int as = 0, accph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile - b * p.tiles_per_seq) * TT;
-      const int as = it % p.nacc;
-      mbar_wait(ACC_FULL(as), (it / p.nacc) & 1);
+      // L2 prefetch of the NEXT tile's residual (and read-modify-write) lines: one 128-byte line per
+      // (m-tile, column) and warp, no registers held; the epilogue's loads then hit L2 instead of HBM
+      if (generic && (res || p.accumulate) && !(p.variant & 8)) {
+        const int ncol = col_end - col_begin;
+        for (int pass = (tile == (int)blockIdx.x ? 0 : 1); pass < 2; ++pass) {
+          const int tl = pass ? tile + (int)gridDim.x : tile;
+          if (tl >= p.total_tiles) break;
+          const int bb = tl / p.tiles_per_seq;
+          const int tt0 = (tl - bb * p.tiles_per_seq) * TT;
+          for (int i = lane; i < p.MT * ncol; i += 32) {
+            const int mt = i / ncol;
+            const int col = col_begin + (i - mt * ncol);
+            const int tp = tt0 + mt * 128 + ew * 32;
+            if (tp < p.T_out) {
+              const long long off = (long long)(p.co_off + col) * st + tp;
+              if (res) prefetch_l2(res + (long long)bb * p.rbs + off);
+              if (p.accumulate) prefetch_l2(y + (long long)bb * p.ybs + off);
+            }
+          }
+        }
+      }
+      mbar_wait(ACC_FULL(as), accph);
       tc_fence_after();
       const unsigned tacc = tmem_base + ((unsigned)(ew * 32) << 16) + (unsigned)(as * acc_cols);
-      const long long st = p.T_out;
       for (int mt = 0; mt < p.MT; ++mt) {
         const int t = t0 + mt * 128 + m;
         const bool tv = t < p.T_out;
@@ -639,9 +716,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           // address recomputation), every independent load of a 16-column group issued before use
           float* yq = y + (long long)b * p.ybs + (long long)(p.co_off + col_begin) * st + t;
           const float* rq = res ? res + (long long)b * p.rbs + (long long)(p.co_off + col_begin) * st + t : nullptr;
-          int col = col_begin;
-          // (32-column groups were tried: they spill at the 112-register budget of 576 threads)
-          for (; col < col_end; col += 16, yq += 16 * st) {
+          // (32-column groups were tried: they spill at the register budget of this block size)
+          for (int col = col_begin; col < col_end; col += 16, yq += 16 * st) {
             epi_generic<16>(p, tacc + (unsigned)(mt * p.Cout + col), bias_s, col, rq, yq, st, tv);
             if (rq) rq += 16 * st;
           }
@@ -649,68 +725,109 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(as));  // accumulator set drained: the MMA warp may overwrite it
+      if (++as == p.nacc) { as = 0; accph ^= 1; }
     }
   } else if (warp == W_TMA) {
     // ===================== B producer (TMA bulk copies of packed weight stages) =====================
-    {
-      const int per_tile = p.nchunks * p.K + p.nchunks2;
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(wpk);
-      unsigned i = 0;
+    const int per_tile = p.nchunks * p.K + p.nchunks2;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(wpk);
+    int s = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int j = 0; j < per_tile; ++j) {
+        mbar_wait_spin(B_EMPTY(s), ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
+          bulk_g2s(smem_u32(b_buf + (size_t)s * p.b_bytes), src + (size_t)j * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
+        }
+        __syncwarp();
+        if (++s == p.nb) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == W_LDA) {
+    // ===================== raw activation loader (TMA bulk row copies) =====================
+    if (p.tma_act) {
+      int s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        for (int j = 0; j < per_tile; ++j, ++i) {
-          const int s = i % p.nb;
-          mbar_wait_spin(B_EMPTY(s), ((i / p.nb) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
-            bulk_g2s(smem_u32(b_buf + (size_t)s * p.b_bytes), src + (size_t)j * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
+        const int b = tile / p.tiles_per_seq;
+        const int t0 = (tile - b * p.tiles_per_seq) * TT;
+        const int ts0 = (t0 - p.padL) & ~3;
+        for (int c = 0; c < nc_total; ++c) {
+          mbar_wait(RAW_EMPTY(s), ph ^ 1);
+          const float* src;
+          int start, end, rowstride, dst_off;
+          if (c < p.nchunks) {
+            start = ts0 < 0 ? 0 : ts0;
+            end = ts0 + p.R4 < p.T_in ? ts0 + p.R4 : p.T_in;
+            rowstride = p.T_in;
+            dst_off = start - ts0;
+            src = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in;
+          } else {
+            start = t0;
+            end = t0 + TT < p.T_out ? t0 + TT : p.T_out;
+            rowstride = p.T_out;
+            dst_off = 0;
+            src = x2 + ((long long)b * p.C2 + (long long)(c - p.nchunks) * KC) * p.T_out;
+          }
+          const int nbytes = (end - start) * 4;
+          if (nbytes > 0) {
+            if (lane == 0) mbar_expect_tx(RAW_FULL(s), (unsigned)nbytes * KC);
+            __syncwarp();
+            bulk_g2s(smem_u32(raw_buf + (size_t)s * p.raw_bytes) + (unsigned)(lane * p.R4 + dst_off) * 4u,
+                     src + (long long)lane * rowstride + start, (unsigned)nbytes, RAW_FULL(s));
+          } else if (lane == 0) {
+            mbar_arrive(RAW_FULL(s));
           }
           __syncwarp();
+          if (++s == p.ns) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else {
-    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
-    {
-      // descriptor = hi_const : (lo_const + (addr >> 4));  LBO/SBO/version never change in a launch
-      const unsigned long long hi_const = ((unsigned long long)((128u >> 4) | (1u << 14))) << 32;
-      const unsigned a_lo = (((unsigned)p.R) & 0x3FFFu) << 16;     // LBO = R*16 B  -> R 16-byte units
-      const unsigned b_lo = (((unsigned)p.Cout) & 0x3FFFu) << 16;  // LBO = Cout*16 B
-      const unsigned a_sub = (unsigned)(KC / 8) * p.R;             // hi -> lo image distance (16 B units)
-      const unsigned b_sub = (unsigned)(KC / 8) * p.Cout;
-      unsigned ca = 0, i = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = it % p.nacc;
-        mbar_wait_spin(ACC_EMPTY(as), ((it / p.nacc) & 1) ^ 1);
-        tc_fence_after();
-        const unsigned d_base = tmem_base + (unsigned)(as * acc_cols);
-        for (int c = 0; c < nc_total; ++c, ++ca) {
-          const int buf = ca % p.na;
-          mbar_wait_spin(A_FULL(buf), (ca / p.na) & 1);
-          const unsigned a16 = smem_u32(a_buf + (size_t)buf * p.a_bytes) >> 4;
-          const int ntaps = c < p.nchunks ? p.K : 1;
-          for (int k = 0; k < ntaps; ++k, ++i) {
-            const int s = i % p.nb;
-            mbar_wait_spin(B_FULL(s), (i / p.nb) & 1);
-            tc_fence_after();
-            const unsigned b16 = smem_u32(b_buf + (size_t)s * p.b_bytes) >> 4;
-            const unsigned tap_row = c < p.nchunks ? (unsigned)(p.win_mode ? k * TT : k * p.D) : 0u;
+  } else if (warp - W_MMA < p.nmma) {
+    // ===================== MMA issuer(s) (whole warp converged; one elected lane issues) =====================
+    // nmma == 2: warp W_MMA + i owns m-tile i (its own accumulator columns); both commit to the same
+    // stage barriers, whose arrival counts are nmma.
+    const int mw = warp - W_MMA;
+    const bool split2 = p.nmma == 2;
+    // descriptor = hi_const : (lo_const + (addr >> 4));  LBO/SBO/version never change in a launch
+    const unsigned long long hi_const = ((unsigned long long)((128u >> 4) | (1u << 14))) << 32;
+    const unsigned a_lo = ((((unsigned)p.R) & 0x3FFFu) << 16) + (split2 ? (unsigned)mw * 128u : 0u);  // LBO = R*16 B
+    const unsigned b_lo = (((unsigned)p.Cout) & 0x3FFFu) << 16;                                      // LBO = Cout*16 B
+    const unsigned a_sub = (unsigned)(KC / 8) * p.R;  // hi -> lo image distance (16 B units)
+    const unsigned b_sub = (unsigned)(KC / 8) * p.Cout;
+    int buf = 0, aph = 0, s = 0, bph = 0, as = 0, accph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait_spin(ACC_EMPTY(as), accph ^ 1);
+      tc_fence_after();
+      const unsigned d_base = tmem_base + (unsigned)(as * acc_cols) + (split2 ? (unsigned)(mw * p.Cout) : 0u);
+      for (int c = 0; c < nc_total; ++c) {
+        mbar_wait_spin(A_FULL(buf), aph);
+        const unsigned a16 = smem_u32(a_buf + (size_t)buf * p.a_bytes) >> 4;
+        const int ntaps = c < p.nchunks ? p.K : 1;
+        for (int k = 0; k < ntaps; ++k) {
+          mbar_wait_spin(B_FULL(s), bph);
+          tc_fence_after();
+          const unsigned b16 = smem_u32(b_buf + (size_t)s * p.b_bytes) >> 4;
+          const unsigned tap_row = c < p.nchunks ? (unsigned)(p.win_mode ? k * TT : k * p.D) : 0u;
 #pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks) {
-              const unsigned bk = b16 + (unsigned)(2 * ks) * p.Cout;
-              const unsigned ak = a16 + (unsigned)(2 * ks) * p.R + tap_row;
-              const unsigned long long b_hi = hi_const | (unsigned long long)(b_lo + bk);
-              const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + ak);
-              if (p.MT > 1)
-                tc_mma_x3(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, (c | k | ks) != 0 ? 1u : 0u, 1u, (unsigned)p.Cout);
-              else
-                tc_mma_x3_single(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, (c | k | ks) != 0 ? 1u : 0u);
-            }
-            tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const unsigned bk = b16 + (unsigned)(2 * ks) * p.Cout;
+            const unsigned ak = a16 + (unsigned)(2 * ks) * p.R + tap_row;
+            const unsigned long long b_hi = hi_const | (unsigned long long)(b_lo + bk);
+            const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + ak);
+            const unsigned acc = (c | k | ks) != 0 ? 1u : 0u;
+            if (p.MT > 1 && !split2)
+              tc_mma_x3(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, acc, 1u, (unsigned)p.Cout);
+            else
+              tc_mma_x3_single(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, acc);
           }
-          tc_commit(A_EMPTY(buf));
+          tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
+          if (++s == p.nb) { s = 0; bph ^= 1; }
         }
-        tc_commit(ACC_FULL(as));
+        tc_commit(A_EMPTY(buf));
+        if (++buf == p.na) { buf = 0; aph ^= 1; }
       }
+      tc_commit(ACC_FULL(as));
+      if (++as == p.nacc) { as = 0; accph ^= 1; }
     }
   }
   __syncthreads();
@@ -789,13 +906,23 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     if (!p.win_mode && halo > 2048) continue;
     if (p.win_mode && halo <= p.MT * 128) continue;  // a contiguous tile is never larger in that case
     p.a_bytes = 2 * (KC / 8) * p.R * 16;
+    p.R4 = (p.R + 6) & ~3;
+    p.raw_bytes = KC * p.R4 * 4;
+    // activation rows by TMA: zero padding only (out-of-range samples are masked, never copied) and
+    // 16-byte aligned rows; anything else is staged with 4-byte cp.async by the producers
+    p.tma_act = !(p.variant & 2) && !d->pre_gate && !p.win_mode && d->pad_mode == PWGB_PAD_ZERO && d->t_in % 4 == 0 &&
+                (aux_c2 == 0 || d->t_out % 4 == 0);
+    p.nmma = (p.MT == 2 && !(p.variant & 4)) ? 2 : 1;
     // shared-memory split: [na operand buffers][nb weight stages][ns raw staging buffers]
     int na = 0, nb = 0, ns = 0;
-    const size_t A = (size_t)p.a_bytes, Bs = (size_t)p.b_bytes, slack = 2048;
-    if (!d->pre_gate && 2 * A + 3 * A + 3 * Bs + slack <= budget) {
+    const size_t A = (size_t)p.a_bytes, Bs = (size_t)p.b_bytes, S = (size_t)p.raw_bytes, slack = 2048;
+    if (p.tma_act && 2 * A + 3 * S + 3 * Bs + slack <= budget) {
+      ns = 3;
+      na = 2;
+    } else if (!d->pre_gate && 3 * A + 2 * S + 3 * Bs + slack <= budget) {
       ns = 2;
       na = 3;
-    } else if (!d->pre_gate && 2 * A + 2 * A + 2 * Bs + slack <= budget) {
+    } else if (!d->pre_gate && 2 * A + 2 * S + 2 * Bs + slack <= budget) {
       ns = 2;
       na = 2;
     } else if (3 * A + 2 * Bs + slack <= budget) {
@@ -805,7 +932,8 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     } else {
       continue;
     }
-    nb = (int)((budget - slack - (size_t)(na + ns) * A) / Bs);
+    if (ns == 0) p.tma_act = 0;
+    nb = (int)((budget - slack - (size_t)na * A - (size_t)ns * S) / Bs);
     if (nb > 24) nb = 24;
     p.na = na;
     p.nb = nb;
@@ -817,7 +945,7 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     int alloc = 32;
     while (alloc < p.nacc * cols) alloc <<= 1;
     p.tmem_cols = alloc;
-    smem_bytes = (size_t)(na + ns) * p.a_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4) + 16 + 4 * 256;
+    smem_bytes = (size_t)na * p.a_bytes + (size_t)ns * p.raw_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4 + 2 * NS_MAX) + 16 + 4 * 256;
     return 1;
   }
   return 0;
@@ -847,6 +975,8 @@ static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w,
     set_error("conv1d_tc: too many tiles");
     return PWGB_UNSUPPORTED;
   }
+  if (p.tma_act && ((reinterpret_cast<uintptr_t>(x) & 15) || (x2 && (reinterpret_cast<uintptr_t>(x2) & 15))))
+    p.tma_act = 0;  // unaligned base pointer: the producers stage with cp.async instead
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, x2, (const uint4*)packed_w, bias, residual, y, y2);
   return check_launch("conv1d_tc_kernel");
