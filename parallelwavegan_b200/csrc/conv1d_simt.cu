@@ -273,6 +273,104 @@ __global__ void __launch_bounds__(256) conv1d_small_cout_kernel(const ConvK p, c
   }
 }
 
+// Few output channels over LONG sequences (the generators' output convs: 32 -> 1 k7 at 16 x 102400
+// samples, MelGAN 32 -> 4): HBM-bound by the input read.  One CTA = 1024 consecutive positions, a
+// thread owns positions tid + 256 q (coalesced, L1-resident taps), the whole weight tensor sits in
+// shared memory (broadcast reads) and all CO accumulators stay in registers.
+template <int CO>
+__global__ void __launch_bounds__(256) conv1d_fewcout_long_kernel(const ConvK p, const float* __restrict__ x,
+                                                                  const float* __restrict__ w,
+                                                                  const float* __restrict__ bias,
+                                                                  float* __restrict__ y) {
+  extern __shared__ __align__(16) float wsm[];  // [ci][k][CO]
+  for (int i = threadIdx.x; i < p.Cin * p.K * CO; i += 256) {
+    const int co = i % CO, ck = i / CO;
+    wsm[i] = co < p.Cout ? __ldg(w + (long long)co * p.Cin * p.K + ck) : 0.f;
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int o0 = blockIdx.x * 1024 + threadIdx.x;
+  const float* xb = x + (long long)b * p.xbs;
+  float acc[4][CO];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[q][co] = 0.f;
+  const long long first = (long long)blockIdx.x * 1024;
+  const bool interior = first * p.S - p.padL >= 0 && (first + 1023) * p.S + (long long)(p.K - 1) * p.D - p.padL < p.t_in &&
+                        first + 1023 < p.t_out;
+  if (interior) {
+    // no padding inside this CTA: channel-outer / tap-inner so the K re-reads of a row hit L1 at once
+    const float* xq = xb + (long long)o0 * p.S - p.padL;
+    const long long qs = 256LL * p.S;
+    const float* wk = wsm;
+    for (int ci = 0; ci < p.Cin; ++ci, xq += p.xcs) {
+      for (int k = 0; k < p.K; ++k, wk += CO) {
+        const float* xk = xq + (long long)k * p.D;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = lrelu(__ldg(xk + q * qs), p.pre_slope);
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+          const float wv = wk[co];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q][co] = fmaf(v[q], wv, acc[q][co]);
+        }
+      }
+    }
+  } else
+  for (int k = 0; k < p.K; ++k) {
+    // source row of every owned position for this tap (padding policy resolved once per tap)
+    long long row[4];
+    bool ok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      long long r = (long long)(o0 + 256 * q) * p.S + (long long)k * p.D - p.padL;
+      ok[q] = o0 + 256 * q < p.t_out;
+      if (r < 0 || r >= p.t_in) {
+        if (p.pad_mode == PWGB_PAD_ZERO) {
+          ok[q] = false;
+        } else if (p.pad_mode == PWGB_PAD_REFLECT) {
+          r = r < 0 ? -r : 2LL * (p.t_in - 1) - r;
+          ok[q] = ok[q] && r >= 0 && r < p.t_in;
+        } else {
+          r = r < 0 ? 0 : p.t_in - 1;
+        }
+      }
+      row[q] = ok[q] ? r : 0;
+    }
+    const float* wk = wsm + k * CO;
+    const float* xc = xb;
+#pragma unroll 4
+    for (int ci = 0; ci < p.Cin; ++ci, xc += p.xcs, wk += p.K * CO) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = ok[q] ? lrelu(__ldg(xc + row[q]), p.pre_slope) : 0.f;
+#pragma unroll
+      for (int co = 0; co < CO; ++co) {
+        const float wv = wk[co];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q][co] = fmaf(v[q], wv, acc[q][co]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int o = o0 + 256 * q;
+    if (o >= p.t_out) continue;
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      if (co >= p.Cout) break;
+      float v = acc[q][co] + (bias ? __ldg(bias + co) : 0.f);
+      if (p.post_act == PWGB_ACT_TANH)
+        v = tanhf(v);
+      else if (p.post_act == PWGB_ACT_LRELU)
+        v = lrelu(v, p.post_slope);
+      y[(long long)b * p.ybs + (long long)co * p.t_out + o] = v * p.out_scale;
+    }
+  }
+}
+
 // short sequences (discriminator tails, 10-50 positions per item): 1 position per lane instead of 4
 template <int RCO, int WARPS_CO>
 static int launch_conv(ConvK p, const float* x, const float* w, const float* bias, const float* res, float* y,
@@ -322,6 +420,18 @@ int conv1d_forward_simt(const pwgb_conv1d_desc* d, const float* x, const float* 
       !p.accumulate && p.shuffle <= 1 && (long long)p.Lout * p.B <= 65536 && p.B <= 65535) {
     conv1d_small_cout_kernel<<<dim3(ceil_div(p.Lout, 32), p.B), 256, 0, st>>>(p, x, w, bias, y);
     return check_launch("conv1d_small_cout_kernel");
+  }
+  if (p.Cout <= 4 && p.groups == 1 && p.P == 1 && p.t_valid == p.Lin && !p.pre_gate && !residual && !p.accumulate &&
+      p.shuffle <= 1 && p.t_out >= 4096 && p.B <= 65535 && (size_t)p.Cin * p.K * 4 * sizeof(float) <= 40 * 1024) {
+    const dim3 grid(ceil_div(p.t_out, 1024), p.B);
+    if (p.Cout == 1) {
+      conv1d_fewcout_long_kernel<1><<<grid, 256, (size_t)p.Cin * p.K * sizeof(float), st>>>(p, x, w, bias, y);
+    } else if (p.Cout == 2) {
+      conv1d_fewcout_long_kernel<2><<<grid, 256, (size_t)p.Cin * p.K * 2 * sizeof(float), st>>>(p, x, w, bias, y);
+    } else {
+      conv1d_fewcout_long_kernel<4><<<grid, 256, (size_t)p.Cin * p.K * 4 * sizeof(float), st>>>(p, x, w, bias, y);
+    }
+    return check_launch("conv1d_fewcout_long_kernel");
   }
   const int cg = p.Cout_g;
   if (cg >= 64) return launch_conv<8, 8>(p, x, w, bias, residual, y, st);

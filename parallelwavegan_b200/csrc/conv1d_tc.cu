@@ -29,7 +29,7 @@ constexpr int KC = 32;  // input channels per activation chunk / weight stage (2
 constexpr int NPROD = 256;  // producer threads (warps 0-7); 4 warps measured slower (conversion-bound)
 constexpr int NEPI = 256;   // epilogue threads (warps 8-15)
 // warp roles after the producers / epilogue: weight TMA, MMA issuer(s), activation TMA
-constexpr int W_EPI0 = NPROD / 32, W_TMA = (NPROD + NEPI) / 32, W_MMA = W_TMA + 1, W_MMA1 = W_TMA + 2, W_LDA = W_TMA + 3;
+constexpr int W_EPI0 = NPROD / 32, W_TMA = (NPROD + NEPI) / 32, W_MMA = W_TMA + 1, W_LDA = W_TMA + 3;  // W_MMA + 1: second MMA issuer
 constexpr int TC_THREADS = NPROD + NEPI + 128;
 constexpr int NS_MAX = 4;  // raw activation stages
 constexpr unsigned SPIN_LIMIT = 1u << 22;
@@ -47,6 +47,8 @@ struct TcK {
   int R4, raw_bytes;     // raw stage: KC rows of R4 floats (R4 = R + alignment slack, multiple of 4)
   int tma_act;           // 1: raw stages are filled by cp.async.bulk row copies (warp W_LDA), 0: by cp.async (producers)
   int nmma;              // MMA issuer warps: 2 = one per 128-row m-tile (MT == 2)
+  int shuffle_vec;       // pixel-shuffle epilogue may use 16-byte stores
+  int nco;               // column chunks of Cout channels sharing this launch (conv-transpose: cout * stride > 256)
   long long xbs, ybs, rbs;
   unsigned idesc;
   int tmem_cols;
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int TT = p.MT * 128;
   const int nc_total = p.nchunks + p.nchunks2;
   const int acc_cols = p.MT * p.Cout;
+  const int pct = p.B * p.tiles_per_seq;  // work items per column chunk (nco chunks share one launch)
 
   const unsigned bar0 = smem_u32(bars);
   auto A_FULL = [&](int i) { return bar0 + 8u * i; };
@@ -466,8 +469,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // outside [0, T) are never copied and are masked here (zero padding).
     int s = 0, sph = 0, buf = 0, aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = tile / p.tiles_per_seq;
-      const int t0 = (tile - b * p.tiles_per_seq) * TT;
+      const int tr = p.nco > 1 ? tile % pct : tile;  // tile within its column chunk
+      const int b = tr / p.tiles_per_seq;
+      const int t0 = (tr - b * p.tiles_per_seq) * TT;
       const int ts_first = t0 - p.padL;
       const int shift = ts_first - (ts_first & ~3);
       for (int c = 0; c < nc_total; ++c) {
@@ -512,8 +516,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     auto issue = [&](int q) {
       const int tile = blockIdx.x + (q / nc_total) * gridDim.x;
       const int c = q % nc_total;
-      const int b = tile / p.tiles_per_seq;
-      const int t0 = (tile - b * p.tiles_per_seq) * TT;
+      const int tr = p.nco > 1 ? tile % pct : tile;  // tile within its column chunk
+      const int b = tr / p.tiles_per_seq;
+      const int t0 = (tr - b * p.tiles_per_seq) * TT;
       const unsigned raw = smem_u32(raw_buf + (size_t)(q % p.ns) * p.raw_bytes);
       if (c < p.nchunks) {
         const float* xc = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in;
@@ -594,8 +599,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===================== A producers, direct register path =====================
     unsigned ca = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = tile / p.tiles_per_seq;
-      const int t0 = (tile - b * p.tiles_per_seq) * TT;
+      const int tr = p.nco > 1 ? tile % pct : tile;  // tile within its column chunk
+      const int b = tr / p.tiles_per_seq;
+      const int t0 = (tr - b * p.tiles_per_seq) * TT;
       const float* xb = x + (long long)b * p.xbs;
       for (int c = 0; c < nc_total; ++c, ++ca) {
         const int buf = ca % p.na;
@@ -637,8 +643,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const long long st = p.T_out;
     int as = 0, accph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = tile / p.tiles_per_seq;
-      const int t0 = (tile - b * p.tiles_per_seq) * TT;
+      const int tr = p.nco > 1 ? tile % pct : tile;  // tile within its column chunk
+      const int b = tr / p.tiles_per_seq;
+      const int t0 = (tr - b * p.tiles_per_seq) * TT;
       // L2 prefetch of the NEXT tile's residual (and read-modify-write) lines: one 128-byte line per
       // (m-tile, column) and warp, no registers held; the epilogue's loads then hit L2 instead of HBM
       if (generic && (res || p.accumulate) && !(p.variant & 8)) {
@@ -646,8 +653,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int pass = (tile == (int)blockIdx.x ? 0 : 1); pass < 2; ++pass) {
           const int tl = pass ? tile + (int)gridDim.x : tile;
           if (tl >= p.total_tiles) break;
-          const int bb = tl / p.tiles_per_seq;
-          const int tt0 = (tl - bb * p.tiles_per_seq) * TT;
+          const int tlr = p.nco > 1 ? tl % pct : tl;
+          const int bb = tlr / p.tiles_per_seq;
+          const int tt0 = (tlr - bb * p.tiles_per_seq) * TT;
           for (int i = lane; i < p.MT * ncol; i += 32) {
             const int mt = i / ncol;
             const int col = col_begin + (i - mt * ncol);
@@ -660,13 +668,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
+      const int co_base = p.co_off + (p.nco > 1 ? (tile / pct) * p.Cout : 0);
       mbar_wait(ACC_FULL(as), accph);
       tc_fence_after();
       const unsigned tacc = tmem_base + ((unsigned)(ew * 32) << 16) + (unsigned)(as * acc_cols);
       for (int mt = 0; mt < p.MT; ++mt) {
         const int t = t0 + mt * 128 + m;
         const bool tv = t < p.T_out;
-        if (p.shuffle > 1) {
+        if (p.shuffle > 1 && p.shuffle_vec) {
+          // pixel-shuffle epilogue, vector form: the `shuffle` phases of one output channel are adjacent
+          // columns AND adjacent output samples, so a thread stores 16-byte pieces (a warp: contiguous KBs)
+          for (int col = col_begin; col < col_end; col += 16) {
+            unsigned r[16];
+            tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
+            tc_wait_ld();
+            if (tv) {
+#pragma unroll
+              for (int j0 = 0; j0 < 16; j0 += 4) {
+                const int co = co_base + col + j0;
+                const int cof = co / p.shuffle;
+                const int of = t * p.shuffle + (co - cof * p.shuffle) - p.shuffle_pad;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  v[j] = __uint_as_float(r[j0 + j]) + (p.nco > 1 ? (bias ? __ldg(bias + cof) : 0.f) : bias_s[col + j0 + j]);
+                  if (p.post_act == PWGB_ACT_TANH)
+                    v[j] = tanhf(v[j]);
+                  else if (p.post_act == PWGB_ACT_LRELU)
+                    v[j] = lrelu(v[j], p.post_slope);
+                  v[j] *= p.out_scale;
+                }
+                if (of >= 0 && of < p.shuffle_tout)
+                  *reinterpret_cast<float4*>(y + (long long)b * p.ybs + (long long)cof * p.shuffle_tout + of) =
+                      make_float4(v[0], v[1], v[2], v[3]);
+              }
+            }
+          }
+        } else if (p.shuffle > 1) {
           for (int col = col_begin; col < col_end; col += 16) {
             unsigned r[16];
             tc_ld16(tacc + (unsigned)(mt * p.Cout + col), r);
@@ -674,9 +712,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (tv) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const int co = p.co_off + col + j;
+                const int co = co_base + col + j;
                 const int cof = co / p.shuffle;
-                float v = __uint_as_float(r[j]) + bias_s[col + j];
+                float v = __uint_as_float(r[j]) + (p.nco > 1 ? (bias ? __ldg(bias + cof) : 0.f) : bias_s[col + j]);
                 if (p.post_act == PWGB_ACT_TANH)
                   v = tanhf(v);
                 else if (p.post_act == PWGB_ACT_LRELU)
@@ -733,11 +771,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const unsigned char* src = reinterpret_cast<const unsigned char*>(wpk);
     int s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const unsigned char* srcc = src + (p.nco > 1 ? (size_t)(tile / pct) * per_tile * p.b_bytes : 0);
       for (int j = 0; j < per_tile; ++j) {
         mbar_wait_spin(B_EMPTY(s), ph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(B_FULL(s), (unsigned)p.b_bytes);
-          bulk_g2s(smem_u32(b_buf + (size_t)s * p.b_bytes), src + (size_t)j * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
+          bulk_g2s(smem_u32(b_buf + (size_t)s * p.b_bytes), srcc + (size_t)j * p.b_bytes, (unsigned)p.b_bytes, B_FULL(s));
         }
         __syncwarp();
         if (++s == p.nb) { s = 0; ph ^= 1; }
@@ -748,8 +787,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (p.tma_act) {
       int s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int b = tile / p.tiles_per_seq;
-        const int t0 = (tile - b * p.tiles_per_seq) * TT;
+        const int tr = p.nco > 1 ? tile % pct : tile;  // tile within its column chunk
+      const int b = tr / p.tiles_per_seq;
+        const int t0 = (tr - b * p.tiles_per_seq) * TT;
         const int ts0 = (t0 - p.padL) & ~3;
         for (int c = 0; c < nc_total; ++c) {
           mbar_wait(RAW_EMPTY(s), ph ^ 1);
@@ -845,6 +885,7 @@ static int g_tc_variant = 0;
 static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int aux_c2 = 0, int split = 0) {
   p.variant = g_tc_variant;
   p.co_off = 0;
+  p.nco = 1;
   const int P = d->period < 1 ? 1 : d->period;
   if (d->stride != 1 || d->groups != 1 || P != 1) return 0;
   if (d->cin % KC != 0 || d->cout % 16 != 0 || d->cout < 16 || d->cout > 256) return 0;
@@ -913,6 +954,8 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     p.tma_act = !(p.variant & 2) && !d->pre_gate && !p.win_mode && d->pad_mode == PWGB_PAD_ZERO && d->t_in % 4 == 0 &&
                 (aux_c2 == 0 || d->t_out % 4 == 0);
     p.nmma = (p.MT == 2 && !(p.variant & 4)) ? 2 : 1;
+    p.shuffle_vec = d->shuffle > 1 && d->shuffle % 4 == 0 && 16 % d->shuffle == 0 && d->shuffle_pad % 4 == 0 &&
+                    d->shuffle_tout % 4 == 0 && !(p.variant & 16);
     // shared-memory split: [na operand buffers][nb weight stages][ns raw staging buffers]
     int na = 0, nb = 0, ns = 0;
     const size_t A = (size_t)p.a_bytes, Bs = (size_t)p.b_bytes, S = (size_t)p.raw_bytes, slack = 2048;
@@ -977,6 +1020,7 @@ static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w,
   }
   if (p.tma_act && ((reinterpret_cast<uintptr_t>(x) & 15) || (x2 && (reinterpret_cast<uintptr_t>(x2) & 15))))
     p.tma_act = 0;  // unaligned base pointer: the producers stage with cp.async instead
+  if (p.shuffle_vec && ((reinterpret_cast<uintptr_t>(y) & 15) || p.co_off % 16 != 0)) p.shuffle_vec = 0;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, x2, (const uint4*)packed_w, bias, residual, y, y2);
   return check_launch("conv1d_tc_kernel");
@@ -985,12 +1029,18 @@ static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w,
 // Internal entry for N-chunked callers (conv_transpose): runs output channels
 // [co_off, co_off + d->cout) of a conv whose full output has cout_total channels.
 int conv1d_tc_chunk(const pwgb_conv1d_desc* d, int co_off, int cout_total, const float* x, const void* packed_w,
-                    const float* bias, float* y, cudaStream_t st) {
+                    const float* bias, float* y, cudaStream_t st, int nco) {
   TcK p;
   size_t bytes = 0;
   if (!tc_plan(d, p, bytes)) return PWGB_UNSUPPORTED;
   p.co_off = co_off;
   p.ybs = d->shuffle > 1 ? (long long)(cout_total / d->shuffle) * d->shuffle_tout : (long long)cout_total * d->t_out;
+  if (nco > 1) {
+    // the chunks' packed images are consecutive: one launch walks (chunk, batch, time tile)
+    if (d->shuffle <= 1 || (long long)p.total_tiles * nco > 0x7fffffffLL) return PWGB_UNSUPPORTED;
+    p.nco = nco;
+    p.total_tiles *= nco;
+  }
   return tc_launch(p, bytes, x, packed_w, bias, nullptr, y, st);
 }
 

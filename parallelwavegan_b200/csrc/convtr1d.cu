@@ -9,7 +9,7 @@ namespace pwgb {
 int conv1d_forward_simt(const pwgb_conv1d_desc* d, const float* x, const float* w, const float* bias,
                         const float* residual, float* y, cudaStream_t st);
 int conv1d_tc_chunk(const pwgb_conv1d_desc* d, int co_off, int cout_total, const float* x, const void* packed_w,
-                    const float* bias, float* y, cudaStream_t st);
+                    const float* bias, float* y, cudaStream_t st, int nco);
 int conv1d_tc_plan_ok(const pwgb_conv1d_desc* d);
 void tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, cudaStream_t st);
 
@@ -103,10 +103,8 @@ extern "C" int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const 
         tc_pack_weight(wv + (size_t)co * d->cin * M, d->cin, chunk, M, pkc, st);
         rc = check_launch("tc_pack_weight_kernel");
         if (rc) return rc;
-        rc = conv1d_tc_chunk(&cc, co, c.cout, x, pkc, bias, y, st);
-        if (rc) return rc;
       }
-      return PWGB_OK;
+      return conv1d_tc_chunk(&cc, 0, c.cout, x, pk, bias, y, st, c.cout / chunk);
     }
   }
   return conv1d_forward_simt(&c, x, wv, bias, nullptr, y, st);
