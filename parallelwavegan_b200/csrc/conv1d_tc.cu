@@ -205,6 +205,40 @@ __device__ __forceinline__ void tc_mma_x3_single(unsigned d0, unsigned long long
       "l"(a_hi), "l"(b_hi), "r"(a_sub), "r"(b_sub), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Both K-steps of one (chunk, tap) for one m-tile: 6 MMAs from two base descriptors.  Everything that
+// differs between the six instructions is added in the uniform datapath inside the block, so the
+// issuing thread pays the register->uniform moves once per tap instead of once per MMA.
+// a_step / b_step: descriptor distance of the second 16-channel K-step (16-byte units).
+__device__ __forceinline__ void tc_mma_tap6(unsigned d0, unsigned long long a_hi, unsigned long long b_hi, unsigned a_sub,
+                                            unsigned b_sub, unsigned a_step, unsigned b_step, unsigned idesc,
+                                            unsigned accumulate) {
+  static_assert(KC == 32, "tc_mma_tap6 issues exactly two K-steps");
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pacc;\n\t"
+      ".reg .b64 a_lo, b_lo, a1, b1, a1_lo, b1_lo, t64;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pacc, %8, 0;\n\t"
+      "cvt.u64.u32 t64, %3;\n\t"
+      "add.u64 a_lo, %1, t64;\n\t"
+      "cvt.u64.u32 t64, %4;\n\t"
+      "add.u64 b_lo, %2, t64;\n\t"
+      "cvt.u64.u32 t64, %5;\n\t"
+      "add.u64 a1, %1, t64;\n\t"
+      "add.u64 a1_lo, a_lo, t64;\n\t"
+      "cvt.u64.u32 t64, %6;\n\t"
+      "add.u64 b1, %2, t64;\n\t"
+      "add.u64 b1_lo, b_lo, t64;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %7, pacc;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a_lo, %2, %7, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b_lo, %7, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %7, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1_lo, b1, %7, 1;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1_lo, %7, 1;\n\t"
+      "}" ::"r"(d0),
+      "l"(a_hi), "l"(b_hi), "r"(a_sub), "r"(b_sub), "r"(a_step), "r"(b_step), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -848,17 +882,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tc_fence_after();
           const unsigned b16 = smem_u32(b_buf + (size_t)s * p.b_bytes) >> 4;
           const unsigned tap_row = c < p.nchunks ? (unsigned)(p.win_mode ? k * TT : k * p.D) : 0u;
+          if (p.MT == 1 || split2) {
+            const unsigned long long b_hi = hi_const | (unsigned long long)(b_lo + b16);
+            const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + a16 + tap_row);
+            tc_mma_tap6(d_base, a_hi, b_hi, a_sub, b_sub, 2u * (unsigned)p.R, 2u * (unsigned)p.Cout, p.idesc,
+                        (c | k) != 0 ? 1u : 0u);
+          } else {
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            const unsigned bk = b16 + (unsigned)(2 * ks) * p.Cout;
-            const unsigned ak = a16 + (unsigned)(2 * ks) * p.R + tap_row;
-            const unsigned long long b_hi = hi_const | (unsigned long long)(b_lo + bk);
-            const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + ak);
-            const unsigned acc = (c | k | ks) != 0 ? 1u : 0u;
-            if (p.MT > 1 && !split2)
-              tc_mma_x3(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, acc, 1u, (unsigned)p.Cout);
-            else
-              tc_mma_x3_single(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, acc);
+            for (int ks = 0; ks < KC / 16; ++ks) {
+              const unsigned bk = b16 + (unsigned)(2 * ks) * p.Cout;
+              const unsigned ak = a16 + (unsigned)(2 * ks) * p.R + tap_row;
+              const unsigned long long b_hi = hi_const | (unsigned long long)(b_lo + bk);
+              const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + ak);
+              tc_mma_x3(d_base, a_hi, b_hi, a_sub, b_sub, p.idesc, (c | k | ks) != 0 ? 1u : 0u, 1u, (unsigned)p.Cout);
+            }
           }
           tc_commit(B_EMPTY(s));  // weight stage reusable once these MMAs retire
           if (++s == p.nb) { s = 0; bph ^= 1; }
