@@ -421,8 +421,8 @@ def main():
     fl, by, tms, cnt = agg[dom]
     achieved = fl / (tms * 1e-3) / 1e12
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf_peak, "traffic": 592.1e6,
-                "traffic_note": "dram__bytes_read+write of ONE representative launch (cin=cout=128, k=3, T=25600, B=16, with residual; profiles/ncu_r1_tc_v6_c128k3_summary.txt) whose algorithmic bytes are 629 MB; launches differ in shape so this is not an average",
+                "frac": achieved / tf_peak, "traffic": 709.2e6,
+                "traffic_note": "dram__bytes_read+write of ONE representative launch (cin=cout=128, k=3, T=25600, B=16, with residual; profiles/ncu_r1_tc_v13_c128k3_summary.txt: 533.2 MB read + 175.9 MB written) whose algorithmic bytes are 629 MB (the 80 MB over-read is halo rows plus the epilogue's L2 prefetch); launches differ in shape so this is not an average",
                 "peak_source": peak_src,
                 "launches_per_step": cnt / 3, "avg_launch_ms": tms / cnt, "share_of_step": tms / sum(v[2] for v in agg.values()),
                 "algorithmic_flops_per_step": fl / 3,
