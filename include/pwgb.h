@@ -260,6 +260,27 @@ PWGB_API int pwgb_stft_loss_terms(const float* xm, const float* ym, long long n,
 PWGB_API int pwgb_stft_loss_dmag(const float* xm, const float* ym, long long n, const double* sums3, const float* gout2,
                         float weight, float* dxm, void* stream);
 
+/* ------------------------------------------------------------------------
+ * StyleMelGAN generator glue (layers/tade_res_block.py:56-75, 135-160; models/style_melgan.py:140-160).
+ * The six k=9 convs of a TADEResBlock go through the conv entry points above; these are the element /
+ * row kernels between them (inference; no adjoints yet):
+ *   instance_norm:     torch.nn.InstanceNorm1d (biased variance, no affine) of rows x t, with an optional
+ *                      LeakyReLU(pre_slope) applied to the input first (pre_slope = 1: none)
+ *   upsample_nearest:  torch.nn.Upsample(scale_factor, "nearest"): y[r, o] = x[r, o / scale]
+ *   leaky_relu:        y = LeakyReLU(x) (may run in place)
+ *   tade_combine:      cg (B, 2C, t_out), xn (B, C, t_out / scale): y = cg[:, :C] * up(xn) + cg[:, C:]
+ *   tade_gate:         x (B, 2C, t): y = gate(x[:, :C]) * tanh(x[:, C:]) [+ up(residual (B, C, t / scale))],
+ *                      gate = softmax over channels (softmax != 0) or sigmoid
+ * ---------------------------------------------------------------------- */
+PWGB_API int pwgb_instance_norm_forward(const float* x, float* y, long long rows, long long t, float eps, float pre_slope,
+                               void* stream);
+PWGB_API int pwgb_upsample_nearest_forward(const float* x, float* y, long long rows, long long t_in, int scale, void* stream);
+PWGB_API int pwgb_leaky_relu_forward(const float* x, float* y, long long n, float slope, void* stream);
+PWGB_API int pwgb_tade_combine_forward(const float* cg, const float* xn, float* y, int batch, int channels, long long t_out,
+                              int scale, void* stream);
+PWGB_API int pwgb_tade_gate_forward(const float* x, const float* residual, float* y, int batch, int channels, long long t,
+                           int scale, int softmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

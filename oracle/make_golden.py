@@ -137,6 +137,24 @@ def gen_pwg(name, kwargs, B, frames, seed, gain):
     save(name, meta, y=y, c_up=c_up[:, :, :512], x1=x1[:, :, :256], s1=s1[:, :, :256], y_inf=y_inf)
 
 
+def gen_style_melgan(name, kwargs, B, T, seed, gain):
+    from parallel_wavegan.models import StyleMelGANGenerator
+
+    torch.manual_seed(0)
+    m = StyleMelGANGenerator(**kwargs).eval()
+    spec, sd = load_synth(m, seed, gain)
+    c = synth.randn((B, kwargs.get("aux_channels", 80), T), seed + 1)
+    z = synth.randn((B, kwargs.get("in_channels", 128), 1), seed + 2)
+    with torch.no_grad():
+        y = m(c, z)
+        x0 = m.noise_upsample(z)
+        x1, c1 = m.blocks[0](x0, c)
+    meta = dict(kind="style_melgan_generator", kwargs=kwargs, spec=spec, seed=seed, gain=gain, checksum=synth.checksum(sd),
+                c_shape=list(c.shape), c_seed=seed + 1, z_shape=list(z.shape), z_seed=seed + 2)
+    print("   out std %.3f absmax %.3f" % (y.std(), y.abs().max()))
+    save(name, meta, y=y, x0=x0, x1=x1, c1=c1)
+
+
 def gen_pqmf():
     from parallel_wavegan.layers import PQMF
 
@@ -289,6 +307,16 @@ def main():
     # causal variants (test/test_hifigan.py:198-226, test/test_melgan.py causal cases)
     gen_hifigan("hifigan_causal", dict(small_hifi, use_causal_conv=True), B=2, T=16, seed=14, gain=1.15)
     gen_melgan("melgan_causal", dict(mel_small, use_causal_conv=True, use_final_nonlinear_activation=True), B=2, T=20, seed=23, gain=1.2)
+    # StyleMelGAN v1 (egs/csmsc/voc1/conf/style_melgan.v1.yaml:31-50; test/test_style_melgan.py:24-42): the noise
+    # path fixes the length, T = prod(noise_upsample_scales) = 88 frames for one noise frame
+    style = dict(in_channels=128, aux_channels=80, channels=64, out_channels=1, kernel_size=9, dilation=2, bias=True,
+                 noise_upsample_scales=[11, 2, 2, 2], noise_upsample_activation="LeakyReLU",
+                 noise_upsample_activation_params={"negative_slope": 0.2}, upsample_scales=[2, 2, 2, 2, 2, 2, 2, 2, 1],
+                 upsample_mode="nearest", gated_function="softmax", use_weight_norm=True)
+    gen_style_melgan("style_melgan_v1", style, B=2, T=88, seed=41, gain=1.0)
+    style_small = dict(style, in_channels=16, channels=32, aux_channels=10, noise_upsample_scales=[3, 2], upsample_scales=[2, 3, 1],
+                       gated_function="sigmoid", kernel_size=5, dilation=3)
+    gen_style_melgan("style_melgan_small", style_small, B=2, T=6, seed=42, gain=1.0)
     # PWG v1 (egs/ljspeech/voc1/conf/parallel_wavegan.v1.yaml:28-46)
     pwg = dict(in_channels=1, out_channels=1, kernel_size=3, layers=30, stacks=3, residual_channels=64, gate_channels=128, skip_channels=64, aux_channels=80, aux_context_window=2, dropout=0.0, use_weight_norm=True, use_causal_conv=False, upsample_conditional_features=True, upsample_net="ConvInUpsampleNetwork", upsample_params={"upsample_scales": [4, 4, 4, 4]})
     gen_pwg("pwg_v1", pwg, B=1, frames=10, seed=31, gain=1.0)

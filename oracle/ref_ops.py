@@ -302,6 +302,71 @@ def melgan_generator(w, c, cfg=MB_MELGAN_V2):
 
 
 # --------------------------------------------------------------------------
+# StyleMelGAN generator (models/style_melgan.py:22-270, layers/tade_res_block.py)
+# --------------------------------------------------------------------------
+
+STYLE_MELGAN_V1 = dict(  # egs/csmsc/voc1/conf/style_melgan.v1.yaml:31-50
+    in_channels=128,
+    aux_channels=80,
+    channels=64,
+    out_channels=1,
+    kernel_size=9,
+    dilation=2,
+    noise_upsample_scales=(11, 2, 2, 2),
+    noise_upsample_negative_slope=0.2,
+    upsample_scales=(2, 2, 2, 2, 2, 2, 2, 2, 1),
+    gated_function="softmax",
+)
+
+
+def _nearest(x, factor):
+    """torch.nn.Upsample(scale_factor=factor, mode="nearest") on (B, C, T)."""
+    return F.interpolate(x, scale_factor=factor, mode="nearest") if factor != 1 else F.interpolate(x, scale_factor=1, mode="nearest")
+
+
+def tade_layer(w, prefix, x, c, kernel_size, upsample_factor):
+    """TADELayer.forward (layers/tade_res_block.py:56-75)."""
+    pad = (kernel_size - 1) // 2
+    x = F.instance_norm(x)  # InstanceNorm1d: no affine, no running stats, eps 1e-5, biased variance
+    c = _nearest(c, upsample_factor)
+    c = F.conv1d(c, w[f"{prefix}.aux_conv.0.weight"], w.get(f"{prefix}.aux_conv.0.bias"), padding=pad)
+    cg = F.conv1d(c, w[f"{prefix}.gated_conv.0.weight"], w.get(f"{prefix}.gated_conv.0.bias"), padding=pad)
+    cg1, cg2 = cg.split(cg.size(1) // 2, dim=1)
+    return cg1 * _nearest(x, upsample_factor) + cg2, c
+
+
+def tade_res_block(w, prefix, x, c, kernel_size, dilation, upsample_factor, gated_function="softmax"):
+    """TADEResBlock.forward (layers/tade_res_block.py:135-160)."""
+    gate = (lambda t: torch.softmax(t, dim=1)) if gated_function == "softmax" else torch.sigmoid
+    pad = (kernel_size - 1) // 2
+    residual = x
+    x, c = tade_layer(w, f"{prefix}.tade1", x, c, kernel_size, 1)
+    x = F.conv1d(x, w[f"{prefix}.gated_conv1.weight"], w.get(f"{prefix}.gated_conv1.bias"), padding=pad)
+    xa, xb = x.split(x.size(1) // 2, dim=1)
+    x = gate(xa) * torch.tanh(xb)
+    x, c = tade_layer(w, f"{prefix}.tade2", x, c, kernel_size, upsample_factor)
+    x = F.conv1d(x, w[f"{prefix}.gated_conv2.weight"], w.get(f"{prefix}.gated_conv2.bias"), dilation=dilation, padding=pad * dilation)
+    xa, xb = x.split(x.size(1) // 2, dim=1)
+    x = gate(xa) * torch.tanh(xb)
+    return _nearest(residual, upsample_factor) + x, c
+
+
+def style_melgan_generator(w, c, z, cfg=STYLE_MELGAN_V1):
+    """StyleMelGANGenerator.forward (models/style_melgan.py:140-160) with an explicit noise tensor
+    z (B, in_channels, T_z): x = noise_upsample(z); x, c = block(x, c) ...; tanh(output_conv(x))."""
+    slope = cfg.get("noise_upsample_negative_slope", 0.2)
+    x = z
+    for i, s in enumerate(cfg["noise_upsample_scales"]):
+        x = F.conv_transpose1d(x, w[f"noise_upsample.{2 * i}.weight"], w.get(f"noise_upsample.{2 * i}.bias"), stride=s,
+                               padding=s // 2 + s % 2, output_padding=s % 2)
+        x = F.leaky_relu(x, slope)
+    for i, s in enumerate(cfg["upsample_scales"]):
+        x, c = tade_res_block(w, f"blocks.{i}", x, c, cfg["kernel_size"], cfg["dilation"], s, cfg.get("gated_function", "softmax"))
+    pad = (cfg["kernel_size"] - 1) // 2
+    return torch.tanh(F.conv1d(x, w["output_conv.0.weight"], w.get("output_conv.0.bias"), padding=pad))
+
+
+# --------------------------------------------------------------------------
 # PQMF (layers/pqmf.py)
 # --------------------------------------------------------------------------
 

@@ -436,3 +436,67 @@ class ConvInUpsampleNetwork(torch.nn.Module):
     def forward(self, c, out_channels=None):
         c_ = ops.conv1d(c, effective_weight(self.conv_in), None)  # no padding: input already carries the context
         return self.upsample(c_, out_channels=out_channels)
+
+
+# --------------------------------------------------------------------------
+# StyleMelGAN blocks (layers/tade_res_block.py) -- inference only
+# --------------------------------------------------------------------------
+
+
+class TADELayer(torch.nn.Module):
+    """layers/tade_res_block.py:13-75: x_norm modulated by two convs of the (upsampled) conditioning."""
+
+    def __init__(self, in_channels=64, aux_channels=80, kernel_size=9, bias=True, upsample_factor=2, upsample_mode="nearest"):
+        super().__init__()
+        if upsample_mode != "nearest":
+            raise PwgbError(f"TADELayer: upsample_mode={upsample_mode!r} has no sm_100a kernel (nearest only)")
+        self.norm = torch.nn.InstanceNorm1d(in_channels)  # parameter-free container (eps read from it)
+        self.aux_conv = torch.nn.Sequential(
+            torch.nn.Conv1d(aux_channels, in_channels, kernel_size, 1, bias=bias, padding=(kernel_size - 1) // 2))
+        self.gated_conv = torch.nn.Sequential(
+            torch.nn.Conv1d(in_channels, in_channels * 2, kernel_size, 1, bias=bias, padding=(kernel_size - 1) // 2))
+        self.upsample = torch.nn.Upsample(scale_factor=upsample_factor, mode=upsample_mode)
+        self.upsample_factor = int(upsample_factor)
+        self.pad = (kernel_size - 1) // 2
+
+    def forward(self, x, c, pre_slope=1.0):
+        """(B, C, T), (B, aux, T') -> (B, C, T * f), (B, C, T' * f); ``pre_slope``: pending LeakyReLU on x."""
+        f = self.upsample_factor
+        xn = ops.instance_norm(x, eps=self.norm.eps, pre_slope=pre_slope)
+        c = ops.upsample_nearest(c, f)
+        ac, gc = self.aux_conv[0], self.gated_conv[0]
+        c = ops.conv1d(c, effective_weight(ac), ac.bias, padding=self.pad)
+        cg = ops.conv1d(c, effective_weight(gc), gc.bias, padding=self.pad)
+        return ops.tade_combine(cg, xn, f), c
+
+
+class TADEResBlock(torch.nn.Module):
+    """layers/tade_res_block.py:78-160."""
+
+    def __init__(self, in_channels=64, aux_channels=80, kernel_size=9, dilation=2, bias=True, upsample_factor=2,
+                 upsample_mode="nearest", gated_function="softmax"):
+        super().__init__()
+        if gated_function not in ("softmax", "sigmoid"):
+            raise ValueError(f"{gated_function} is not supported.")
+        self.tade1 = TADELayer(in_channels, aux_channels, kernel_size, bias, 1, upsample_mode)
+        self.gated_conv1 = torch.nn.Conv1d(in_channels, in_channels * 2, kernel_size, 1, bias=bias, padding=(kernel_size - 1) // 2)
+        self.tade2 = TADELayer(in_channels, in_channels, kernel_size, bias, upsample_factor, upsample_mode)
+        self.gated_conv2 = torch.nn.Conv1d(in_channels, in_channels * 2, kernel_size, 1, bias=bias, dilation=dilation,
+                                           padding=(kernel_size - 1) // 2 * dilation)
+        self.upsample = torch.nn.Upsample(scale_factor=upsample_factor, mode=upsample_mode)
+        self.gated_function_name = gated_function
+        self.upsample_factor = int(upsample_factor)
+        self.pad = (kernel_size - 1) // 2
+        self.dilation = dilation
+
+    def forward(self, x, c):
+        """(B, C, T), (B, aux, T) -> (B, C, T * f), (B, C, T * f)."""
+        residual = x
+        x, c = self.tade1(x, c)
+        g1 = self.gated_conv1
+        x = ops.tade_gate(ops.conv1d(x, effective_weight(g1), g1.bias, padding=self.pad), None, 1, self.gated_function_name)
+        x, c = self.tade2(x, c)
+        g2 = self.gated_conv2
+        x = ops.conv1d(x, effective_weight(g2), g2.bias, dilation=self.dilation, padding=self.pad * self.dilation)
+        # gate + nearest-upsampled residual in one pass
+        return ops.tade_gate(x, residual, self.upsample_factor, self.gated_function_name), c

@@ -12,7 +12,7 @@ import torch
 from . import ops
 from .capi import PwgbError
 from .layers import HiFiGANResidualBlock as ResidualBlock
-from .layers import CausalConv1d, CausalConvTranspose1d, ResidualStack, activation_slope, effective_weight, pad_mode_of
+from .layers import CausalConv1d, CausalConvTranspose1d, ResidualStack, TADEResBlock, activation_slope, effective_weight, pad_mode_of
 
 
 def _read_stats(stats):
@@ -299,6 +299,113 @@ class MelGANGenerator(_GeneratorBase):
         if self.pqmf is not None:
             c = self.pqmf.synthesis(c)
         return c.squeeze(0).transpose(1, 0)
+
+
+class StyleMelGANGenerator(_GeneratorBase):
+    """models/style_melgan.py:22-270 -- inference only (forward / inference under ``torch.no_grad()``)."""
+
+    def __init__(
+        self,
+        in_channels=128,
+        aux_channels=80,
+        channels=64,
+        out_channels=1,
+        kernel_size=9,
+        dilation=2,
+        bias=True,
+        noise_upsample_scales=[11, 2, 2, 2],
+        noise_upsample_activation="LeakyReLU",
+        noise_upsample_activation_params={"negative_slope": 0.2},
+        upsample_scales=[2, 2, 2, 2, 2, 2, 2, 2, 1],
+        upsample_mode="nearest",
+        gated_function="softmax",
+        use_weight_norm=True,
+    ):
+        super().__init__()
+        self.in_channels = in_channels
+        self.noise_slope = activation_slope(noise_upsample_activation, noise_upsample_activation_params)
+        noise_upsample = []
+        in_chs = in_channels
+        for s in noise_upsample_scales:
+            noise_upsample += [torch.nn.ConvTranspose1d(in_chs, channels, s * 2, stride=s, padding=s // 2 + s % 2,
+                                                        output_padding=s % 2, bias=bias)]
+            noise_upsample += [getattr(torch.nn, noise_upsample_activation)(**noise_upsample_activation_params)]
+            in_chs = channels
+        self.noise_upsample = torch.nn.Sequential(*noise_upsample)
+        self.noise_upsample_factor = int(np.prod(noise_upsample_scales))
+        self.blocks = torch.nn.ModuleList()
+        aux_chs = aux_channels
+        for s in upsample_scales:
+            self.blocks += [TADEResBlock(in_channels=channels, aux_channels=aux_chs, kernel_size=kernel_size, dilation=dilation,
+                                         bias=bias, upsample_factor=s, upsample_mode=upsample_mode, gated_function=gated_function)]
+            aux_chs = channels
+        self.upsample_factor = int(np.prod(upsample_scales))
+        self.kernel_size = kernel_size
+        self.output_conv = torch.nn.Sequential(
+            torch.nn.Conv1d(channels, out_channels, kernel_size, 1, bias=bias, padding=(kernel_size - 1) // 2),
+            torch.nn.Tanh(),
+        )
+        if use_weight_norm:
+            self.apply_weight_norm()
+        self.reset_parameters()
+
+    def _noise_path(self, z):
+        """noise_upsample (style_melgan.py:76-98): every LeakyReLU but the last is fused into the next
+        transposed conv's loader; the last one is applied explicitly (the block needs it as the residual)."""
+        x, pre = z, 1.0
+        for m in self.noise_upsample:
+            if isinstance(m, torch.nn.ConvTranspose1d):
+                x = ops.conv_transpose1d(x, effective_weight(m), m.bias, stride=m.stride[0], padding=m.padding[0],
+                                         output_padding=m.output_padding[0], pre_slope=pre)
+                pre = self.noise_slope
+        return ops.leaky_relu(x, self.noise_slope, inplace=True)
+
+    def _check_inference_only(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise PwgbError("StyleMelGANGenerator is inference-only in this build (no backward kernels): use torch.no_grad()")
+
+    def forward(self, c, z=None):
+        """(B, aux_channels, T) [, (B, in_channels, T_z)] -> (B, out_channels, T * prod(upsample_scales))  (style_melgan.py:140-160)."""
+        self._check_inference_only()
+        if z is None:
+            z = torch.randn(c.size(0), self.in_channels, 1).to(device=c.device, dtype=c.dtype)
+        x = self._noise_path(z)
+        for block in self.blocks:
+            x, c = block(x, c)
+        oc = self.output_conv[0]
+        return ops.conv1d(x, effective_weight(oc), oc.bias, padding=(self.kernel_size - 1) // 2, post_act="tanh")
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+    def reset_parameters(self):
+        def _reset_parameters(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                m.weight.data.normal_(0.0, 0.02)
+
+        self.apply(_reset_parameters)
+
+    def inference(self, c, normalize_before=False, noise=None):
+        """(T, aux_channels) -> (T * prod(upsample_scales), out_channels)  (style_melgan.py:226-262); ``noise``
+        (1, in_channels, ceil(T / noise_upsample_factor)) may be passed for reproducibility."""
+        self._check_inference_only()
+        c = self._prep_inference_input(c, normalize_before)
+        n_frames = (c.size(2) - 1) // self.noise_upsample_factor + 1
+        if noise is None:
+            noise = torch.randn(1, self.in_channels, n_frames, dtype=torch.float).to(c.device)
+        x = self._noise_path(noise.contiguous())
+        total_length = c.size(2) * self.upsample_factor
+        if x.size(2) > c.size(2):  # replicate-pad the conditioning up to the noise length (data movement)
+            c = torch.cat([c, c[:, :, -1:].expand(-1, -1, x.size(2) - c.size(2))], dim=2).contiguous()
+        for block in self.blocks:
+            x, c = block(x, c)
+        oc = self.output_conv[0]
+        y = ops.conv1d(x, effective_weight(oc), oc.bias, padding=(self.kernel_size - 1) // 2, post_act="tanh")[..., :total_length]
+        return y.squeeze(0).transpose(1, 0)
 
 
 class ParallelWaveGANGenerator(_GeneratorBase):

@@ -39,7 +39,8 @@ def _mirror(kind, kwargs):
     from parallelwavegan_b200 import models
 
     cls = {"hifigan_generator": models.HiFiGANGenerator, "melgan_generator": models.MelGANGenerator,
-           "pwg_generator": getattr(models, "ParallelWaveGANGenerator", None)}[kind]
+           "pwg_generator": getattr(models, "ParallelWaveGANGenerator", None),
+           "style_melgan_generator": models.StyleMelGANGenerator}[kind]
     if cls is None:
         pytest.skip(f"{kind} not built yet")
     import json
@@ -47,7 +48,7 @@ def _mirror(kind, kwargs):
     return cls(**json.loads(json.dumps(kwargs)))
 
 
-@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd", "hifigan_causal", "mb_melgan_v2", "melgan_small", "melgan_causal", "pwg_v1", "pwg_small"])
+@pytest.mark.parametrize("name", ["hifigan_small", "hifigan_v1", "hifigan_odd", "hifigan_causal", "mb_melgan_v2", "melgan_small", "melgan_causal", "pwg_v1", "pwg_small", "style_melgan_v1", "style_melgan_small"])
 def test_state_dict_layout_matches_reference(name, built_lib):
     meta, _ = load_golden(name)
     m = _mirror(meta["kind"], meta["kwargs"])

@@ -37,6 +37,25 @@ def test_melgan_generator(name):
         assert rel_l2(yp[0].t(), g["y_inf"]) < ORACLE_TOL
 
 
+@pytest.mark.parametrize("name", ["style_melgan_v1", "style_melgan_small"])
+def test_style_melgan_generator(name):
+    meta, g = load_golden(name)
+    w = golden_effective_weights(meta)
+    kw = meta["kwargs"]
+    cfg = dict(kw, noise_upsample_negative_slope=kw["noise_upsample_activation_params"]["negative_slope"])
+    c = synth.randn(meta["c_shape"], meta["c_seed"])
+    z = synth.randn(meta["z_shape"], meta["z_seed"])
+    y = ref_ops.style_melgan_generator(w, c, z, cfg)
+    assert y.shape == g["y"].shape
+    # 9 instance-normalised blocks amplify fp32 reassociation differences (module vs functional ATen calls):
+    # 2.4e-5 end to end, 5e-7 per block
+    assert rel_l2(y, g["y"]) < 5 * ORACLE_TOL
+    # first TADE residual block in isolation (layers/tade_res_block.py:135-160)
+    x1, c1 = ref_ops.tade_res_block(w, "blocks.0", torch.from_numpy(g["x0"]) if not isinstance(g["x0"], torch.Tensor) else g["x0"], c,
+                                    kw["kernel_size"], kw["dilation"], kw["upsample_scales"][0], kw["gated_function"])
+    assert rel_l2(x1, g["x1"]) < ORACLE_TOL and rel_l2(c1, g["c1"]) < ORACLE_TOL
+
+
 @pytest.mark.parametrize("name", ["pwg_v1", "pwg_small"])
 def test_pwg_generator(name):
     meta, g = load_golden(name)
