@@ -1,6 +1,13 @@
 """StyleMelGAN generator on the libpwgb kernels vs the real-reference golden vectors and
-the travelling oracle.  Written after the round's GPU budget was spent: marked ``gpu_unverified`` (not selected
-by ``-m gpu``) until its first green run on a B200; run it with ``pytest -m gpu_unverified``."""
+the travelling oracle.
+
+Tolerances.  The bar is 1e-3 relative L2.  The 9-block instance-normalised, softmax-gated stack is ill-conditioned
+with the synthetic weights: on the CPU, in pure fp32, a 1e-6 relative perturbation of the conditioning moves the
+reference output by 9e-5 rel-L2 and 1.9e-3 of peak at the worst sample, and the oracle differs from the reference
+by 2.4e-5 / 5.3e-4 just through the order of fp32 sums.  Emulating the bf16x3 operand split of the tcgen05 convs on
+the CPU gives 2.5e-4 / 3.5e-3; the B200 measured 4.5e-4 / 9.1e-3 (profiles/gpu_tests_r1_stylemelgan_first_run.log).
+So the full-depth model is held to the 1e-3 rel-L2 bar and to 2e-2 of peak pointwise; single blocks and the small
+model are held to 1e-3 on both."""
 import json
 
 import pytest
@@ -10,7 +17,7 @@ import torch.nn.functional as F
 from helpers import golden_effective_weights, golden_weights, load_golden, max_abs_over_peak, rel_l2
 from oracle import ref_ops, synth
 
-pytestmark = pytest.mark.gpu_unverified
+pytestmark = pytest.mark.gpu
 REL_TOL = 1e-3  # north_star bar
 
 
@@ -72,7 +79,8 @@ def test_style_melgan_generator_vs_reference(dev, name):
     assert rel_l2(x0.cpu(), g["x0"]) < REL_TOL
     assert rel_l2(x1.cpu(), g["x1"]) < REL_TOL and rel_l2(c1.cpu(), g["c1"]) < REL_TOL
     assert tuple(y.shape) == tuple(g["y"].shape)
-    assert rel_l2(y.cpu(), g["y"]) < REL_TOL and max_abs_over_peak(y.cpu(), g["y"]) < REL_TOL
+    deep = len(meta["kwargs"]["upsample_scales"]) > 4
+    assert rel_l2(y.cpu(), g["y"]) < REL_TOL and max_abs_over_peak(y.cpu(), g["y"]) < (2e-2 if deep else REL_TOL)
     kw = meta["kwargs"]
     cfg = dict(kw, noise_upsample_negative_slope=kw["noise_upsample_activation_params"]["negative_slope"])
     ref = ref_ops.style_melgan_generator(golden_effective_weights(meta), c.cpu(), z.cpu(), cfg)
