@@ -39,7 +39,7 @@ WORKLOAD = "HiFi-GAN v1 generator inference (ljspeech hifigan.v1.yaml), 16x80x40
 def synth_weights(seed=1234):
     """Random-init weights of the HiFi-GAN v1 architecture (no checkpoints offline): synthetic
     state dict in the reference layout, folded (remove_weight_norm) like decode.py:147."""
-    from oracle import synth  # test infrastructure: only used to draw reproducible weights
+    from parallelwavegan_b200 import synth_weights as synth  # seeded random-init weights (no checkpoints offline)
     from parallelwavegan_b200 import models
 
     m = models.HiFiGANGenerator(**CFG)
@@ -175,8 +175,8 @@ def measure_train_step(dev, rank, local_rank, world, dist, steps=3, warmup=2):
     """Secondary metric (BASELINE.json "train steps/sec"): HiFi-GAN v1 G + MSD/MPD full train step
     (C5: per-GPU batch 16 x 8192 samples; mel + adversarial + feature-matching losses, Adam), forward and
     backward on libpwgb kernels, DDP gradient all-reduce over NCCL when world > 1."""
-    from oracle import synth
     from parallelwavegan_b200 import losses, models
+    from parallelwavegan_b200 import synth_weights as synth
     from parallelwavegan_b200.train_step import GanTrainStep
 
     g = models.HiFiGANGenerator(**CFG)
@@ -220,8 +220,8 @@ def measure_train_step(dev, rank, local_rank, world, dist, steps=3, warmup=2):
 def measure_pwg_train_step(dev, rank, local_rank, world, dist, steps=2, warmup=1, batch=64):
     """BASELINE.json configs[2]: Parallel WaveGAN v1 G + D train step (30-layer residual stack,
     MultiResolutionSTFTLoss + adversarial loss, RAdam), per-GPU batch 64 x 25600 samples, DDP when world > 1."""
-    from oracle import synth
     from parallelwavegan_b200 import losses, models
+    from parallelwavegan_b200 import synth_weights as synth
 
     g = models.ParallelWaveGANGenerator()
     g.load_state_dict(synth.synth_state_dict([(k, tuple(v.shape)) for k, v in g.state_dict().items()], 31, 1.0))
