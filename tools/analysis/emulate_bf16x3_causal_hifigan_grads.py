@@ -38,3 +38,28 @@ for name,ragged in (("v13 (input conv exact)",False),("v14 (input conv bf16x3)",
     errs={k:rel_l2(g1[k],g0[k]) for k in g0 if g0[k] is not None}
     worst=sorted(errs.items(), key=lambda kv:-kv[1])[:5]
     print(name, "fwd rel", rel_l2(y1,y0), "dc", rel_l2(c1,c0), "worst grads", [(k,round(v,5)) for k,v in worst])
+
+# conditioning-aware criterion for weight-norm pairs: |a - r| relative to ||dL/dw_eff||,
+# ||dL/dw||^2 = (dL/dg)^2 + (||v|| / g)^2 ||dL/dv||^2  (per output channel, summed)
+def wn_scale(gr, sd_, name_g):
+    name_v = name_g[:-2] + "_v"
+    v, gg = sd_[name_v], sd_[name_g]
+    dims = tuple(range(1, v.dim()))
+    vn = v.pow(2).sum(dim=dims, keepdim=True).sqrt()
+    dv = gr[name_v]
+    return float(((gr[name_g] ** 2).sum() + ((vn / gg) ** 2 * dv.pow(2)).sum()).sqrt())
+y1, g1, c1 = grads(make_conv(True))
+rows = []
+for k in g0:
+    if g0[k] is None or not (k.endswith("weight_g") or k.endswith("weight_v")):
+        continue
+    kg = k if k.endswith("_g") else k[:-2] + "_g"
+    sc = wn_scale(g0, sd, kg)
+    if k.endswith("_v"):
+        v, gg = sd[k], sd[kg]
+        sc = sc * float((gg / v.pow(2).sum(dim=tuple(range(1, v.dim())), keepdim=True).sqrt()).abs().max())
+    rows.append((float((g1[k] - g0[k]).norm()) / sc, rel_l2(g1[k], g0[k]), k))
+rows.sort(reverse=True)
+print("v14 emulation, error / ||dL/dw_eff|| (first column) vs plain rel-L2:")
+for r in rows[:6]:
+    print("  %.5f  %.5f  %s" % r)
