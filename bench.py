@@ -316,9 +316,11 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        # keep stdout to the ONE JSON line: NCCL writes its version banner / debug lines to stdout unless told
+        # otherwise, so whatever NCCL_DEBUG level the launcher chose goes to a per-process file instead
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pwgb_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     model, sd = synth_weights()
