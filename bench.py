@@ -320,7 +320,10 @@ def main():
         # otherwise, so whatever NCCL_DEBUG level the launcher chose goes to a per-process file instead
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pwgb_bench_nccl_%h_%p.log")
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            logdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpurun_out")
+            os.makedirs(logdir, exist_ok=True)
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(logdir, "bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     model, sd = synth_weights()
