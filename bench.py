@@ -98,6 +98,13 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def shared_config(world):
+    """`config` of BOTH arms (ours and --impl reference): the workload only, nothing implementation specific."""
+    return {"workload": WORKLOAD, "per_gpu_batch": BATCH, "frames": FRAMES, "mel_channels": 80, "hop": HOP, "fs": FS,
+            "weights": "random-init HiFi-GAN v1 (seeded synthetic state dict), weight norm folded",
+            "parallelism": f"utterance-sharded x{world}"}
+
+
 def cpu_reference_forward(weights, c):
     """The reference's CPU implementation of the path, restated (oracle port): same ATen CPU ops."""
     from oracle import ref_ops
@@ -125,16 +132,25 @@ def tune_cpu_threads(weights):
     return best, cores
 
 
+def cpu_decode_batch(weights, c):
+    """ONE protocol for every CPU leg: the batch is decoded utterance by utterance, exactly like the
+    reference's own decode loop (bin/decode.py:214-243 calls model.inference once per utterance)."""
+    n = 0
+    for i in range(c.shape[0]):
+        n += cpu_reference_forward(weights, c[i : i + 1]).numel()
+    return n
+
+
 def time_cpu(weights, batch, frames, reps):
     c = torch.randn(batch, 80, frames)
     cpu_reference_forward(weights, torch.randn(1, 80, 16))  # warm-up (thread pool, oneDNN primitives)
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
-        y = cpu_reference_forward(weights, c)
+        n = cpu_decode_batch(weights, c)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return y.numel() / best, best
+    return n / best, best
 
 
 def run_reference(args, rank, world):
@@ -147,24 +163,24 @@ def run_reference(args, rank, world):
     _, sd = synth_weights()
     w = fold_weight_norm(sd)
     cores, host_cores = tune_cpu_threads(w)
-    sb, sf = 2, FRAMES  # bounded sample: 2 of the 16 utterances per step
-    c = torch.randn(sb, 80, sf)
+    # the full workload every step: all 16 utterances of the 16x80x400 batch (decoded one by one like
+    # bin/decode.py does); warm-up steps run on short mels (they only warm the thread pool / oneDNN)
+    c = torch.randn(BATCH, 80, FRAMES, generator=torch.Generator().manual_seed(100))
     for _ in range(max(args.warmup, 1)):
-        cpu_reference_forward(w, c[:, :, :64])
+        cpu_reference_forward(w, c[:1, :, :64])
     t0 = time.perf_counter()
     n = 0
     for _ in range(args.steps):
-        y = cpu_reference_forward(w, c)
-        n += y.numel()
+        n += cpu_decode_batch(w, c)
     dt = time.perf_counter() - t0
     val = n / dt
-    sample = (f"{sb}x80x{sf} mels per step (1/8 of the 16x80x400 batch), {args.steps} steps, torch CPU fp32 (oracle port), "
-              f"{cores} threads (best of a probe over 8..{host_cores} on a {host_cores}-core host)")
+    sample = (f"the full {BATCH}x80x{FRAMES} batch every step, utterance by utterance (bin/decode.py:214-243), {args.steps} steps, "
+              f"torch CPU fp32 (oracle port), {cores} threads (best of a probe over 8..{host_cores} on a {host_cores}-core host)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": shared_config(world),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rtf": FS / val,
@@ -285,6 +301,115 @@ def measure_pwg_train_step(dev, rank, local_rank, world, dist, steps=2, warmup=1
             "losses": {"generator_loss": float(st[0]), "discriminator_loss": float(st[1])}}
 
 
+def measure_batch1(model, dev, flush, steps=20):
+    """north_star RTF target: HiFi-GAN v1 at batch 1 (1 x 80 x 400 mels = 4.64 s of audio), eager launches and
+    CUDA-graph replay (decode driver), L2 flushed between steps, device events."""
+    from parallelwavegan_b200 import decode
+
+    c1 = torch.randn(1, 80, FRAMES, generator=torch.Generator().manual_seed(7)).to(dev)
+    out = {"workload": f"1x80x{FRAMES} mels -> {FRAMES * HOP} samples ({FRAMES * HOP / FS:.2f} s of audio)"}
+    with torch.no_grad():
+        runner = decode.GraphedGenerator(model)
+        for name, fn in (("eager", model), ("cuda_graph", runner)):
+            for _ in range(3):
+                fn(c1)
+            torch.cuda.synchronize()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for e0, e1 in evs:
+                flush.zero_()
+                e0.record()
+                fn(c1)
+                e1.record()
+            torch.cuda.synchronize()
+            ms = statistics.median(e0.elapsed_time(e1) for e0, e1 in evs)
+            out[name] = {"ms": ms, "rtf": ms * 1e-3 / (FRAMES * HOP / FS), "x_realtime": (FRAMES * HOP / FS) / (ms * 1e-3)}
+    return out
+
+
+def _time_cuda(fn, steps, warmup, flush):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        flush.zero_()
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    return sum(e0.elapsed_time(e1) for e0, e1 in evs) / steps
+
+
+def measure_torch_eager_gpu(dev, sd, mel_dev, flush):
+    """The honest GPU comparison: the reference's algorithm as plain PyTorch eager ops
+    (cuDNN / cuBLAS / cuFFT; the oracle port run on CUDA tensors, weight norm folded) on the SAME B200, for the C2
+    forward (TF32 off = fp32 parity class, and on) and the C5 train step.  A baseline, measured in the same run."""
+    import torch.nn.functional as F
+
+    from oracle import ref_ops
+    from oracle.ref_ops import fold_spectral_norm_eval, fold_weight_norm
+    from parallelwavegan_b200 import models
+    from parallelwavegan_b200 import synth_weights as synth
+
+    out = {"what": "reference algorithm as PyTorch eager ops on this GPU (oracle port on CUDA tensors, folded weight norm)"}
+    w = {k: v.to(dev) for k, v in fold_weight_norm(sd).items()}
+    cfg = dict(CFG, negative_slope=0.1)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        with torch.no_grad():
+            for tag, tf32 in (("c2_fp32", False), ("c2_tf32", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                ms = _time_cuda(lambda: ref_ops.hifigan_generator(w, mel_dev, cfg), 5, 3, flush)
+                out[tag] = {"ms_per_step": ms, "samples_per_s": BATCH * FRAMES * HOP / (ms * 1e-3)}
+        # ---- C5 train step, eager autograd (train.py:200-335 restated on functional ops), fp32 (TF32 off) and TF32
+        d = models.HiFiGANMultiScaleMultiPeriodDiscriminator()
+        dsd = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in d.state_dict().items()], 4321, 1.4)
+        del d
+        gw = {k: v.to(dev).requires_grad_(True) for k, v in fold_weight_norm(sd).items()}
+        dw = {k: v.to(dev).requires_grad_(True) for k, v in fold_weight_norm(fold_spectral_norm_eval(dsd)).items()}
+        og = torch.optim.Adam(list(gw.values()), lr=2e-4, betas=(0.5, 0.9))
+        od = torch.optim.Adam(list(dw.values()), lr=2e-4, betas=(0.5, 0.9))
+        melmat = torch.from_numpy(ref_ops.slaney_mel_filterbank(22050, 1024, 80, 0, 11025)).t().contiguous().to(dev)
+        win = torch.hann_window(1024, device=dev)
+        gen = torch.Generator().manual_seed(1000)
+        c = torch.randn(16, 80, 32, generator=gen).to(dev)
+        y = (torch.rand(16, 1, 8192, generator=gen) - 0.5).to(dev)
+
+        def logmel(x):
+            sp = torch.stft(x.squeeze(1), 1024, 256, 1024, win, return_complex=True)
+            amp = torch.sqrt(torch.clamp(sp.real**2 + sp.imag**2, min=1e-10)).transpose(1, 2)
+            return torch.log(torch.clamp(torch.matmul(amp, melmat), min=1e-10))
+
+        def step():
+            y_ = ref_ops.hifigan_generator(gw, c, cfg)
+            loss = 45.0 * F.l1_loss(logmel(y_), logmel(y))
+            p_ = ref_ops.hifigan_msmpd(dw, y_)
+            with torch.no_grad():
+                p = ref_ops.hifigan_msmpd(dw, y)
+            loss = loss + ref_ops.generator_adv_loss(p_) + 2.0 * ref_ops.feature_match_loss(p_, p)
+            og.zero_grad(set_to_none=True)
+            od.zero_grad(set_to_none=True)
+            loss.backward()
+            og.step()
+            with torch.no_grad():
+                y_ = ref_ops.hifigan_generator(gw, c, cfg)
+            real, fake = ref_ops.discriminator_adv_loss(ref_ops.hifigan_msmpd(dw, y_), ref_ops.hifigan_msmpd(dw, y))
+            od.zero_grad(set_to_none=True)
+            (real + fake).backward()
+            od.step()
+
+        for tag, tf32 in (("c5_step_fp32", False), ("c5_step_tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            ms = _time_cuda(step, 3, 2, flush)
+            out[tag] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,6 +418,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step measurement")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-GPU side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -385,17 +511,42 @@ def main():
         prof = ops.PROFILE
         ops.PROFILE = None
 
+    # ---- self-check of the timed output: utterance 0 of the last timed step vs the CPU oracle (rank 0)
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.ref_ops import fold_weight_norm as _fold
+
+        ref0 = cpu_reference_forward(_fold(sd), mel_host[:1].clone())
+        y0 = y[:1].float().cpu()
+        rel = float((y0.double() - ref0.double()).norm() / ref0.double().norm())
+        mx = float((y0.double() - ref0.double()).abs().max() / ref0.double().abs().max())
+        parity = {"utterance": 0, "rel_l2_vs_oracle": rel, "max_abs_over_peak": mx, "tolerance": 1e-3}
+        assert rel <= 1e-3, f"bench output does not match the oracle: rel-L2 {rel:.3e}"
+
+    batch1 = eager_gpu = None
+    try:
+        batch1 = measure_batch1(model, dev, flush)
+    except Exception as e:
+        batch1 = {"error": repr(e)[:300]}
+    if rank == 0 and not args.no_eager:
+        try:
+            eager_gpu = measure_torch_eager_gpu(dev, sd, mel_dev, flush)
+        except Exception as e:
+            eager_gpu = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    if dist is not None:
+        dist.barrier()
+
     train = train_pwg = None
     if not args.no_train:
         try:
             train = measure_train_step(dev, rank, local_rank, world, dist)
         except Exception as e:  # the headline line must survive a failure of the secondary measurement
             train = {"error": repr(e)[:300]}
-        if world == 1:  # the C3 step is reported single-GPU only (DDP run of it: tools/train_bench_pwg.py)
-            try:
-                train_pwg = measure_pwg_train_step(dev, rank, local_rank, world, dist)
-            except Exception as e:
-                train_pwg = {"error": repr(e)[:300]}
+        try:  # BASELINE.json configs[2]: per-GPU batch 64, DDP when world > 1
+            train_pwg = measure_pwg_train_step(dev, rank, local_rank, world, dist)
+        except Exception as e:
+            train_pwg = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
 
     from parallelwavegan_b200 import sharding
@@ -443,14 +594,19 @@ def main():
             sb = 4
             v, dt = time_cpu(wf, sb, FRAMES, 2)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{sb}x80x{FRAMES} mels (1/4 of the batch), best of 2, {dt:.2f} s, oracle port (torch CPU fp32 ATen ops), "
+                   "sample": f"{sb} of the {BATCH} utterances (80x{FRAMES} mels each), decoded utterance by utterance like the --impl reference arm "
+                             f"(bin/decode.py:214-243), best of 2, {dt:.2f} s, oracle port (torch CPU fp32 ATen ops), "
                              f"{cores} threads = best of a probe over 8..{host_cores} on a {host_cores}-core host"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "precision": "fp32 I/O and accumulation; wide convs on tcgen05 with a bf16x3 operand split (measured 5e-6 rel per conv, 1e-5 end to end vs the fp32 oracle)", "per_gpu_batch": BATCH, "frames": FRAMES, "l2": "flushed between timed steps (256 MiB write); activations (>=210 MB per stage tensor) exceed L2 anyway",
-                       "parallelism": f"utterance-sharded x{world}"},
+            "config": shared_config(world),
+            "precision": "fp32 I/O and accumulation; wide convs on tcgen05 with a bf16x3 operand split (parity measured below)",
+            "l2": "flushed between timed steps (256 MiB write); activations (>=210 MB per stage tensor) exceed L2 anyway",
+            "parity": parity,
+            "batch1": batch1,
+            "torch_eager_gpu": eager_gpu,
             "rtf": FS / (value / world) , "x_realtime_per_gpu": (value / world) / FS,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mel_host.numel() * 4 * world,
                     "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": ms_e2e_total / args.steps},

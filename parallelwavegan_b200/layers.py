@@ -328,14 +328,13 @@ class WaveNetResidualBlock(torch.nn.Module):
         """x: (B, R, T); c: (B, aux[_padded], T) or None; skips: (B, S, T) accumulated in place.
         Returns (x_out, skips) -- with ``skips=None`` a fresh zero tensor is used so that the pair
         equals the reference's ``(x, s)`` (layers/residual_block.py:140)."""
-        if skips is None:
-            skips = torch.zeros((x.shape[0], self.conv1x1_skip.out_channels, x.shape[2]), device=x.device, dtype=x.dtype)
         aux = self.conv1x1_aux
         if torch.is_grad_enabled() and (x.requires_grad or next(self.parameters()).requires_grad):
-            xo, s = self._forward_train(x, c)
             if skips is not None:
                 raise PwgbError("in-place skip accumulation is inference-only; use the returned skip tensor under autograd")
-            return xo, s
+            return self._forward_train(x, c)  # (x_out, s): the reference's pair, differentiable
+        if skips is None:
+            skips = torch.zeros((x.shape[0], self.conv1x1_skip.out_channels, x.shape[2]), device=x.device, dtype=x.dtype)
         x_out = ops.wavenet_layer(
             x, c,
             effective_weight(self.conv), self.conv.bias,
@@ -343,6 +342,7 @@ class WaveNetResidualBlock(torch.nn.Module):
             effective_weight(self.conv1x1_skip), self.conv1x1_skip.bias,
             effective_weight(self.conv1x1_out), self.conv1x1_out.bias,
             self.dilation, skips, self.aux_channels, cache=self._cache,
+            key=ops.param_key(self.conv, aux, self.conv1x1_skip, self.conv1x1_out),
         )
         return x_out, skips
 

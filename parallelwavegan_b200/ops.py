@@ -228,7 +228,36 @@ class WaveNetLayerWeights:
     __slots__ = ("desc", "packed", "b_conv", "b_skip_out", "key")
 
 
-def wavenet_layer(x, c, w_conv, b_conv, w_aux, w_skip, b_skip, w_out, b_out, dilation, skips, aux_real, cache=None):
+def param_key(*mods):
+    """Cache key for data derived from module parameters: identity and version counter of every LEAF
+    parameter / buffer (weight_g, weight_v, weight, bias ...).  Effective weights are temporaries under
+    weight norm (fresh tensor, version 0, recycled address), so they must never be the key.  In-place
+    updates through ``.data`` do not bump the version counter: call ``invalidate_caches(module)`` after
+    such surgery."""
+    key = []
+    for m in mods:
+        if m is None:
+            continue
+        for t in list(m.parameters(recurse=False)) + list(m.buffers(recurse=False)):
+            key.append((id(t), t._version, t.data_ptr()))
+    return tuple(key)
+
+
+def invalidate_caches(module):
+    """Drop every packed-operand cache below ``module`` (after weight surgery through ``.data``)."""
+    for m in module.modules():
+        c = getattr(m, "_cache", None)
+        if isinstance(c, dict):
+            c.clear()
+        for t in list(m.parameters(recurse=False)):
+            if hasattr(t, "_pwgb_packed"):
+                try:
+                    del t._pwgb_packed
+                except Exception:
+                    pass
+
+
+def wavenet_layer(x, c, w_conv, b_conv, w_aux, w_skip, b_skip, w_out, b_out, dilation, skips, aux_real, cache=None, key=None):
     """WaveNetResidualBlock.forward (layers/residual_block.py:102-140), in place on ``skips``:
     returns x_out.  ``c``: (B, aux_pad, T) conditioning, zero-padded to a multiple of 32 channels
     (or None).  Uses the fused tcgen05 layer when pwgb_wavenet_supported(), otherwise composes the
@@ -242,8 +271,9 @@ def wavenet_layer(x, c, w_conv, b_conv, w_aux, w_skip, b_skip, w_out, b_out, dil
     d = capi.WaveNetDesc(batch=B, t=T, residual_channels=R, gate_channels=G, skip_channels=S, aux_channels=aux_pad,
                          kernel=K, dilation=int(dilation))
     if ENGINE != "simt" and L.pwgb_wavenet_supported(C.byref(d)):
-        key = tuple((t.data_ptr(), t._version) for t in (w_conv, w_aux, w_skip, w_out) if t is not None)
-        ent = cache.get("wn") if cache is not None else None
+        # ``key`` identifies the leaf parameters the effective weights were derived from (param_key); without
+        # it nothing is cached (effective weights are temporaries whose address / version say nothing)
+        ent = cache.get("wn") if (cache is not None and key is not None) else None
         if ent is None or ent[0] != key:
             nbytes = L.pwgb_wavenet_packed_bytes(C.byref(d))
             packed = torch.empty(nbytes // 4, device=x.device, dtype=torch.int32)
@@ -254,7 +284,7 @@ def wavenet_layer(x, c, w_conv, b_conv, w_aux, w_skip, b_skip, w_out, b_out, dil
             if b_skip is not None:
                 bso = torch.cat([b_skip.detach().reshape(-1), b_out.detach().reshape(-1)]).contiguous()
             ent = (key, packed, bso)
-            if cache is not None:
+            if cache is not None and key is not None:
                 cache["wn"] = ent
         _, packed, bso = ent
         g_ws = torch.empty((B, G, T), device=x.device, dtype=torch.float32)
