@@ -155,6 +155,43 @@ PWGB_API int pwgb_wavenet_layer_forward(const pwgb_wavenet_desc* d, const float*
                                void* stream);
 
 /* ------------------------------------------------------------------------
+ * Packed WaveNet residual stack: the fused ONE-kernel form of WaveNetResidualBlock.forward
+ * (layers/residual_block.py:102-140) used by ParallelWaveGANGenerator.forward's layer loop
+ * (models/parallel_wavegan.py:161-166).  Between layers the residual stream x and the conditioning c
+ * stay in the tensor core's operand layout, split bf16 hi/lo (same bytes per sample as fp32):
+ *   xpk [batch][hi|lo][residual_channels/8][t_pad][8] bf16, t_pad = 2*halo + round_up(t,128); rows
+ *       [halo, halo+t) hold the samples; every other row MUST be zero (allocate zero-filled once; the
+ *       kernels only ever write rows [halo, halo+t));
+ *   cpk [batch][hi|lo][ceil(aux_channels/8)][round_up(t,128)][8] bf16 (written completely by pack_c).
+ * halo >= (kernel-1)/2 * (largest dilation of the stack).  Weights: the image written by
+ * pwgb_wavenet_pack() for the same channel counts with the aux weight padded to a multiple of 32
+ * channels (desc.aux_channels there = round_up(aux_channels, 32)).  b_skip_out = concat(b_skip, b_out).
+ * layer_forward:  skips (fp32, (batch, skip_channels, t)) = [skips_init ? 0 : skips] + s;
+ * xpk_out = packed x' or NULL when the residual output is not needed (last layer of a stack).
+ * pwgb_wnstack_supported() == 0: use pwgb_wavenet_layer_forward / the generic composition instead.
+ * ---------------------------------------------------------------------- */
+typedef struct pwgb_wnstack_desc {
+  int32_t batch, t;
+  int32_t residual_channels, gate_channels, skip_channels;
+  int32_t aux_channels; /* real conditioning channels (multiple of 16) */
+  int32_t kernel, halo;
+} pwgb_wnstack_desc;
+PWGB_API int pwgb_wnstack_supported(const pwgb_wnstack_desc* d);
+PWGB_API size_t pwgb_wnstack_x_bytes(const pwgb_wnstack_desc* d);
+PWGB_API size_t pwgb_wnstack_c_bytes(const pwgb_wnstack_desc* d);
+PWGB_API int pwgb_wnstack_pack_x(const pwgb_wnstack_desc* d, const float* x, void* xpk, void* stream);
+PWGB_API int pwgb_wnstack_unpack_x(const pwgb_wnstack_desc* d, const void* xpk, float* x, void* stream);
+/* c: (batch, >= aux_channels stored channels, t) fp32 with batch stride c_batch_stride floats */
+PWGB_API int pwgb_wnstack_pack_c(const pwgb_wnstack_desc* d, const float* c, long long c_batch_stride, void* cpk, void* stream);
+/* first_conv (Conv1d1x1 in_channels -> residual_channels, parallel_wavegan.py:155): z (batch, in_channels, t),
+ * w (residual_channels, in_channels) -> packed residual stream */
+PWGB_API int pwgb_wnstack_first_conv(const pwgb_wnstack_desc* d, const float* z, int in_channels, const float* w, const float* bias,
+                            void* xpk, void* stream);
+PWGB_API int pwgb_wnstack_layer_forward(const pwgb_wnstack_desc* d, int dilation, const void* xpk_in, const void* cpk,
+                               const void* packed_w, const float* b_conv, const float* b_skip_out, void* xpk_out,
+                               float* skips, int skips_init, void* stream);
+
+/* ------------------------------------------------------------------------
  * One stage of the PWG conditioning upsampler (layers/upsample.py:112-128): nearest repeat
  * x`scale` along time followed by the (2*scale+1)-tap FIR shared by all rows, zero padded:
  *   y[r, o] = sum_k f[k] * x[r, (o + k - scale) / scale]   for 0 <= o + k - scale < t_in*scale.

@@ -40,6 +40,13 @@ class WaveNetDesc(C.Structure):
     ]
 
 
+class WnStackDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("t", C.c_int32), ("residual_channels", C.c_int32), ("gate_channels", C.c_int32),
+        ("skip_channels", C.c_int32), ("aux_channels", C.c_int32), ("kernel", C.c_int32), ("halo", C.c_int32),
+    ]
+
+
 class StftDesc(C.Structure):
     _fields_ = [("batch", C.c_int32), ("t", C.c_int32), ("n_fft", C.c_int32), ("hop", C.c_int32),
                 ("win_length", C.c_int32), ("clamp_eps", C.c_float)]
@@ -91,6 +98,21 @@ def lib():
     L.pwgb_wavenet_pack.argtypes = [C.POINTER(WaveNetDesc), vp, vp, C.c_int, vp, vp, vp, vp]
     L.pwgb_wavenet_layer_forward.restype = C.c_int
     L.pwgb_wavenet_layer_forward.argtypes = [C.POINTER(WaveNetDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.pwgb_wnstack_supported.restype = C.c_int
+    L.pwgb_wnstack_supported.argtypes = [C.POINTER(WnStackDesc)]
+    for fn in (L.pwgb_wnstack_x_bytes, L.pwgb_wnstack_c_bytes):
+        fn.restype = C.c_size_t
+        fn.argtypes = [C.POINTER(WnStackDesc)]
+    L.pwgb_wnstack_pack_x.restype = C.c_int
+    L.pwgb_wnstack_pack_x.argtypes = [C.POINTER(WnStackDesc), vp, vp, vp]
+    L.pwgb_wnstack_unpack_x.restype = C.c_int
+    L.pwgb_wnstack_unpack_x.argtypes = [C.POINTER(WnStackDesc), vp, vp, vp]
+    L.pwgb_wnstack_pack_c.restype = C.c_int
+    L.pwgb_wnstack_pack_c.argtypes = [C.POINTER(WnStackDesc), vp, C.c_longlong, vp, vp]
+    L.pwgb_wnstack_first_conv.restype = C.c_int
+    L.pwgb_wnstack_first_conv.argtypes = [C.POINTER(WnStackDesc), vp, C.c_int, vp, vp, vp, vp]
+    L.pwgb_wnstack_layer_forward.restype = C.c_int
+    L.pwgb_wnstack_layer_forward.argtypes = [C.POINTER(WnStackDesc), C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
     L.pwgb_upsample_fir_forward.restype = C.c_int
     L.pwgb_upsample_fir_forward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_longlong, vp]
     L.pwgb_mr_stft_loss_workspace.restype = C.c_size_t
@@ -177,6 +199,8 @@ EXPORTED_SYMBOLS = [
     "pwgb_conv1d_tc_supported",
     "pwgb_conv1d_tc_forward", "pwgb_debug_set", "pwgb_wavenet_supported", "pwgb_wavenet_packed_bytes",
     "pwgb_wavenet_pack", "pwgb_wavenet_layer_forward", "pwgb_upsample_fir_forward",
+    "pwgb_wnstack_supported", "pwgb_wnstack_x_bytes", "pwgb_wnstack_c_bytes", "pwgb_wnstack_pack_x", "pwgb_wnstack_unpack_x",
+    "pwgb_wnstack_pack_c", "pwgb_wnstack_first_conv", "pwgb_wnstack_layer_forward",
     "pwgb_mr_stft_loss_workspace", "pwgb_mr_stft_loss_forward", "pwgb_stft_amplitude_forward",
     "pwgb_mel_project_forward", "pwgb_reduce_mean_forward", "pwgb_avg_pool1d_forward",
     "pwgb_conv1d_wgrad_workspace", "pwgb_conv1d_wgrad", "pwgb_conv1d_wgrad_tc_supported",

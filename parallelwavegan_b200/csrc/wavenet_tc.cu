@@ -1,0 +1,588 @@
+// Fused WaveNet residual layer (layers/residual_block.py:102-140) for the Parallel WaveGAN residual
+// stack (models/parallel_wavegan.py:161-166): ONE tcgen05 kernel per layer, fed by TMA only.
+//
+//   g  = conv_{k, dil}(x) + W_aux c + b          G columns of one TMEM accumulator set
+//   z  = tanh(g[:H]) * sigmoid(g[H:])            gate warps: TMEM -> registers -> bf16 hi/lo operand image in smem
+//   so = [W_skip ; W_out] z                      second contraction into the SAME TMEM columns (G is dead by then)
+//   skips (+)= so[:S] + b_skip ;  x' = (so[S:] + b_out + x) * sqrt(1/2)
+//
+// Algorithmic HBM bytes per sample and layer: x 4R + c 4A + x' 4R + skips 8S = 1344 B for PWG v1
+//  -- the gate tensor never leaves the SM.
+//
+// Data layout: between layers the residual stream and the conditioning live in HBM in the tensor core's
+// operand layout, split bf16 hi/lo (the same bytes per sample as fp32):
+//   xpk [batch][hi|lo][R/8][t_pad][8 ch] bf16,  t_pad = 2*halo + round_up(t, 128); rows [halo, halo + t) hold
+//       the samples, every other row is zero (the conv's zero padding and the tail of the last tile);
+//   cpk [batch][hi|lo][ceil(A/8)][round_up(t, 128)][8 ch] bf16.
+// A (32 channel, 128 row) operand window of any tap / dilation is then 8 contiguous 2 KB blocks: the
+// activation side of a pipeline stage is 8 cp.async.bulk copies, the weight side one 16 KB copy, and no
+// thread ever converts or re-lays-out an input (the conversion happens once, in the epilogue that
+// produces the value).  x = hi + lo carries 16 mantissa bits -- exactly what the bf16x3 MMA consumes;
+// the residual add sees the same value.
+//
+// Warp roles (576 threads, one persistent CTA per SM, mbarriers only):
+//   warp 0      TMA: per stage 8 activation blocks + 1 weight block into a ring of 32 KB slots
+//   warp 1      MMA issuer (elected lane): conv(i) into set i%4, then the skip/out contraction of tile i-1
+//   warps 2-9   gate:     G (TMEM) -> z operand image (smem)
+//   warps 10-17 epilogue: SO (TMEM) -> skips (fp32, read-modify-write) and x' (packed)
+// TMEM: 4 accumulator sets of max(G, S+R) <= 128 columns; the tile sequence conv(i+1) | SO(i) keeps the
+// tensor pipe busy while gate(i) runs.
+#include "tc_common.cuh"
+
+namespace pwgb {
+
+constexpr int WN_TT = 128;                 // rows (samples) per tile
+constexpr int WN_NGATE = 256, WN_NEPI = 256;
+constexpr int WN_W_TMA = 0, WN_W_MMA = 1, WN_W_GATE0 = 2, WN_W_EPI0 = WN_W_GATE0 + WN_NGATE / 32;
+constexpr int WN_THREADS = (WN_W_EPI0 + WN_NEPI / 32) * 32;
+constexpr int WN_MAX_SLOTS = 8;
+constexpr int WN_BLK = WN_TT * 16;         // one (8 channel, 128 row) operand block: 2 KB
+
+struct WnK {
+  int B, T, R, G, S, A, K, D, halo;
+  int H;                 // gate output channels = G / 2
+  int Tp, Tc;            // rows per plane of xpk / cpk
+  int ngx, ngc;          // 8-channel groups of x / c
+  int nxc, ncc, nsc;     // 32-channel chunks of x, c and z
+  int N2;                // S + R
+  int tiles_per_seq, total_tiles;
+  int nslot, a_bytes, b_bytes, slot_bytes, z_bytes;
+  int nset, set_cols, tmem_cols;
+  int write_x, skip_init;
+  unsigned idesc1, idesc2;
+};
+
+__device__ __forceinline__ float ex2_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// tanh(a) * sigmoid(b) = (Ea - 1) / ((Ea + 1)(1 + Eb)), Ea = e^{2a}, Eb = e^{-b}: two ex2 and one rcp.
+// Absolute error ~3e-7 (ex2.approx: 2^-22 relative); |a| is clamped where tanh is 1 to fp32 precision.
+__device__ __forceinline__ float gate_fast(float a, float b) {
+  a = fminf(fmaxf(a, -15.f), 15.f);
+  b = fmaxf(b, -80.f);
+  const float ea = ex2_approx(a * 2.8853900817779268f);
+  const float eb = ex2_approx(b * -1.4426950408889634f);
+  return __fdividef(ea - 1.f, (ea + 1.f) * (1.f + eb));
+}
+
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
+  const unsigned u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(u[i] << 16);
+    f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
+  }
+}
+
+__global__ void __launch_bounds__(WN_THREADS, 1)
+    wavenet_fused_kernel(const WnK p, const uint4* __restrict__ xin, const uint4* __restrict__ cpk,
+                         const unsigned char* __restrict__ wpk, const float* __restrict__ b_conv,
+                         const float* __restrict__ b_so, uint4* __restrict__ xout, float* __restrict__ skips) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: ring[nslot] (A 16 KB | B) | z image | barriers | tmem slot | bias (G + N2 floats)
+  unsigned char* ring = smem;
+  unsigned char* z_buf = smem + (size_t)p.nslot * p.slot_bytes;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(z_buf + p.z_bytes);
+  constexpr int NBAR = 2 * WN_MAX_SLOTS + 4 * 3 + 2;
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + NBAR);
+  float* bias1 = reinterpret_cast<float*>(tmem_slot + 4);
+  float* bias2 = bias1 + p.G;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned bar0 = smem_u32(bars);
+  auto FULL = [&](int i) { return bar0 + 8u * i; };
+  auto EMPTY = [&](int i) { return bar0 + 8u * (WN_MAX_SLOTS + i); };
+  auto G_FULL = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + i); };
+  auto SO_FULL = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + 4 + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + 8 + i); };
+  const unsigned Z_FULL = bar0 + 8u * (2 * WN_MAX_SLOTS + 12), Z_EMPTY = Z_FULL + 8u;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nslot; ++i) {
+      mbar_init(FULL(i), 1);
+      mbar_init(EMPTY(i), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(G_FULL(i), 1);
+      mbar_init(SO_FULL(i), 1);
+      mbar_init(ACC_EMPTY(i), WN_NEPI);
+    }
+    mbar_init(Z_FULL, WN_NGATE);
+    mbar_init(Z_EMPTY, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WN_W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((unsigned)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < p.G; i += WN_THREADS) bias1[i] = b_conv ? __ldg(b_conv + i) : 0.f;
+  for (int i = tid; i < p.N2; i += WN_THREADS) bias2[i] = b_so ? __ldg(b_so + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+
+  const int ntl = ((int)p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  const int conv_stages = p.nxc * p.K + p.ncc;
+
+  if (warp == WN_W_TMA) {
+    // ===================== TMA: activation windows + weight stages =====================
+    int s = 0, ph = 0;
+    const unsigned char* w_aux = wpk + (size_t)p.nxc * p.K * p.b_bytes;
+    const unsigned char* w_so = w_aux + (size_t)p.ncc * p.b_bytes;
+    const int cgl = p.ngc - (p.ncc - 1) * 4;  // 8-channel groups of the last conditioning chunk
+    auto stage_so = [&](int sc) {
+      mbar_wait(EMPTY(s), ph ^ 1);
+      if (lane == 0) {
+        mbar_expect_tx(FULL(s), (unsigned)p.b_bytes);
+        bulk_g2s(smem_u32(ring + (size_t)s * p.slot_bytes + p.a_bytes), w_so + (size_t)sc * p.b_bytes, (unsigned)p.b_bytes, FULL(s));
+      }
+      __syncwarp();
+      if (++s == p.nslot) { s = 0; ph ^= 1; }
+    };
+    for (int n = 0; n < ntl; ++n) {
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / p.tiles_per_seq;
+      const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
+      for (int j = 0; j < conv_stages; ++j) {
+        const bool is_x = j < p.nxc * p.K;
+        const int chunk = is_x ? j / p.K : j - p.nxc * p.K;
+        const int tap = is_x ? j - chunk * p.K : 0;
+        const int ng = is_x ? 4 : (chunk == p.ncc - 1 ? cgl : 4);
+        mbar_wait(EMPTY(s), ph ^ 1);
+        const unsigned dstA = smem_u32(ring + (size_t)s * p.slot_bytes);
+        if (lane == 0) mbar_expect_tx(FULL(s), (unsigned)(2 * ng * WN_BLK + p.b_bytes));
+        __syncwarp();
+        if (lane < 2 * ng) {
+          const int hl = lane / ng, gi = lane - hl * ng;
+          const uint4* src;
+          if (is_x) {
+            const long long row = (long long)p.halo + t0 + (long long)(tap - p.K / 2) * p.D;
+            src = xin + ((long long)(b * 2 + hl) * p.ngx + chunk * 4 + gi) * p.Tp + row;
+          } else {
+            src = cpk + ((long long)(b * 2 + hl) * p.ngc + chunk * 4 + gi) * p.Tc + t0;
+          }
+          bulk_g2s(dstA + (unsigned)((hl * 4 + gi) * WN_BLK), src, WN_BLK, FULL(s));
+        } else if (lane == 31) {
+          const unsigned char* wsrc = is_x ? wpk + (size_t)j * p.b_bytes : w_aux + (size_t)chunk * p.b_bytes;
+          bulk_g2s(dstA + (unsigned)p.a_bytes, wsrc, (unsigned)p.b_bytes, FULL(s));
+        }
+        __syncwarp();
+        if (++s == p.nslot) { s = 0; ph ^= 1; }
+      }
+      if (n > 0)
+        for (int sc = 0; sc < p.nsc; ++sc) stage_so(sc);
+    }
+    if (ntl > 0)
+      for (int sc = 0; sc < p.nsc; ++sc) stage_so(sc);
+  } else if (warp == WN_W_MMA) {
+    // ===================== MMA issuer (converged warp, elected lane) =====================
+    const unsigned long long hi_const = ((unsigned long long)((128u >> 4) | (1u << 14))) << 32;  // SBO = 128 B, version 1
+    const unsigned a_lo = ((unsigned)(WN_BLK >> 4)) << 16;           // LBO of an activation window: next 8-channel block
+    const unsigned a_sub = (unsigned)(4 * WN_BLK) >> 4;              // hi -> lo image
+    const unsigned a_step = (unsigned)(2 * WN_BLK) >> 4;             // second 16-channel K-step
+    const unsigned z_sub = (unsigned)(p.H / 8 * WN_BLK) >> 4;
+    const unsigned b1_lo = (((unsigned)p.G) & 0x3FFFu) << 16, b2_lo = (((unsigned)p.N2) & 0x3FFFu) << 16;
+    const unsigned b1_sub = 4u * p.G, b2_sub = 4u * p.N2, b1_step = 2u * p.G, b2_step = 2u * p.N2;
+    const unsigned z16 = smem_u32(z_buf) >> 4;
+    const int cgl = p.ngc - (p.ncc - 1) * 4;
+    int s = 0, ph = 0;
+    auto so_tile = [&](int m) {  // skip / out contraction of local tile m into its (now dead) G columns
+      const unsigned d = tmem_base + (unsigned)((m % p.nset) * p.set_cols);
+      mbar_wait_spin(Z_FULL, m & 1);
+      tc_fence_after();
+      for (int sc = 0; sc < p.nsc; ++sc) {
+        mbar_wait_spin(FULL(s), ph);
+        tc_fence_after();
+        const unsigned b16 = smem_u32(ring + (size_t)s * p.slot_bytes + p.a_bytes) >> 4;
+        const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + z16 + (unsigned)(sc * 4 * WN_BLK >> 4));
+        const unsigned long long b_hi = hi_const | (unsigned long long)(b2_lo + b16);
+        tc_mma_tap6(d, a_hi, b_hi, z_sub, b2_sub, a_step, b2_step, p.idesc2, sc != 0 ? 1u : 0u);
+        tc_commit(EMPTY(s));
+        if (++s == p.nslot) { s = 0; ph ^= 1; }
+      }
+      tc_commit(Z_EMPTY);
+      tc_commit(SO_FULL(m % p.nset));
+    };
+    for (int n = 0; n < ntl; ++n) {
+      const int set = n % p.nset;
+      mbar_wait_spin(ACC_EMPTY(set), ((n / p.nset) & 1) ^ 1);
+      tc_fence_after();
+      const unsigned d = tmem_base + (unsigned)(set * p.set_cols);
+      for (int j = 0; j < conv_stages; ++j) {
+        mbar_wait_spin(FULL(s), ph);
+        tc_fence_after();
+        const unsigned a16 = smem_u32(ring + (size_t)s * p.slot_bytes) >> 4;
+        const unsigned b16 = a16 + ((unsigned)p.a_bytes >> 4);
+        const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + a16);
+        const unsigned long long b_hi = hi_const | (unsigned long long)(b1_lo + b16);
+        const bool half = j >= p.nxc * p.K && (j - p.nxc * p.K) == p.ncc - 1 && cgl <= 2;  // one K-step only
+        if (half)
+          tc_mma_x3_single(d, a_hi, b_hi, a_sub, b1_sub, p.idesc1, j != 0 ? 1u : 0u);
+        else
+          tc_mma_tap6(d, a_hi, b_hi, a_sub, b1_sub, a_step, b1_step, p.idesc1, j != 0 ? 1u : 0u);
+        tc_commit(EMPTY(s));
+        if (++s == p.nslot) { s = 0; ph ^= 1; }
+      }
+      tc_commit(G_FULL(set));
+      if (n > 0) so_tile(n - 1);
+    }
+    if (ntl > 0) so_tile(ntl - 1);
+  } else if (warp < WN_W_EPI0) {
+    // ===================== gate: G (TMEM) -> z operand image (smem) =====================
+    const int gw = warp - WN_W_GATE0;
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;         // row of the tile
+    // the 8 warps split the H gate channels into two halves (by 16-channel groups)
+    const int ngrp = p.H / 16;
+    const int g_begin = (gw >> 2) ? ngrp / 2 : 0, g_end = (gw >> 2) ? ngrp : ngrp / 2;
+    for (int n = 0; n < ntl; ++n) {
+      const int set = n % p.nset;
+      mbar_wait(G_FULL(set), (n / p.nset) & 1);
+      tc_fence_after();
+      const unsigned tacc = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(set * p.set_cols);
+      bool z_free = false;
+      for (int g16 = g_begin; g16 < g_end; ++g16) {
+        unsigned ra[16], rb[16];
+        tc_ld16(tacc + (unsigned)(g16 * 16), ra);
+        tc_ld16(tacc + (unsigned)(p.H + g16 * 16), rb);
+        tc_wait_ld();
+        float zv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          zv[j] = gate_fast(__uint_as_float(ra[j]) + bias1[g16 * 16 + j], __uint_as_float(rb[j]) + bias1[p.H + g16 * 16 + j]);
+        if (!z_free) {  // the previous tile's skip/out MMAs must have retired before z is overwritten
+          mbar_wait(Z_EMPTY, (n & 1) ^ 1);
+          z_free = true;
+        }
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          float u[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = zv[h8 * 8 + j];
+          uint4 hi, lo;
+          split8(u, hi, lo);
+          const int grp = g16 * 2 + h8;
+          *reinterpret_cast<uint4*>(z_buf + ((size_t)grp * WN_TT + m) * 16) = hi;
+          *reinterpret_cast<uint4*>(z_buf + ((size_t)(p.H / 8 + grp) * WN_TT + m) * 16) = lo;
+        }
+      }
+      if (!z_free) mbar_wait(Z_EMPTY, (n & 1) ^ 1);
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(Z_FULL);
+    }
+  } else {
+    // ===================== epilogue: SO (TMEM) -> skips (fp32 RMW), x' (packed hi/lo) =====================
+    const int ew = warp - WN_W_EPI0;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const bool out_half = (ew >> 2) != 0;  // warps 0-3: skip columns [0, S); warps 4-7: residual columns [S, S + R)
+    const float rs = 0.70710678118654752440f;
+    for (int n = 0; n < ntl; ++n) {
+      const int set = n % p.nset;
+      const int tile = blockIdx.x + n * gridDim.x;
+      const int b = tile / p.tiles_per_seq;
+      const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
+      const int t = t0 + m;
+      const bool tv = t < p.T;
+      if (!out_half && !p.skip_init) {
+        // L2 prefetch of the skip lines two tiles ahead (one 128-byte line per column and warp)
+        const int tl = tile + 2 * (int)gridDim.x;
+        if (tl < p.total_tiles) {
+          const int bb = tl / p.tiles_per_seq;
+          const int tt = (tl - bb * p.tiles_per_seq) * WN_TT + q * 32;
+          if (tt < p.T)
+            for (int col = lane; col < p.S; col += 32) prefetch_l2(skips + ((long long)bb * p.S + col) * p.T + tt);
+        }
+      }
+      mbar_wait(SO_FULL(set), (n / p.nset) & 1);
+      tc_fence_after();
+      const unsigned tacc = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(set * p.set_cols);
+      if (!out_half) {
+        float* sq = skips + (long long)b * p.S * p.T + t;
+        for (int col = 0; col < p.S; col += 16) {
+          unsigned r[16];
+          tc_ld16(tacc + (unsigned)col, r);
+          float sv[16];
+          if (tv && !p.skip_init) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sv[j] = sq[(long long)(col + j) * p.T];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sv[j] = 0.f;
+          }
+          tc_wait_ld();
+          if (tv) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sq[(long long)(col + j) * p.T] = __uint_as_float(r[j]) + bias2[col + j] + sv[j];
+          }
+        }
+      } else if (p.write_x) {
+        const long long row = (long long)p.halo + t;
+        for (int col = 0; col < p.R; col += 16) {
+          unsigned r[16];
+          tc_ld16(tacc + (unsigned)(p.S + col), r);
+          uint4 xh[2], xl[2];
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const long long gi = col / 8 + h8;
+            if (tv) {
+              xh[h8] = ldg16(xin + ((long long)(b * 2 + 0) * p.ngx + gi) * p.Tp + row);
+              xl[h8] = ldg16(xin + ((long long)(b * 2 + 1) * p.ngx + gi) * p.Tp + row);
+            } else {
+              xh[h8] = xl[h8] = make_uint4(0, 0, 0, 0);
+            }
+          }
+          tc_wait_ld();
+          if (tv) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              float fh[8], fl[8], u[8];
+              bf16x8_to_float(xh[h8], fh);
+              bf16x8_to_float(xl[h8], fl);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                u[j] = (__uint_as_float(r[h8 * 8 + j]) + bias2[p.S + col + h8 * 8 + j] + (fh[j] + fl[j])) * rs;
+              uint4 hi, lo;
+              split8(u, hi, lo);
+              const long long gi = col / 8 + h8;
+              xout[((long long)(b * 2 + 0) * p.ngx + gi) * p.Tp + row] = hi;
+              xout[((long long)(b * 2 + 1) * p.ngx + gi) * p.Tp + row] = lo;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(ACC_EMPTY(set));
+    }
+  }
+  __syncthreads();
+  if (warp == WN_W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ layout helpers (HBM-bound, one pass)
+// fp32 (B, C, T) (batch stride bs) -> packed hi/lo planes [b][hl][ng][rows][8]; rows outside [row0, row0 + T) stay
+// untouched for `zero_tail == 0`, rows [row0 + T, rows) are zero-filled otherwise (conditioning tail).
+__global__ void wn_pack_kernel(const float* __restrict__ x, long long bs, int C, int T, uint4* __restrict__ pk, int ng,
+                               int rows, int row0, int zero_tail) {
+  const int b = blockIdx.z, g = blockIdx.y;
+  const int tlim = zero_tail ? rows - row0 : T;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < tlim; t += gridDim.x * blockDim.x) {
+    float u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      u[j] = (t < T && ch < C) ? __ldg(x + (long long)b * bs + (long long)ch * T + t) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(u, hi, lo);
+    pk[((long long)(b * 2 + 0) * ng + g) * rows + row0 + t] = hi;
+    pk[((long long)(b * 2 + 1) * ng + g) * rows + row0 + t] = lo;
+  }
+}
+
+__global__ void wn_unpack_kernel(const uint4* __restrict__ pk, int ng, int rows, int row0, float* __restrict__ x, int C, int T) {
+  const int b = blockIdx.z, g = blockIdx.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    float fh[8], fl[8];
+    bf16x8_to_float(pk[((long long)(b * 2 + 0) * ng + g) * rows + row0 + t], fh);
+    bf16x8_to_float(pk[((long long)(b * 2 + 1) * ng + g) * rows + row0 + t], fl);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (g * 8 + j < C) x[((long long)b * C + g * 8 + j) * T + t] = fh[j] + fl[j];
+  }
+}
+
+// first_conv (Conv1d1x1 in_channels -> R, parallel_wavegan.py:155) writing the packed residual stream directly
+__global__ void wn_first_conv_kernel(const float* __restrict__ z, int cin, const float* __restrict__ w, const float* __restrict__ bias,
+                                     int T, uint4* __restrict__ pk, int ng, int rows, int row0) {
+  const int b = blockIdx.z, g = blockIdx.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    float u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = bias ? __ldg(bias + g * 8 + j) : 0.f;
+    for (int ci = 0; ci < cin; ++ci) {
+      const float zv = __ldg(z + ((long long)b * cin + ci) * T + t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = fmaf(__ldg(w + (long long)(g * 8 + j) * cin + ci), zv, u[j]);
+    }
+    uint4 hi, lo;
+    split8(u, hi, lo);
+    pk[((long long)(b * 2 + 0) * ng + g) * rows + row0 + t] = hi;
+    pk[((long long)(b * 2 + 1) * ng + g) * rows + row0 + t] = lo;
+  }
+}
+
+static int wn_plan(const pwgb_wnstack_desc* d, WnK& p, size_t& smem_bytes) {
+  if (!d || d->batch < 0 || d->t <= 0 || d->kernel <= 0 || d->kernel % 2 == 0 || d->halo < 0) return 0;
+  const int R = d->residual_channels, G = d->gate_channels, S = d->skip_channels, A = d->aux_channels;
+  if (R <= 0 || R % KC || G <= 0 || G % 2 || (G / 2) % KC || G % 16 || S <= 0 || S % 16 || A <= 0 || A % 16) return 0;
+  const int N2 = S + R;
+  const int width = G > N2 ? G : N2;
+  if (width > 256 || N2 % 16 || R % 16) return 0;
+  p.B = d->batch;
+  p.T = d->t;
+  p.R = R;
+  p.G = G;
+  p.S = S;
+  p.A = A;
+  p.K = d->kernel;
+  p.halo = d->halo;
+  p.H = G / 2;
+  p.D = 1;
+  const int tr = ceil_div(d->t, WN_TT) * WN_TT;
+  p.Tp = 2 * d->halo + tr;
+  p.Tc = tr;
+  p.ngx = R / 8;
+  p.ngc = (A + 7) / 8;
+  p.nxc = R / KC;
+  p.ncc = (A + KC - 1) / KC;
+  p.nsc = p.H / KC;
+  p.N2 = N2;
+  p.tiles_per_seq = tr / WN_TT;
+  if ((long long)p.tiles_per_seq * d->batch > 0x7fffffffLL) return 0;
+  p.total_tiles = p.tiles_per_seq * d->batch;
+  p.a_bytes = 8 * WN_BLK;
+  p.b_bytes = 2 * (KC / 8) * width * 16;
+  if (G != N2) return 0;  // one weight-stage size and one ring slot size (true for every reference config: S = R = G/2)
+  p.slot_bytes = p.a_bytes + p.b_bytes;
+  p.z_bytes = 2 * (p.H / 8) * WN_BLK;
+  p.set_cols = width;
+  p.nset = 512 / width > 4 ? 4 : 512 / width;
+  int alloc = 32;
+  while (alloc < p.nset * width) alloc <<= 1;
+  p.tmem_cols = alloc;
+  const size_t fixed = (size_t)p.z_bytes + 8 * (2 * WN_MAX_SLOTS + 14) + 16 + 4 * (size_t)(G + N2) + 128;
+  const size_t budget = 227 * 1024;
+  if (fixed + 3 * (size_t)p.slot_bytes > budget) return 0;
+  int ns = (int)((budget - fixed) / p.slot_bytes);
+  p.nslot = ns > WN_MAX_SLOTS ? WN_MAX_SLOTS : ns;
+  smem_bytes = (size_t)p.nslot * p.slot_bytes + fixed;
+  p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(G >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N2 >> 3) << 17) | ((128u >> 4) << 24);
+  p.write_x = 1;
+  p.skip_init = 0;
+  return 1;
+}
+
+}  // namespace pwgb
+
+using namespace pwgb;
+
+extern "C" int pwgb_wnstack_supported(const pwgb_wnstack_desc* d) {
+  WnK p;
+  size_t bytes;
+  return wn_plan(d, p, bytes);
+}
+
+extern "C" size_t pwgb_wnstack_x_bytes(const pwgb_wnstack_desc* d) {
+  WnK p;
+  size_t bytes;
+  if (!wn_plan(d, p, bytes)) return 0;
+  return (size_t)p.B * 2 * p.ngx * p.Tp * 16;
+}
+
+extern "C" size_t pwgb_wnstack_c_bytes(const pwgb_wnstack_desc* d) {
+  WnK p;
+  size_t bytes;
+  if (!wn_plan(d, p, bytes)) return 0;
+  return (size_t)p.B * 2 * p.ngc * p.Tc * 16;
+}
+
+static dim3 wn_grid(int T, int ng, int B) { return dim3((unsigned)((T + 255) / 256 > 64 ? 64 : (T + 255) / 256), (unsigned)ng, (unsigned)B); }
+
+extern "C" int pwgb_wnstack_pack_x(const pwgb_wnstack_desc* d, const float* x, void* xpk, void* stream) {
+  WnK p;
+  size_t bytes;
+  PWGB_UNSUPPORTED_IF(!wn_plan(d, p, bytes), "wnstack: configuration not supported");
+  PWGB_CHECK_ARG(x && xpk, "wnstack_pack_x: null argument");
+  if (p.B == 0) return PWGB_OK;
+  wn_pack_kernel<<<wn_grid(p.T, p.ngx, p.B), 256, 0, (cudaStream_t)stream>>>(x, (long long)p.R * p.T, p.R, p.T, (uint4*)xpk, p.ngx, p.Tp,
+                                                                            p.halo, 0);
+  return check_launch("wn_pack_kernel");
+}
+
+extern "C" int pwgb_wnstack_pack_c(const pwgb_wnstack_desc* d, const float* c, long long c_batch_stride, void* cpk, void* stream) {
+  WnK p;
+  size_t bytes;
+  PWGB_UNSUPPORTED_IF(!wn_plan(d, p, bytes), "wnstack: configuration not supported");
+  PWGB_CHECK_ARG(c && cpk && c_batch_stride >= (long long)p.A * p.T, "wnstack_pack_c: bad argument");
+  if (p.B == 0) return PWGB_OK;
+  wn_pack_kernel<<<wn_grid(p.Tc, p.ngc, p.B), 256, 0, (cudaStream_t)stream>>>(c, c_batch_stride, p.A, p.T, (uint4*)cpk, p.ngc, p.Tc, 0, 1);
+  return check_launch("wn_pack_kernel");
+}
+
+extern "C" int pwgb_wnstack_unpack_x(const pwgb_wnstack_desc* d, const void* xpk, float* x, void* stream) {
+  WnK p;
+  size_t bytes;
+  PWGB_UNSUPPORTED_IF(!wn_plan(d, p, bytes), "wnstack: configuration not supported");
+  PWGB_CHECK_ARG(x && xpk, "wnstack_unpack_x: null argument");
+  if (p.B == 0) return PWGB_OK;
+  wn_unpack_kernel<<<wn_grid(p.T, p.ngx, p.B), 256, 0, (cudaStream_t)stream>>>((const uint4*)xpk, p.ngx, p.Tp, p.halo, x, p.R, p.T);
+  return check_launch("wn_unpack_kernel");
+}
+
+extern "C" int pwgb_wnstack_first_conv(const pwgb_wnstack_desc* d, const float* z, int in_channels, const float* w, const float* bias,
+                                       void* xpk, void* stream) {
+  WnK p;
+  size_t bytes;
+  PWGB_UNSUPPORTED_IF(!wn_plan(d, p, bytes), "wnstack: configuration not supported");
+  PWGB_CHECK_ARG(z && w && xpk && in_channels > 0, "wnstack_first_conv: bad argument");
+  if (p.B == 0) return PWGB_OK;
+  wn_first_conv_kernel<<<wn_grid(p.T, p.ngx, p.B), 256, 0, (cudaStream_t)stream>>>(z, in_channels, w, bias, p.T, (uint4*)xpk, p.ngx, p.Tp,
+                                                                                  p.halo);
+  return check_launch("wn_first_conv_kernel");
+}
+
+extern "C" int pwgb_wnstack_layer_forward(const pwgb_wnstack_desc* d, int dilation, const void* xpk_in, const void* cpk,
+                                          const void* packed_w, const float* b_conv, const float* b_skip_out, void* xpk_out,
+                                          float* skips, int skips_init, void* stream) {
+  WnK p;
+  size_t bytes = 0;
+  PWGB_UNSUPPORTED_IF(!wn_plan(d, p, bytes), "wnstack: configuration not supported by the fused tcgen05 layer");
+  PWGB_CHECK_ARG(xpk_in && cpk && packed_w && skips, "wnstack_layer: null argument");
+  PWGB_CHECK_ARG(dilation > 0 && (long long)(d->kernel / 2) * dilation <= d->halo, "wnstack_layer: dilation %d exceeds the halo %d of the packed stream",
+                 dilation, d->halo);
+  PWGB_CHECK_ARG(xpk_in != xpk_out, "wnstack_layer: xpk_out must not alias xpk_in (other tiles read the halo)");
+  PWGB_CHECK_ARG(!((reinterpret_cast<uintptr_t>(xpk_in) | reinterpret_cast<uintptr_t>(cpk) | reinterpret_cast<uintptr_t>(packed_w) |
+                    reinterpret_cast<uintptr_t>(xpk_out)) & 15),
+                 "wnstack_layer: packed buffers must be 16-byte aligned");
+  if (p.B == 0) return PWGB_OK;
+  p.D = dilation;
+  p.write_x = xpk_out != nullptr;
+  p.skip_init = skips_init != 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wavenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("wnstack_layer: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return PWGB_CUDA_ERROR;
+    }
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  wavenet_fused_kernel<<<(unsigned)grid, WN_THREADS, bytes, (cudaStream_t)stream>>>(
+      p, (const uint4*)xpk_in, (const uint4*)cpk, (const unsigned char*)packed_w, b_conv, b_skip_out, (uint4*)xpk_out, skips);
+  return check_launch("wavenet_fused_kernel");
+}

@@ -499,8 +499,11 @@ class ParallelWaveGANGenerator(_GeneratorBase):
             cp[:, : c.shape[1]].copy_(c)
             c = cp
         fc = self.first_conv
-        x = ops.conv1d(z, effective_weight(fc), fc.bias)
-        if torch.is_grad_enabled() and next(self.parameters()).requires_grad:
+        train = torch.is_grad_enabled() and next(self.parameters()).requires_grad
+        skips = None if train else self._forward_packed(z, c)
+        if skips is None:
+            x = ops.conv1d(z, effective_weight(fc), fc.bias)
+        if train:
             from .autograd import ScaledSumFn  # training: differentiable layer composition
 
             hs = []
@@ -511,13 +514,53 @@ class ParallelWaveGANGenerator(_GeneratorBase):
             l1, l3 = self.last_conv_layers[1], self.last_conv_layers[3]
             h = ops.conv1d(skips, effective_weight(l1), l1.bias, pre_slope=0.0)
             return ops.conv1d(h, effective_weight(l3), l3.bias, pre_slope=0.0)
-        skips = torch.zeros((x.shape[0], self.conv_layers[0].conv1x1_skip.out_channels, x.shape[2]), device=x.device, dtype=torch.float32)
-        for f in self.conv_layers:
-            x, _ = f(x, c, skips)
+        if skips is None:
+            skips = torch.zeros((x.shape[0], self.conv_layers[0].conv1x1_skip.out_channels, x.shape[2]), device=x.device, dtype=torch.float32)
+            for f in self.conv_layers:
+                x, _ = f(x, c, skips)
         # relu(a * s) = a * relu(s) for a > 0: the sqrt(1/layers) scale is folded into the 1x1 weights
         l1, l3 = self.last_conv_layers[1], self.last_conv_layers[3]
         h = ops.conv1d(skips, effective_weight(l1) * self._skip_scale, l1.bias, pre_slope=0.0)
         return ops.conv1d(h, effective_weight(l3), l3.bias, pre_slope=0.0)
+
+    def _forward_packed(self, z, c):
+        """Inference fast path: the residual stack as fused one-kernel layers on the packed (bf16 hi/lo operand
+        layout) residual stream -- pwgb_wnstack_*.  Returns the skip sum (B, S, T) or None when the configuration
+        has no fused kernel (the caller then runs the per-layer fp32 path)."""
+        if c is None:
+            return None
+        l0 = self.conv_layers[0]
+        G, R, K = l0.conv.out_channels, l0.conv.in_channels, l0.conv.kernel_size[0]
+        S = l0.conv1x1_skip.out_channels
+        A = self.aux_channels
+        B, _, T = z.shape
+        dmax = max(f.dilation for f in self.conv_layers)
+        if c.shape[1] < A or not ops.WnStack.supported(B, T, R, G, S, A, K, dmax):
+            return None
+        cache = self.__dict__.setdefault("_wn_stacks", {})
+        key = (B, T, str(z.device))
+        st = cache.get(key)
+        if st is None:
+            if len(cache) >= 4:
+                cache.clear()
+            st = cache[key] = ops.WnStack(B, T, R, G, S, A, K, dmax, z.device)
+        st.cur = 0
+        st.pack_c(c)
+        fc = self.first_conv
+        st.first_conv(z, effective_weight(fc), fc.bias)
+        skips = torch.empty((B, S, T), device=z.device, dtype=torch.float32)
+        n = len(self.conv_layers)
+        for i, f in enumerate(self.conv_layers):
+            k = ops.param_key(f.conv, f.conv1x1_aux, f.conv1x1_skip, f.conv1x1_out)
+            ent = f._cache.get("wnp")
+            if ent is None or ent[0] != k:
+                packed, bso = ops.wavenet_packed_weights(effective_weight(f.conv), effective_weight(f.conv1x1_aux), effective_weight(f.conv1x1_skip),
+                                                         effective_weight(f.conv1x1_out), f.conv1x1_skip.bias, f.conv1x1_out.bias, A,
+                                                         cache=f._cache, key=k)
+            else:
+                packed, bso = ent[1], ent[2]
+            st.layer(packed, f.conv.bias, bso, f.dilation, skips, skips_init=(i == 0), write_x=(i < n - 1))
+        return skips
 
     def apply_weight_norm(self):
         def _apply_weight_norm(m):

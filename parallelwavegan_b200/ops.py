@@ -306,6 +306,110 @@ def wavenet_layer(x, c, w_conv, b_conv, w_aux, w_skip, b_skip, w_out, b_out, dil
     return conv1d(g, w_out, b_out, pre_gate=True, residual=x, out_scale=0.7071067811865476)
 
 
+class WnStack:
+    """Packed WaveNet residual stack (pwgb_wnstack_*): the residual stream and the conditioning stay in the
+    tensor core's operand layout (bf16 hi/lo) between the fused one-kernel layers.  Holds the two ping-pong
+    stream buffers (zero halos, allocated once per (B, T)) and the packed conditioning."""
+
+    def __init__(self, B, T, R, G, S, A, K, max_dilation, device):
+        self.desc = capi.WnStackDesc(batch=B, t=T, residual_channels=R, gate_channels=G, skip_channels=S, aux_channels=A,
+                                     kernel=K, halo=(K - 1) // 2 * int(max_dilation))
+        L = capi.lib()
+        if not L.pwgb_wnstack_supported(C.byref(self.desc)):
+            raise PwgbError("wnstack: configuration not supported by the fused tcgen05 layer")
+        nx = L.pwgb_wnstack_x_bytes(C.byref(self.desc))
+        nc = L.pwgb_wnstack_c_bytes(C.byref(self.desc))
+        self.x = [torch.zeros(nx // 4, device=device, dtype=torch.int32) for _ in range(2)]  # zero halos: written once
+        self.c = torch.empty(nc // 4, device=device, dtype=torch.int32)
+        self.cur = 0
+        self.shape = (B, R, T)
+        self.S, self.A = S, A
+
+    @staticmethod
+    def supported(B, T, R, G, S, A, K, max_dilation):
+        d = capi.WnStackDesc(batch=B, t=T, residual_channels=R, gate_channels=G, skip_channels=S, aux_channels=A, kernel=K,
+                             halo=(K - 1) // 2 * int(max_dilation))
+        return ENGINE != "simt" and bool(capi.lib().pwgb_wnstack_supported(C.byref(d)))
+
+    def pack_c(self, c):
+        """c: (B, >= A, T) fp32 conditioning at the waveform rate."""
+        c = _dev(c, "c")
+        B, Cs, T = c.shape
+        if (B, T) != (self.shape[0], self.shape[2]) or Cs < self.A:
+            raise PwgbError(f"wnstack.pack_c: conditioning shape {tuple(c.shape)} does not match the stack")
+        prof = _Prof("wn_pack_c", 0.0, 8.0 * B * self.A * T, f"B{B} A{self.A} T{T}")
+        rc = capi.lib().pwgb_wnstack_pack_c(C.byref(self.desc), _p(c), Cs * T, _p(self.c), _stream())
+        capi.check(rc, "pwgb_wnstack_pack_c")
+        prof.done()
+
+    def pack_x(self, x):
+        x = _dev(x, "x")
+        if tuple(x.shape) != self.shape:
+            raise PwgbError(f"wnstack.pack_x: expected {self.shape}, got {tuple(x.shape)}")
+        rc = capi.lib().pwgb_wnstack_pack_x(C.byref(self.desc), _p(x), _p(self.x[self.cur]), _stream())
+        capi.check(rc, "pwgb_wnstack_pack_x")
+
+    def unpack_x(self):
+        x = torch.empty(self.shape, device=self.c.device, dtype=torch.float32)
+        rc = capi.lib().pwgb_wnstack_unpack_x(C.byref(self.desc), _p(self.x[self.cur]), _p(x), _stream())
+        capi.check(rc, "pwgb_wnstack_unpack_x")
+        return x
+
+    def first_conv(self, z, w, bias):
+        """Conv1d1x1 in_channels -> R on the noise, written straight into the packed stream."""
+        z = _dev(z, "z")
+        w = _dev(w, "w").reshape(w.shape[0], -1)
+        B, cin, T = z.shape
+        if (B, T) != (self.shape[0], self.shape[2]) or w.shape != (self.shape[1], cin):
+            raise PwgbError("wnstack.first_conv: shape mismatch")
+        prof = _Prof("wn_first_conv", 2.0 * B * T * cin * self.shape[1], 4.0 * B * T * (cin + self.shape[1]), f"B{B} T{T}")
+        rc = capi.lib().pwgb_wnstack_first_conv(C.byref(self.desc), _p(z), cin, _p(w), _p(bias), _p(self.x[self.cur]), _stream())
+        capi.check(rc, "pwgb_wnstack_first_conv")
+        prof.done()
+
+    def layer(self, packed, b_conv, b_skip_out, dilation, skips, skips_init=False, write_x=True):
+        """One fused layer on the current stream buffer; the result becomes the current buffer."""
+        B, R, T = self.shape
+        G = self.desc.gate_channels
+        K = self.desc.kernel
+        prof = _Prof("wavenet_fused_tc", 2.0 * B * T * (G * R * K + G * self.A + (self.S + R) * (G // 2)),
+                     4.0 * B * T * ((2 if write_x else 1) * R + self.A + (1 if skips_init else 2) * self.S),
+                     f"B{B} R{R} G{G} S{self.S} A{self.A} k{K} d{dilation} T{T}")
+        nxt = self.x[1 - self.cur] if write_x else None
+        rc = capi.lib().pwgb_wnstack_layer_forward(C.byref(self.desc), int(dilation), _p(self.x[self.cur]), _p(self.c), _p(packed),
+                                                   _p(b_conv), _p(b_skip_out), _p(nxt), _p(skips), int(bool(skips_init)), _stream())
+        capi.check(rc, "pwgb_wnstack_layer_forward")
+        prof.done()
+        if write_x:
+            self.cur = 1 - self.cur
+
+
+def wavenet_packed_weights(w_conv, w_aux, w_skip, w_out, b_skip, b_out, aux_real, cache=None, key=None):
+    """Operand images of one WaveNet layer (pwgb_wavenet_pack, conditioning weight padded to a multiple of 32
+    input channels) + concat(b_skip, b_out); cached under ``key`` (see param_key)."""
+    ent = cache.get("wnp") if (cache is not None and key is not None) else None
+    if ent is not None and ent[0] == key:
+        return ent[1], ent[2]
+    G, R, K = w_conv.shape
+    S = w_skip.shape[0]
+    aux_pad = (aux_real + 31) // 32 * 32
+    d = capi.WaveNetDesc(batch=1, t=128, residual_channels=R, gate_channels=G, skip_channels=S, aux_channels=aux_pad, kernel=K, dilation=1)
+    L = capi.lib()
+    nbytes = L.pwgb_wavenet_packed_bytes(C.byref(d))
+    if nbytes == 0:
+        raise PwgbError("wavenet_packed_weights: configuration not supported")
+    packed = torch.empty(nbytes // 4, device=w_conv.device, dtype=torch.int32)
+    rc = L.pwgb_wavenet_pack(C.byref(d), _p(_dev(w_conv, "w_conv")), _p(_dev(w_aux, "w_aux").reshape(G, -1).contiguous()), int(aux_real),
+                             _p(_dev(w_skip, "w_skip")), _p(_dev(w_out, "w_out")), _p(packed), _stream())
+    capi.check(rc, "pwgb_wavenet_pack")
+    bso = None
+    if b_skip is not None:
+        bso = torch.cat([b_skip.detach().reshape(-1), b_out.detach().reshape(-1)]).contiguous()
+    if cache is not None and key is not None:
+        cache["wnp"] = (key, packed, bso)
+    return packed, bso
+
+
 def mr_stft_loss(x, y, fft_sizes, hop_sizes, win_lengths, windows, eps=1e-7):
     """MultiResolutionSTFTLoss.forward (losses/stft_loss.py:146-170) -> device tensor [sc, mag].
     x, y: (B, T) or (B, C, T); windows: list of device tensors (win_length,)."""

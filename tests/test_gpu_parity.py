@@ -335,6 +335,48 @@ def test_wavenet_layer(dev, dilation, T, B, engine):
     assert rel_l2(so.cpu(), sk0 + sr) < tol
 
 
+@pytest.mark.parametrize("dilation,T,B", [(1, 700, 2), (16, 1000, 2), (64, 515, 1), (128, 1500, 2), (512, 2100, 1), (2, 128 * 150, 3)])
+@pytest.mark.parametrize("skips_init,write_x", [(False, True), (True, True), (False, False)])
+def test_wavenet_fused_layer_packed(dev, dilation, T, B, skips_init, write_x):
+    """The ONE-kernel fused layer on the packed (bf16 hi/lo operand layout) residual stream vs the oracle:
+    pack -> pwgb_wnstack_layer_forward -> unpack.  Covers ragged tails (T % 128 != 0), every tap window
+    reaching into the zero halo, skip initialisation and the last-layer form (no residual output);
+    the last case gives every CTA several tiles (all 4 TMEM accumulator sets and both ring phases wrap)."""
+    from parallelwavegan_b200 import layers, ops
+
+    blk = layers.WaveNetResidualBlock(dilation=dilation)
+    sd = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in blk.state_dict().items()], 40 + dilation, 1.0)
+    blk.load_state_dict(sd)
+    blk = blk.to(dev)
+    x = synth.randn((B, 64, T), 1)
+    c = synth.randn((B, 80, T), 2)
+    sk0 = synth.randn((B, 64, T), 3)
+    w = {f"b.{k}": v for k, v in sd.items()}
+    xr, sr = ref_ops.wavenet_residual_block(w, "b", x, c, dilation, 3)
+    assert ops.WnStack.supported(B, T, 64, 128, 64, 80, 3, 512)
+    st = ops.WnStack(B, T, 64, 128, 64, 80, 3, 512, dev)
+    st.pack_c(c.to(dev))
+    st.pack_x(x.to(dev))
+    assert rel_l2(st.unpack_x().cpu(), x) < 1e-5  # the packed stream carries 16+ mantissa bits
+    skips = sk0.clone().to(dev)
+    with torch.no_grad():
+        packed, bso = ops.wavenet_packed_weights(layers.effective_weight(blk.conv), layers.effective_weight(blk.conv1x1_aux),
+                                                 layers.effective_weight(blk.conv1x1_skip), layers.effective_weight(blk.conv1x1_out),
+                                                 blk.conv1x1_skip.bias, blk.conv1x1_out.bias, 80)
+        st.layer(packed, blk.conv.bias, bso, dilation, skips, skips_init=skips_init, write_x=write_x)
+        torch.cuda.synchronize()
+        xo = st.unpack_x().cpu()
+    if write_x:
+        assert rel_l2(xo, xr) < TC_TOL and max_abs_over_peak(xo, xr) < 5 * TC_TOL
+    else:
+        assert rel_l2(xo, x) < 1e-5  # stream untouched
+    assert rel_l2(skips.cpu(), sr if skips_init else sk0 + sr) < TC_TOL
+    # the zero halo of the written buffer must still be zero (the next layer's padding)
+    raw = st.x[st.cur].view(torch.int32)
+    planes = raw.view(B * 2 * 8, -1, 4)
+    assert int(planes[:, :512].abs().sum()) == 0 and int(planes[:, 512 + T:].abs().sum()) == 0
+
+
 def test_upsample_fir(dev):
     from parallelwavegan_b200 import ops
 

@@ -43,5 +43,30 @@ for spec in sys.argv[1:]:
         torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in evs)[2]
     rate = B * T / (ms * 1e-3)
-    print(f"wavenet layer d{d} T{T} B{B}: {ms:.3f} ms  {rate / 1e9:.2f} G sample-layers/s  {rate * 1344 / 1e9:.0f} GB/s(alg) = "
+    if os.environ.get("WN_FUSED", "1") != "0" and ops.WnStack.supported(B, T, 64, 128, 64, 80, 3, 512):
+        st = ops.WnStack(B, T, 64, 128, 64, 80, 3, 512, dev)
+        st.pack_c(c)
+        st.pack_x(x)
+        with torch.no_grad():
+            packed, bso = ops.wavenet_packed_weights(layers.effective_weight(blk.conv), layers.effective_weight(blk.conv1x1_aux),
+                                                     layers.effective_weight(blk.conv1x1_skip), layers.effective_weight(blk.conv1x1_out),
+                                                     blk.conv1x1_skip.bias, blk.conv1x1_out.bias, 80)
+            for _ in range(3):
+                st.layer(packed, blk.conv.bias, bso, d, skips)
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(5):
+                flush.zero_()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                st.layer(packed, blk.conv.bias, bso, d, skips)
+                e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+        msf = sorted(a.elapsed_time(b) for a, b in evs)[2]
+        rf = B * T / (msf * 1e-3)
+        print(f"FUSED   layer d{d} T{T} B{B}: {msf:.3f} ms  {rf / 1e9:.2f} G sample-layers/s  {rf * 1344 / 1e9:.0f} GB/s(alg) = "
+              f"{rf * 1344 / 1e9 / HBM:.3f} of measured HBM {HBM:.0f} GB/s")
+    print(f"2-launch layer d{d} T{T} B{B}: {ms:.3f} ms  {rate / 1e9:.2f} G sample-layers/s  {rate * 1344 / 1e9:.0f} GB/s(alg) = "
           f"{rate * 1344 / 1e9 / HBM:.3f} of measured HBM {HBM:.0f} GB/s")
