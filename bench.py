@@ -207,8 +207,11 @@ def measure_train_step(dev, rank, local_rank, world, dist, steps=3, warmup=2):
                                              fmin=0, fmax=11025, log_base=None).to(dev),
             "gen_adv": losses.GeneratorAdversarialLoss(), "dis_adv": losses.DiscriminatorAdversarialLoss(),
             "feat_match": losses.FeatureMatchLoss()}
-    step = GanTrainStep(g, d, crit, torch.optim.Adam(g.parameters(), lr=2e-4, betas=(0.5, 0.9)),
-                        torch.optim.Adam(d.parameters(), lr=2e-4, betas=(0.5, 0.9)))
+    from parallelwavegan_b200.optimizers import FusedAdam
+
+    step = GanTrainStep(g, d, crit, FusedAdam(g.parameters(), lr=2e-4, betas=(0.5, 0.9)),
+                        FusedAdam(d.parameters(), lr=2e-4, betas=(0.5, 0.9)), lambda_aux=45.0, lambda_adv=1.0, lambda_feat_match=2.0,
+                        steps=1)
     gen = torch.Generator().manual_seed(1000 + rank)
     c = torch.randn(16, 80, 32, generator=gen).to(dev)
     y = (torch.rand(16, 1, 8192, generator=gen) - 0.5).to(dev)
@@ -247,38 +250,23 @@ def measure_pwg_train_step(dev, rank, local_rank, world, dist, steps=2, warmup=1
     if world > 1:  # the last layer's residual 1x1 has no influence on the output (parallel_wavegan.py:161-166)
         g = torch.nn.parallel.DistributedDataParallel(g, device_ids=[local_rank], find_unused_parameters=True)
         d = torch.nn.parallel.DistributedDataParallel(d, device_ids=[local_rank])
-    mr = losses.MultiResolutionSTFTLoss().to(dev)
-    gen_adv, dis_adv = losses.GeneratorAdversarialLoss(), losses.DiscriminatorAdversarialLoss()
-    opt_g = torch.optim.RAdam(g.parameters(), lr=1e-4, eps=1e-6)
-    opt_d = torch.optim.RAdam(d.parameters(), lr=5e-5, eps=1e-6)
+    from parallelwavegan_b200.optimizers import RAdam
+    from parallelwavegan_b200.train_step import GanTrainStep
+
+    crit = {"stft": losses.MultiResolutionSTFTLoss().to(dev), "gen_adv": losses.GeneratorAdversarialLoss(),
+            "dis_adv": losses.DiscriminatorAdversarialLoss()}
+    # parallel_wavegan.v1.yaml:67-108: lambda_adv 4.0, RAdam lr 1e-4 / 5e-5 eps 1e-6, grad clip 10 / 1
+    tstep = GanTrainStep(g, d, crit, RAdam(g.parameters(), lr=1e-4, eps=1e-6), RAdam(d.parameters(), lr=5e-5, eps=1e-6),
+                         lambda_aux=1.0, lambda_adv=4.0, grad_norm_g=10.0, grad_norm_d=1.0, steps=1)
     T = 25600
     gen = torch.Generator().manual_seed(2000 + rank)
     c = torch.randn(batch, 80, T // 256 + 4, generator=gen).to(dev)
     y = (torch.rand(batch, 1, T, generator=gen) - 0.5).to(dev)
-    dpar = list((d.module if hasattr(d, "module") else d).parameters())
 
     def step():
         z = torch.randn(batch, 1, T, device=dev)
-        y_ = g(z, c)
-        sc, mag = mr(y_.squeeze(1), y.squeeze(1))
-        for p in dpar:
-            p.requires_grad_(False)
-        gen_loss = sc + mag + 4.0 * gen_adv(d(y_))
-        opt_g.zero_grad(set_to_none=True)
-        gen_loss.backward()
-        torch.nn.utils.clip_grad_norm_(g.parameters(), 10.0)
-        opt_g.step()
-        for p in dpar:
-            p.requires_grad_(True)
-        with torch.no_grad():
-            y_ = g(z, c)
-        real, fake = dis_adv(d(y_.detach()), d(y))
-        dis_loss = real + fake
-        opt_d.zero_grad(set_to_none=True)
-        dis_loss.backward()
-        torch.nn.utils.clip_grad_norm_(d.parameters(), 1.0)
-        opt_d.step()
-        return gen_loss.detach(), dis_loss.detach()
+        st = tstep((z, c), y)
+        return st["generator_loss"], st["discriminator_loss"]
 
     for _ in range(warmup):
         st = step()

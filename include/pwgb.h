@@ -155,6 +155,37 @@ PWGB_API int pwgb_wavenet_layer_forward(const pwgb_wavenet_desc* d, const float*
                                void* stream);
 
 /* ------------------------------------------------------------------------
+ * Multi-tensor optimizer step with fused global-norm clipping: replaces
+ * torch.nn.utils.clip_grad_norm_ + optimizer.step() of Trainer._train_step (bin/train.py:289-293, 329-333)
+ * -- Adam (torch.optim.Adam semantics) or the reference's RAdam (optimizers/radam.py:27-99) -- for all
+ * parameters of a model in three launches.  `table`: DEVICE array of n_tensors rows
+ * {param*, grad*, exp_avg*, exp_avg_sq*, numel} (5 x int64); `chunks`: DEVICE array of n_chunks int32 pairs
+ * {tensor index, chunk index}; chunk c of a tensor covers elements [c*chunk_elems, (c+1)*chunk_elems).
+ * pwgb_mt_clip_coef: out2[0] = total gradient norm, out2[1] = min(1, max_norm/(norm+1e-6)) (1 if max_norm<=0);
+ * partial: n_chunks floats of workspace.  pwgb_mt_adam_step: mode 0 Adam (c1 = lr/(1-beta1^t),
+ * c2 = 1/sqrt(1-beta2^t)), 1 RAdam rectified (c1 = step_size*lr), 2 RAdam unrectified (c1 = step_size*lr);
+ * coef2 = the out2 of pwgb_mt_clip_coef or NULL (no clipping); gradients are scaled on the fly and written
+ * back only if write_clipped_grad.  Deterministic (fixed chunk order, no atomics).
+ * ---------------------------------------------------------------------- */
+PWGB_API int pwgb_mt_clip_coef(const void* table, const void* chunks, int n_chunks, int chunk_elems, float max_norm, float* partial,
+                      float* out2, void* stream);
+PWGB_API int pwgb_mt_adam_step(const void* table, const void* chunks, int n_chunks, int chunk_elems, int mode, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, float c1, float c2, const float* coef2, int write_clipped_grad,
+                      void* stream);
+
+/* ------------------------------------------------------------------------
+ * Space-to-depth along time for strided convs (MSD grouped k41 stride 2/4, hifigan.py:586-601; MPD (5,1)
+ * stride (3,1), hifigan.py:354-381):  y[b, g*s*Cg + r*Cg + cl, u, p] = x[b, g*Cg + cl, s*u + r - pad_left, p]
+ * (zero outside [0, rows_in)), so that  conv_stride_s(x, w) = conv_stride_1(y, w') with
+ * w'[co, r*Cg + cl, j] = w[co, cl, s*j + r]  (ceil(K/s) taps, no padding, rows_out = t_out + ceil(K/s) - 1).
+ * x: (batch, channels, rows_in, period) -> y: (batch, channels*stride, rows_out, period); backward is the adjoint.
+ * ---------------------------------------------------------------------- */
+PWGB_API int pwgb_s2d_forward(const float* x, float* y, int batch, int channels, int groups, long long rows_in, int period, int stride,
+                     int pad_left, long long rows_out, void* stream);
+PWGB_API int pwgb_s2d_backward(const float* gy, float* gx, int batch, int channels, int groups, long long rows_in, int period, int stride,
+                      int pad_left, long long rows_out, void* stream);
+
+/* ------------------------------------------------------------------------
  * Packed WaveNet residual stack: the fused ONE-kernel form of WaveNetResidualBlock.forward
  * (layers/residual_block.py:102-140) used by ParallelWaveGANGenerator.forward's layer loop
  * (models/parallel_wavegan.py:161-166).  Between layers the residual stream x and the conditioning c

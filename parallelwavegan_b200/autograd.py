@@ -167,6 +167,20 @@ def conv_transpose1d(x, w, bias=None, *, stride, padding=0, output_padding=0, pr
     return ConvTranspose1dFn.apply(x, w, bias, stride, padding, output_padding, float(pre_slope))
 
 
+class S2DFn(torch.autograd.Function):
+    """Space-to-depth along time (strided convs on the tensor-core path); backward = the adjoint gather."""
+
+    @staticmethod
+    def forward(ctx, x, groups, stride, pad_left, rows_out, period):
+        ctx.cfg = (tuple(x.shape), groups, stride, pad_left, period)
+        return ops.s2d_raw(x, groups, stride, pad_left, rows_out, period)
+
+    @staticmethod
+    def backward(ctx, gy):
+        shape, groups, stride, pad_left, period = ctx.cfg
+        return ops.s2d_backward_raw(gy.contiguous(), shape, groups, stride, pad_left, period), None, None, None, None, None
+
+
 class AvgPool1dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernel_size, stride, padding, count_include_pad):

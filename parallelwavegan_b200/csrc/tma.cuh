@@ -1,0 +1,58 @@
+// Tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG): host-side descriptor encoding through the driver entry
+// point (no link against libcuda) and the device-side load wrappers.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pwgb {
+
+typedef CUresult (*tma_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline tma_encode_tiled_fn tma_encoder() {
+  static tma_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (tma_encode_tiled_fn)p;
+  }
+  return fn;
+}
+
+// rank-4 packed tensor of `elem_bytes`-sized elements: dims[0] fastest.  Out-of-bounds box elements read as zero.
+inline int tma_make_4d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, const unsigned long long dims[4],
+                       const unsigned box[4]) {
+  tma_encode_tiled_fn enc = tma_encoder();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return PWGB_CUDA_ERROR;
+  }
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {dims[0] * elem_bytes, dims[0] * dims[1] * elem_bytes, dims[0] * dims[1] * dims[2] * elem_bytes};
+  cuuint32_t bdim[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, dt, 4, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return PWGB_CUDA_ERROR;
+  }
+  return PWGB_OK;
+}
+
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+}  // namespace pwgb

@@ -14,20 +14,22 @@
 //   xpk [batch][hi|lo][R/8][t_pad][8 ch] bf16,  t_pad = 2*halo + round_up(t, 128); rows [halo, halo + t) hold
 //       the samples, every other row is zero (the conv's zero padding and the tail of the last tile);
 //   cpk [batch][hi|lo][ceil(A/8)][round_up(t, 128)][8 ch] bf16.
-// A (32 channel, 128 row) operand window of any tap / dilation is then 8 contiguous 2 KB blocks: the
-// activation side of a pipeline stage is 8 cp.async.bulk copies, the weight side one 16 KB copy, and no
+// A (32 channel, 128 row) operand window of any tap / dilation is then a 4-D box of the packed tensor: the
+// activation side of a pipeline stage is ONE cp.async.bulk.tensor (TMA), the weight side one 16 KB bulk copy, and no
 // thread ever converts or re-lays-out an input (the conversion happens once, in the epilogue that
 // produces the value).  x = hi + lo carries 16 mantissa bits -- exactly what the bf16x3 MMA consumes;
 // the residual add sees the same value.
 //
 // Warp roles (576 threads, one persistent CTA per SM, mbarriers only):
-//   warp 0      TMA: per stage 8 activation blocks + 1 weight block into a ring of 32 KB slots
+//   warp 0      TMA: per stage ONE tensor-map load of the activation window (4-D box: 8 ch x 128 rows x 4 groups x hi|lo)
+//               + one bulk copy of the weight stage into a ring of 32 KB slots
 //   warp 1      MMA issuer (elected lane): conv(i) into set i%4, then the skip/out contraction of tile i-1
 //   warps 2-9   gate:     G (TMEM) -> z operand image (smem)
 //   warps 10-17 epilogue: SO (TMEM) -> skips (fp32, read-modify-write) and x' (packed)
 // TMEM: 4 accumulator sets of max(G, S+R) <= 128 columns; the tile sequence conv(i+1) | SO(i) keeps the
 // tensor pipe busy while gate(i) runs.
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace pwgb {
 
@@ -82,8 +84,8 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
 }
 
 __global__ void __launch_bounds__(WN_THREADS, 1)
-    wavenet_fused_kernel(const WnK p, const uint4* __restrict__ xin, const uint4* __restrict__ cpk,
-                         const unsigned char* __restrict__ wpk, const float* __restrict__ b_conv,
+    wavenet_fused_kernel(const WnK p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
+                         const uint4* __restrict__ xin, const unsigned char* __restrict__ wpk, const float* __restrict__ b_conv,
                          const float* __restrict__ b_so, uint4* __restrict__ xout, float* __restrict__ skips) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: ring[nslot] (A 16 KB | B) | z image | barriers | tmem slot | bias (G + N2 floats)
@@ -139,9 +141,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
     int s = 0, ph = 0;
     const unsigned char* w_aux = wpk + (size_t)p.nxc * p.K * p.b_bytes;
     const unsigned char* w_so = w_aux + (size_t)p.ncc * p.b_bytes;
-    const int cgl = p.ngc - (p.ncc - 1) * 4;  // 8-channel groups of the last conditioning chunk
     auto stage_so = [&](int sc) {
-      mbar_wait(EMPTY(s), ph ^ 1);
+      mbar_wait_spin(EMPTY(s), ph ^ 1);
       if (lane == 0) {
         mbar_expect_tx(FULL(s), (unsigned)p.b_bytes);
         bulk_g2s(smem_u32(ring + (size_t)s * p.slot_bytes + p.a_bytes), w_so + (size_t)sc * p.b_bytes, (unsigned)p.b_bytes, FULL(s));
@@ -149,6 +150,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       __syncwarp();
       if (++s == p.nslot) { s = 0; ph ^= 1; }
     };
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_x);
+      tma_prefetch_desc(&tm_c);
+    }
     for (int n = 0; n < ntl; ++n) {
       const int tile = blockIdx.x + n * gridDim.x;
       const int b = tile / p.tiles_per_seq;
@@ -157,22 +162,16 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         const bool is_x = j < p.nxc * p.K;
         const int chunk = is_x ? j / p.K : j - p.nxc * p.K;
         const int tap = is_x ? j - chunk * p.K : 0;
-        const int ng = is_x ? 4 : (chunk == p.ncc - 1 ? cgl : 4);
-        mbar_wait(EMPTY(s), ph ^ 1);
-        const unsigned dstA = smem_u32(ring + (size_t)s * p.slot_bytes);
-        if (lane == 0) mbar_expect_tx(FULL(s), (unsigned)(2 * ng * WN_BLK + p.b_bytes));
-        __syncwarp();
-        if (lane < 2 * ng) {
-          const int hl = lane / ng, gi = lane - hl * ng;
-          const uint4* src;
-          if (is_x) {
-            const long long row = (long long)p.halo + t0 + (long long)(tap - p.K / 2) * p.D;
-            src = xin + ((long long)(b * 2 + hl) * p.ngx + chunk * 4 + gi) * p.Tp + row;
-          } else {
-            src = cpk + ((long long)(b * 2 + hl) * p.ngc + chunk * 4 + gi) * p.Tc + t0;
-          }
-          bulk_g2s(dstA + (unsigned)((hl * 4 + gi) * WN_BLK), src, WN_BLK, FULL(s));
-        } else if (lane == 31) {
+        mbar_wait_spin(EMPTY(s), ph ^ 1);
+        if (lane == 0) {
+          // ONE tensor-map TMA per activation window: box (8 ch, 128 rows, 4 groups, hi|lo) = the 16 KB operand image;
+          // groups beyond the tensor (last conditioning chunk) arrive as zeros and count towards the transaction bytes
+          const unsigned dstA = smem_u32(ring + (size_t)s * p.slot_bytes);
+          mbar_expect_tx(FULL(s), (unsigned)(p.a_bytes + p.b_bytes));
+          if (is_x)
+            tma_load_4d(dstA, &tm_x, 0, p.halo + t0 + (tap - p.K / 2) * p.D, chunk * 4, 2 * b, FULL(s));
+          else
+            tma_load_4d(dstA, &tm_c, 0, t0, chunk * 4, 2 * b, FULL(s));
           const unsigned char* wsrc = is_x ? wpk + (size_t)j * p.b_bytes : w_aux + (size_t)chunk * p.b_bytes;
           bulk_g2s(dstA + (unsigned)p.a_bytes, wsrc, (unsigned)p.b_bytes, FULL(s));
         }
@@ -305,43 +304,53 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
             for (int col = lane; col < p.S; col += 32) prefetch_l2(skips + ((long long)bb * p.S + col) * p.T + tt);
         }
       }
-      mbar_wait(SO_FULL(set), (n / p.nset) & 1);
-      tc_fence_after();
+      // The operands that come from HBM / L2 (skip values, residual x) of column group g + 1 are requested while
+      // group g is being processed, and group 0 before the accumulator is even waited for: the epilogue never
+      // sits on a full memory round trip per group.
       const unsigned tacc = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(set * p.set_cols);
       if (!out_half) {
         float* sq = skips + (long long)b * p.S * p.T + t;
+        const bool ld = tv && !p.skip_init;
+        float sv[16], sn[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sv[j] = ld ? sq[(long long)j * p.T] : 0.f;
+        mbar_wait(SO_FULL(set), (n / p.nset) & 1);
+        tc_fence_after();
         for (int col = 0; col < p.S; col += 16) {
           unsigned r[16];
           tc_ld16(tacc + (unsigned)col, r);
-          float sv[16];
-          if (tv && !p.skip_init) {
+          const bool more = ld && col + 16 < p.S;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sv[j] = sq[(long long)(col + j) * p.T];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sv[j] = 0.f;
-          }
+          for (int j = 0; j < 16; ++j) sn[j] = more ? sq[(long long)(col + 16 + j) * p.T] : 0.f;
           tc_wait_ld();
           if (tv) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) sq[(long long)(col + j) * p.T] = __uint_as_float(r[j]) + bias2[col + j] + sv[j];
           }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sv[j] = sn[j];
         }
       } else if (p.write_x) {
         const long long row = (long long)p.halo + t;
+        const uint4* xh_base = xin + ((long long)(b * 2 + 0) * p.ngx) * p.Tp + row;
+        const uint4* xl_base = xin + ((long long)(b * 2 + 1) * p.ngx) * p.Tp + row;
+        uint4 xh[2], xl[2], nh[2], nl[2];
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          xh[h8] = tv ? ldg16(xh_base + (long long)h8 * p.Tp) : make_uint4(0, 0, 0, 0);
+          xl[h8] = tv ? ldg16(xl_base + (long long)h8 * p.Tp) : make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(SO_FULL(set), (n / p.nset) & 1);
+        tc_fence_after();
         for (int col = 0; col < p.R; col += 16) {
           unsigned r[16];
           tc_ld16(tacc + (unsigned)(p.S + col), r);
-          uint4 xh[2], xl[2];
+          const bool more = tv && col + 16 < p.R;
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
-            const long long gi = col / 8 + h8;
-            if (tv) {
-              xh[h8] = ldg16(xin + ((long long)(b * 2 + 0) * p.ngx + gi) * p.Tp + row);
-              xl[h8] = ldg16(xin + ((long long)(b * 2 + 1) * p.ngx + gi) * p.Tp + row);
-            } else {
-              xh[h8] = xl[h8] = make_uint4(0, 0, 0, 0);
-            }
+            const long long gi = col / 8 + 2 + h8;
+            nh[h8] = more ? ldg16(xh_base + gi * p.Tp) : make_uint4(0, 0, 0, 0);
+            nl[h8] = more ? ldg16(xl_base + gi * p.Tp) : make_uint4(0, 0, 0, 0);
           }
           tc_wait_ld();
           if (tv) {
@@ -360,7 +369,15 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
               xout[((long long)(b * 2 + 1) * p.ngx + gi) * p.Tp + row] = lo;
             }
           }
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            xh[h8] = nh[h8];
+            xl[h8] = nl[h8];
+          }
         }
+      } else {
+        mbar_wait(SO_FULL(set), (n / p.nset) & 1);
+        tc_fence_after();
       }
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(set));
@@ -582,7 +599,18 @@ extern "C" int pwgb_wnstack_layer_forward(const pwgb_wnstack_desc* d, int dilati
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  // tensor maps of the packed streams: dims (8 ch, rows, 8-channel groups, batch x hi|lo), box = one operand window
+  CUtensorMap tm_x, tm_c;
+  {
+    const unsigned long long dx[4] = {8ull, (unsigned long long)p.Tp, (unsigned long long)p.ngx, 2ull * p.B};
+    const unsigned long long dc[4] = {8ull, (unsigned long long)p.Tc, (unsigned long long)p.ngc, 2ull * p.B};
+    const unsigned box[4] = {8u, (unsigned)WN_TT, 4u, 2u};
+    int rc = tma_make_4d(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xpk_in, dx, box);
+    if (rc) return rc;
+    rc = tma_make_4d(&tm_c, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cpk, dc, box);
+    if (rc) return rc;
+  }
   wavenet_fused_kernel<<<(unsigned)grid, WN_THREADS, bytes, (cudaStream_t)stream>>>(
-      p, (const uint4*)xpk_in, (const uint4*)cpk, (const unsigned char*)packed_w, b_conv, b_skip_out, (uint4*)xpk_out, skips);
+      p, tm_x, tm_c, (const uint4*)xpk_in, (const unsigned char*)packed_w, b_conv, b_skip_out, (uint4*)xpk_out, skips);
   return check_launch("wavenet_fused_kernel");
 }

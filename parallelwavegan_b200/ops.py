@@ -675,8 +675,85 @@ def _needs_grad(*ts):
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
 
 
+def s2d_raw(x, groups, stride, pad_left, rows_out, period=1):
+    """Space-to-depth along time (pwgb_s2d_forward): (B, C, rows[, P]) -> (B, C*stride, rows_out[, P])."""
+    x = _dev(x, "x")
+    B, Cc = x.shape[0], x.shape[1]
+    P = int(period)
+    rows_in = x.numel() // max(B * Cc * P, 1)
+    shape = (B, Cc * stride, rows_out) if P == 1 else (B, Cc * stride, rows_out, P)
+    y = torch.empty(shape, device=x.device, dtype=torch.float32)
+    prof = _Prof("s2d", 0.0, 4.0 * (x.numel() + y.numel()), f"B{B} C{Cc} rows{rows_in} P{P} s{stride}")
+    rc = capi.lib().pwgb_s2d_forward(_p(x), _p(y), B, Cc, int(groups), rows_in, P, int(stride), int(pad_left), int(rows_out), _stream())
+    capi.check(rc, "pwgb_s2d_forward")
+    prof.done()
+    return y
+
+
+def s2d_backward_raw(gy, x_shape, groups, stride, pad_left, period=1):
+    gy = _dev(gy, "gy")
+    B, Cc = x_shape[0], x_shape[1]
+    P = int(period)
+    n = 1
+    for v in x_shape:
+        n *= v
+    rows_in = n // max(B * Cc * P, 1)
+    rows_out = gy.numel() // max(B * Cc * stride * P, 1)
+    gx = torch.empty(x_shape, device=gy.device, dtype=torch.float32)
+    rc = capi.lib().pwgb_s2d_backward(_p(gy), _p(gx), B, Cc, int(groups), rows_in, P, int(stride), int(pad_left), int(rows_out), _stream())
+    capi.check(rc, "pwgb_s2d_backward")
+    return gx
+
+
+def _conv1d_s2d(x, w, bias, kw):
+    """Strided conv on the tensor-core path: space-to-depth + a stride-1 conv with ceil(K/s) taps and s x the
+    input channels (pwgb_s2d_forward).  Returns None when the configuration does not qualify.  The weight
+    re-layout is torch indexing on the (small) weight tensor, so its backward is autograd's; the activations
+    and their gradients only ever pass through libpwgb kernels (s2d / conv / dgrad / wgrad, all stride 1)."""
+    stride = int(kw.get("stride", 1))
+    if stride <= 1 or ENGINE == "simt" or kw.get("dilation", 1) != 1 or kw.get("pad_mode", "zero") not in ("zero", "zeros"):
+        return None
+    if kw.get("pre_gate") or kw.get("out") is not None or kw.get("accumulate") or kw.get("residual") is not None:
+        return None
+    groups, P = int(kw.get("groups", 1)), int(kw.get("period", 1))
+    wd = w.shape
+    cout, cin_g, K = wd[0], wd[1], wd[2]
+    if (cin_g * stride) % 32 or (cout // groups) % 16 or x.dim() < 3:
+        return None
+    B, cin = x.shape[0], x.shape[1]
+    L = x.numel() // max(B * cin, 1)
+    if L % P or cin != cin_g * groups:
+        return None
+    rows_in = L // P
+    padding = kw.get("padding", 0)
+    pl, pr = (padding, padding) if isinstance(padding, int) else padding
+    t_out = (rows_in + pl + pr - (K - 1) - 1) // stride + 1
+    if t_out <= 0:
+        return None
+    Kp = (K + stride - 1) // stride
+    rows_out = t_out + Kp - 1
+    w3 = w.reshape(cout, cin_g, K)
+    if Kp * stride != K:
+        w3 = torch.nn.functional.pad(w3, (0, Kp * stride - K))
+    w2 = w3.reshape(cout, cin_g, Kp, stride).permute(0, 3, 1, 2).reshape(cout, stride * cin_g, Kp)
+    if w.dim() == 4:
+        w2 = w2.unsqueeze(-1)
+    if _needs_grad(x):
+        from . import autograd as ag
+
+        xs = ag.S2DFn.apply(x, groups, stride, pl, rows_out, P)
+    else:
+        xs = s2d_raw(x, groups, stride, pl, rows_out, P)
+    inner = {k: v for k, v in kw.items() if k not in ("stride", "padding")}
+    return conv1d(xs, w2.contiguous(), bias, stride=1, padding=0, **inner)
+
+
 def conv1d(x, w, bias=None, **kw):
     """Fused conv (see conv1d_raw); differentiable through libpwgb backward kernels when any input requires grad."""
+    if kw.get("stride", 1) > 1:
+        y = _conv1d_s2d(x, w, bias, kw)
+        if y is not None:
+            return y
     if _needs_grad(x, w, bias, kw.get("residual")):
         from . import autograd as ag
 

@@ -377,6 +377,49 @@ def test_wavenet_fused_layer_packed(dev, dilation, T, B, skips_init, write_x):
     assert int(planes[:, :512].abs().sum()) == 0 and int(planes[:, 512 + T:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("update", ["inplace_op", "fused_optimizer", "load_state_dict"])
+def test_pwg_forward_sees_weight_updates(dev, update):
+    """Packed operand images are cached per layer, keyed on the LEAF parameters (weight_g / weight_v / bias):
+    a second no-grad forward after an in-place update, a fused-optimizer step or load_state_dict must use the
+    new weights (round-1 advisor finding: the cache was keyed on weight-norm temporaries)."""
+    from parallelwavegan_b200 import models, optimizers
+
+    kw = dict(layers=6, stacks=3)
+    m = models.ParallelWaveGANGenerator(**kw)
+    sd = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 5, 1.0)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    z = synth.randn((2, 1, 2560), 6)
+    c = synth.randn((2, 80, 14), 7)
+    cfg = dict(ref_ops.PWG_V1, **kw)
+
+    def check():
+        with torch.no_grad():
+            y = m(z.to(dev), c.to(dev)).cpu()
+        cur = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        ref = ref_ops.pwg_generator(ref_ops.fold_weight_norm(cur), z, c, cfg)
+        assert rel_l2(y, ref) < REL_TOL
+
+    check()
+    if update == "inplace_op":
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if n.endswith("weight_g"):
+                    p.mul_(1.3)
+                elif n.endswith("bias"):
+                    p.add_(0.05)
+    elif update == "fused_optimizer":
+        opt = optimizers.RAdam(m.parameters(), lr=5e-2)
+        for i, p in enumerate(m.parameters()):
+            p.grad = synth.randn(tuple(p.shape), 100 + i).to(dev)
+        for _ in range(6):
+            opt.step()
+    else:
+        sd2 = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in m.state_dict().items()], 55, 1.1)
+        m.load_state_dict(sd2)
+    check()
+
+
 def test_upsample_fir(dev):
     from parallelwavegan_b200 import ops
 

@@ -1,0 +1,69 @@
+"""Strided discriminator convs on the tensor-core path (space-to-depth + stride-1 tcgen05 conv):
+forward, data gradient and weight gradient vs torch autograd on the CPU (fp32 oracle of the same op),
+at the HiFi-GAN MSD / MPD layer shapes (hifigan.py:354-381, 586-601) and the C5 batch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import max_abs_over_peak, rel_l2
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+TC_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    import __graft_entry__
+
+    __graft_entry__.build()
+    return torch.device("cuda:0")
+
+
+CASES = [
+    # cin, cout, K, stride, groups, pad, rows, period, B
+    (512, 1024, 5, 3, 1, 2, 152, 2, 16),   # MPD p=2 layer 4 at the C5 batch (68 % of the D MACs with the next layer)
+    (128, 512, 5, 3, 1, 2, 92, 11, 4),     # MPD p=11 layer 3
+    (32, 128, 5, 3, 1, 2, 273, 5, 2),      # MPD layer 2 (cin * s = 96)
+    (128, 128, 41, 2, 4, 20, 4096, 1, 4),  # MSD layer 1 (grouped, stride 2)
+    (256, 512, 41, 4, 16, 20, 1024, 1, 4),  # MSD layer 3 (cin_g * s = 64)
+    (512, 1024, 41, 4, 16, 20, 259, 1, 2),  # MSD layer 4, ragged length
+]
+
+
+@pytest.mark.parametrize("cin,cout,K,stride,groups,pad,rows,P,B", CASES)
+def test_strided_conv_s2d_forward_backward(dev, cin, cout, K, stride, groups, pad, rows, P, B):
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((B, cin, rows * P), 1)
+    w = synth.randn((cout, cin // groups, K), 2, 1.0 / (cin // groups * K) ** 0.5)
+    b = synth.randn((cout,), 3, 0.1)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    if P == 1:
+        ref = F.leaky_relu(F.conv1d(xr, wr, br, stride=stride, padding=pad, groups=groups), 0.1)
+    else:
+        ref = F.leaky_relu(F.conv2d(xr.view(B, cin, rows, P), wr.unsqueeze(-1), br, stride=(stride, 1), padding=(pad, 0), groups=groups), 0.1)
+    gy = synth.randn(tuple(ref.shape), 4)
+    ref.backward(gy)
+    xd, wd, bd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    xin = xd if P == 1 else xd.view(B, cin, rows, P)
+    wq = wd if P == 1 else wd.unsqueeze(-1)
+    ops.PROFILE = []
+    try:
+        y = ops.conv1d(xin, wq, bd, stride=stride, padding=pad, groups=groups, period=P, post_act="lrelu", post_slope=0.1)
+        y.backward(gy.to(dev))
+        torch.cuda.synchronize()
+        names = [p[0] for p in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert "s2d" in names and "conv1d_tc" in names and "conv1d" not in names, names
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert rel_l2(y.detach().cpu(), ref.detach()) < TC_TOL and max_abs_over_peak(y.detach().cpu(), ref.detach()) < 5 * TC_TOL
+    assert rel_l2(xd.grad.cpu(), xr.grad) < TC_TOL
+    assert rel_l2(wd.grad.cpu(), wr.grad) < TC_TOL
+    assert rel_l2(bd.grad.cpu(), br.grad) < TC_TOL
+    # no-grad inference form gives the same values
+    with torch.no_grad():
+        y2 = ops.conv1d(xin.detach(), wq.detach(), bd.detach(), stride=stride, padding=pad, groups=groups, period=P, post_act="lrelu", post_slope=0.1)
+    assert torch.equal(y2, y.detach())

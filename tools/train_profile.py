@@ -21,7 +21,7 @@ orig = bench.measure_train_step
 
 
 def run():
-    from oracle import synth
+    from parallelwavegan_b200 import synth_weights as synth
     from parallelwavegan_b200 import losses, models
     from parallelwavegan_b200.train_step import GanTrainStep
 
@@ -32,7 +32,8 @@ def run():
     g, d = g.to(dev).train(), d.to(dev).train()
     crit = {"mel": losses.MelSpectrogramLoss(fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80, fmin=0, fmax=11025, log_base=None).to(dev),
             "gen_adv": losses.GeneratorAdversarialLoss(), "dis_adv": losses.DiscriminatorAdversarialLoss(), "feat_match": losses.FeatureMatchLoss()}
-    step = GanTrainStep(g, d, crit, torch.optim.Adam(g.parameters(), lr=2e-4, betas=(0.5, 0.9)), torch.optim.Adam(d.parameters(), lr=2e-4, betas=(0.5, 0.9)))
+    from parallelwavegan_b200.optimizers import FusedAdam
+    step = GanTrainStep(g, d, crit, FusedAdam(g.parameters(), lr=2e-4, betas=(0.5, 0.9)), FusedAdam(d.parameters(), lr=2e-4, betas=(0.5, 0.9)), steps=1)
     c = torch.randn(16, 80, 32, device=dev)
     y = (torch.rand(16, 1, 8192, device=dev) - 0.5)
     for _ in range(2):
