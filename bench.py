@@ -564,9 +564,22 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     fl, by, tms, cnt = agg[dom]
     achieved = fl / (tms * 1e-3) / 1e12
+    # DRAM traffic of the dominant class: measured with ncu on the same command (launch list with dram__bytes_read/write,
+    # tools/gpu/run1.sh), averaged over every launch of the class in the 16x80x400 forwards -- not a constant of one launch
+    traffic, traffic_note = None, "no ncu launch list committed for this build"
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2_bench.json")))["dominant_class_batch16"]
+        if tj["kernel"].startswith(dom):
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_note = (f"mean dram__bytes_read.sum + dram__bytes_write.sum per launch over {tj['launches_counted']} launches of the class "
+                            f"(ncu launch list of `bench.py --steps 1 --warmup 3`, profiles/traffic_r2_bench.json); the class's share of the forward "
+                            f"under ncu is {tj['time_share_of_forward_under_ncu']:.3f}")
+    except Exception:
+        pass
+    alg_bytes_per_launch = by / cnt
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf_peak, "traffic": 709.2e6,
-                "traffic_note": "dram__bytes_read+write of ONE representative launch (cin=cout=128, k=3, T=25600, B=16, with residual; profiles/ncu_r1_tc_v13_c128k3_summary.txt: 533.2 MB read + 175.9 MB written) whose algorithmic bytes are 629 MB (the 80 MB over-read is halo rows plus the epilogue's L2 prefetch); launches differ in shape so this is not an average",
+                "frac": achieved / tf_peak, "traffic": traffic, "traffic_note": traffic_note,
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "algorithmic_flops_per_launch": fl / cnt,
                 "peak_source": peak_src,
                 "launches_per_step": cnt / 3, "avg_launch_ms": tms / cnt, "share_of_step": tms / sum(v[2] for v in agg.values()),
                 "algorithmic_flops_per_step": fl / 3,
