@@ -155,6 +155,29 @@ PWGB_API int pwgb_wavenet_layer_forward(const pwgb_wavenet_desc* d, const float*
                                void* stream);
 
 /* ------------------------------------------------------------------------
+ * Training collater on the GPU (Collater.__call__, bin/train.py:711-798): one launch gathers the
+ * random crops of a batch from a device-resident corpus.  audio: all waveforms concatenated; feats: all feature
+ * matrices (frames, channels) concatenated along frames (NULL: audio-only case).  x_offsets / c_offsets: DEVICE
+ * arrays of `batch` int64 -- element offset of each crop's first sample / row offset of its first frame.
+ *   y (batch, t)                 = audio[x_offsets[b] + 0..t)
+ *   c (batch, channels, frames)  = transpose of feats rows [c_offsets[b], c_offsets[b] + frames)
+ * ---------------------------------------------------------------------- */
+PWGB_API int pwgb_collate_crop(const float* audio, const long long* x_offsets, const float* feats, const long long* c_offsets, float* y,
+                      float* c, int batch, int t, int channels, int frames, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Decode-driver glue (bin/decode.py:214-243).
+ * pwgb_prep_features: one utterance's features c (t, channels) row-major -> out (channels, t_out):
+ *   out[ch, u] = (c[u - pad_left, ch] - mean[ch]) / scale[ch]  (mean/scale NULL: no normalisation; hifigan.py:264-265),
+ *   frames outside [0, t) zero (pad_mode PWGB_PAD_ZERO) or edge-replicated (PWGB_PAD_REPLICATE,
+ *   parallel_wavegan.py:250-251).  `out` is usually one batch slot of the generator input.
+ * pwgb_pcm16_forward: lrintf(y * 32767) saturated to int16 -- libsndfile's float -> PCM_16 (decode.py:236-241).
+ * ---------------------------------------------------------------------- */
+PWGB_API int pwgb_prep_features(const float* c, const float* mean, const float* scale, float* out, int t, int channels, int pad_left,
+                       int t_out, int pad_mode, void* stream);
+PWGB_API int pwgb_pcm16_forward(const float* y, short* out, long long n, void* stream);
+
+/* ------------------------------------------------------------------------
  * Multi-tensor optimizer step with fused global-norm clipping: replaces
  * torch.nn.utils.clip_grad_norm_ + optimizer.step() of Trainer._train_step (bin/train.py:289-293, 329-333)
  * -- Adam (torch.optim.Adam semantics) or the reference's RAdam (optimizers/radam.py:27-99) -- for all

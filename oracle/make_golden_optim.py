@@ -50,6 +50,40 @@ def main():
                     out[f"{name}_t{t}_s{i}"] = np.array([float(p.detach().double().sum()), float(p.detach().double().norm())])
     np.savez_compressed(os.path.join(GOLD, "optim.npz"), **out)
     print("wrote optim.npz", len(out), "arrays")
+    make_data_golden()
+
+
+def data_items():
+    """Seeded synthetic corpus: (audio, mel) pairs of ragged lengths, one too short to be kept, one needing edge padding."""
+    items = []
+    for k, frames in enumerate((40, 25, 12, 33, 60)):
+        x = synth.randn((frames * 64,), 7000 + k).numpy()
+        if k == 3:
+            x = x[:-17]  # _adjust_length edge-pads this one
+        items.append((x, synth.randn((frames, 20), 7100 + k).numpy()))
+    return items
+
+
+def make_data_golden():
+    """Collater golden: the REAL reference Collater (bin/train.py:646-925) on the seeded corpus with np.random.seed(11)."""
+    # bin/train.py touches a few names of absent logging / plotting packages at import time: give the stub modules those names
+    sys.modules["tensorboardX"].SummaryWriter = object
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+    from parallel_wavegan.bin.train import Collater
+
+    out = {}
+    items = data_items()
+    np.random.seed(11)
+    (c,), y = Collater(batch_max_steps=1100, hop_size=64, aux_context_window=2, use_noise_input=False)(items)
+    out["mel2wav_c"], out["mel2wav_y"] = c.numpy(), y.numpy()
+    np.random.seed(12)
+    (z, c2), y2 = Collater(batch_max_steps=512, hop_size=64, aux_context_window=0, use_noise_input=True)(items)
+    out["noise_c"], out["noise_y"], out["noise_z_shape"] = c2.numpy(), y2.numpy(), np.array(z.shape)
+    np.random.seed(13)
+    (_l, _g), y3 = Collater(batch_max_steps=1500, hop_size=None, aux_context_window=0, use_aux_input=False)([x for x, _ in items])
+    out["audio_y"] = y3.numpy()
+    np.savez_compressed(os.path.join(GOLD, "data.npz"), **out)
+    print("wrote data.npz", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -113,6 +113,12 @@ def lib():
     L.pwgb_wnstack_first_conv.argtypes = [C.POINTER(WnStackDesc), vp, C.c_int, vp, vp, vp, vp]
     L.pwgb_wnstack_layer_forward.restype = C.c_int
     L.pwgb_wnstack_layer_forward.argtypes = [C.POINTER(WnStackDesc), C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.pwgb_collate_crop.restype = C.c_int
+    L.pwgb_collate_crop.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.pwgb_prep_features.restype = C.c_int
+    L.pwgb_prep_features.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.pwgb_pcm16_forward.restype = C.c_int
+    L.pwgb_pcm16_forward.argtypes = [vp, vp, C.c_longlong, vp]
     L.pwgb_mt_clip_coef.restype = C.c_int
     L.pwgb_mt_clip_coef.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp]
     L.pwgb_mt_adam_step.restype = C.c_int
@@ -206,7 +212,7 @@ EXPORTED_SYMBOLS = [
     "pwgb_conv1d_tc_supported",
     "pwgb_conv1d_tc_forward", "pwgb_debug_set", "pwgb_wavenet_supported", "pwgb_wavenet_packed_bytes",
     "pwgb_wavenet_pack", "pwgb_wavenet_layer_forward", "pwgb_upsample_fir_forward",
-    "pwgb_s2d_forward", "pwgb_s2d_backward", "pwgb_mt_clip_coef", "pwgb_mt_adam_step",
+    "pwgb_s2d_forward", "pwgb_s2d_backward", "pwgb_mt_clip_coef", "pwgb_mt_adam_step", "pwgb_prep_features", "pwgb_pcm16_forward", "pwgb_collate_crop",
     "pwgb_wnstack_supported", "pwgb_wnstack_x_bytes", "pwgb_wnstack_c_bytes", "pwgb_wnstack_pack_x", "pwgb_wnstack_unpack_x",
     "pwgb_wnstack_pack_c", "pwgb_wnstack_first_conv", "pwgb_wnstack_layer_forward",
     "pwgb_mr_stft_loss_workspace", "pwgb_mr_stft_loss_forward", "pwgb_stft_amplitude_forward",

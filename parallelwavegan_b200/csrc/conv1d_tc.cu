@@ -884,8 +884,13 @@ using namespace pwgb;
 
 static int tc_cout_chunk(int cout);
 
+namespace pwgb {
+extern int g_wn_variant;
+}
+
 extern "C" void pwgb_debug_set(int key, int value) {
   if (key == 1) g_tc_variant = value;
+  if (key == 2) pwgb::g_wn_variant = value;  // timing experiments of the fused WaveNet kernel (results are NOT valid)
 }
 
 extern "C" size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kernel) {

@@ -24,20 +24,28 @@ inline tma_encode_tiled_fn tma_encoder() {
   return fn;
 }
 
-// rank-4 packed tensor of `elem_bytes`-sized elements: dims[0] fastest.  Out-of-bounds box elements read as zero.
-inline int tma_make_4d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, const unsigned long long dims[4],
-                       const unsigned box[4]) {
+// packed (dense) tensor of `rank` <= 5 dimensions of `elem_bytes`-sized elements, dims[0] fastest.  Out-of-bounds box
+// elements read as zero.  Keep the innermost box extent long (>= 128 B): TMA requests whole 32-byte sectors per inner
+// row, so a 16-byte inner extent doubles the L2 traffic (measured: profiles/ncu_r2_wavenet_fused_v2_*).
+inline int tma_make(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, int rank, const void* base, const unsigned long long* dims,
+                    const unsigned* box) {
   tma_encode_tiled_fn enc = tma_encoder();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return PWGB_CUDA_ERROR;
   }
-  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
-  cuuint64_t gstr[3] = {dims[0] * elem_bytes, dims[0] * dims[1] * elem_bytes, dims[0] * dims[1] * dims[2] * elem_bytes};
-  cuuint32_t bdim[4] = {box[0], box[1], box[2], box[3]};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, dt, 4, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  unsigned long long stride = elem_bytes;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+  }
+  CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return PWGB_CUDA_ERROR;
@@ -50,6 +58,11 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
       "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");

@@ -51,6 +51,7 @@ struct WnK {
   int nslot, a_bytes, b_bytes, slot_bytes, z_bytes;
   int nset, set_cols, tmem_cols;
   int write_x, skip_init;
+  int variant;  // timing experiments only (pwgb_debug_set(2, v)): 1 no activation TMA, 2 no weight copies, 4 no gate math, 8 no epilogue memory traffic, 16 no MMAs
   unsigned idesc1, idesc2;
 };
 
@@ -144,8 +145,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
     auto stage_so = [&](int sc) {
       mbar_wait_spin(EMPTY(s), ph ^ 1);
       if (lane == 0) {
-        mbar_expect_tx(FULL(s), (unsigned)p.b_bytes);
-        bulk_g2s(smem_u32(ring + (size_t)s * p.slot_bytes + p.a_bytes), w_so + (size_t)sc * p.b_bytes, (unsigned)p.b_bytes, FULL(s));
+        if (p.variant & 2) {
+          mbar_arrive(FULL(s));
+        } else {
+          mbar_expect_tx(FULL(s), (unsigned)p.b_bytes);
+          bulk_g2s(smem_u32(ring + (size_t)s * p.slot_bytes + p.a_bytes), w_so + (size_t)sc * p.b_bytes, (unsigned)p.b_bytes, FULL(s));
+        }
       }
       __syncwarp();
       if (++s == p.nslot) { s = 0; ph ^= 1; }
@@ -164,16 +169,20 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         const int tap = is_x ? j - chunk * p.K : 0;
         mbar_wait_spin(EMPTY(s), ph ^ 1);
         if (lane == 0) {
-          // ONE tensor-map TMA per activation window: box (8 ch, 128 rows, 4 groups, hi|lo) = the 16 KB operand image;
-          // groups beyond the tensor (last conditioning chunk) arrive as zeros and count towards the transaction bytes
+          // ONE tensor-map TMA per activation window: box (128 rows x 16 B as 256 8-byte elements, 4 groups, hi|lo) = the
+          // 16 KB operand image; groups beyond the tensor (last conditioning chunk) arrive as zeros and count towards the
+          // transaction bytes
           const unsigned dstA = smem_u32(ring + (size_t)s * p.slot_bytes);
-          mbar_expect_tx(FULL(s), (unsigned)(p.a_bytes + p.b_bytes));
-          if (is_x)
-            tma_load_4d(dstA, &tm_x, 0, p.halo + t0 + (tap - p.K / 2) * p.D, chunk * 4, 2 * b, FULL(s));
-          else
-            tma_load_4d(dstA, &tm_c, 0, t0, chunk * 4, 2 * b, FULL(s));
+          const unsigned nb = ((p.variant & 1) ? 0u : (unsigned)p.a_bytes) + ((p.variant & 2) ? 0u : (unsigned)p.b_bytes);
+          if (nb) mbar_expect_tx(FULL(s), nb); else mbar_arrive(FULL(s));
+          if (!(p.variant & 1)) {
+            if (is_x)
+              tma_load_3d(dstA, &tm_x, 2 * (p.halo + t0 + (tap - p.K / 2) * p.D), chunk * 4, 2 * b, FULL(s));
+            else
+              tma_load_3d(dstA, &tm_c, 2 * t0, chunk * 4, 2 * b, FULL(s));
+          }
           const unsigned char* wsrc = is_x ? wpk + (size_t)j * p.b_bytes : w_aux + (size_t)chunk * p.b_bytes;
-          bulk_g2s(dstA + (unsigned)p.a_bytes, wsrc, (unsigned)p.b_bytes, FULL(s));
+          if (!(p.variant & 2)) bulk_g2s(dstA + (unsigned)p.a_bytes, wsrc, (unsigned)p.b_bytes, FULL(s));
         }
         __syncwarp();
         if (++s == p.nslot) { s = 0; ph ^= 1; }
@@ -205,7 +214,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         const unsigned b16 = smem_u32(ring + (size_t)s * p.slot_bytes + p.a_bytes) >> 4;
         const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + z16 + (unsigned)(sc * 4 * WN_BLK >> 4));
         const unsigned long long b_hi = hi_const | (unsigned long long)(b2_lo + b16);
-        tc_mma_tap6(d, a_hi, b_hi, z_sub, b2_sub, a_step, b2_step, p.idesc2, sc != 0 ? 1u : 0u);
+        if (!(p.variant & 16)) tc_mma_tap6(d, a_hi, b_hi, z_sub, b2_sub, a_step, b2_step, p.idesc2, sc != 0 ? 1u : 0u);
         tc_commit(EMPTY(s));
         if (++s == p.nslot) { s = 0; ph ^= 1; }
       }
@@ -225,7 +234,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + a16);
         const unsigned long long b_hi = hi_const | (unsigned long long)(b1_lo + b16);
         const bool half = j >= p.nxc * p.K && (j - p.nxc * p.K) == p.ncc - 1 && cgl <= 2;  // one K-step only
-        if (half)
+        if (p.variant & 16) {
+        } else if (half)
           tc_mma_x3_single(d, a_hi, b_hi, a_sub, b1_sub, p.idesc1, j != 0 ? 1u : 0u);
         else
           tc_mma_tap6(d, a_hi, b_hi, a_sub, b1_sub, a_step, b1_step, p.idesc1, j != 0 ? 1u : 0u);
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       tc_fence_after();
       const unsigned tacc = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(set * p.set_cols);
       bool z_free = false;
-      for (int g16 = g_begin; g16 < g_end; ++g16) {
+      for (int g16 = g_begin; g16 < ((p.variant & 4) ? g_begin : g_end); ++g16) {
         unsigned ra[16], rb[16];
         tc_ld16(tacc + (unsigned)(g16 * 16), ra);
         tc_ld16(tacc + (unsigned)(p.H + g16 * 16), rb);
@@ -293,8 +303,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
       const int t = t0 + m;
-      const bool tv = t < p.T;
-      if (!out_half && !p.skip_init) {
+      const bool tv = t < p.T && !(p.variant & 8);
+      if (!out_half && !p.skip_init && !(p.variant & 8)) {
         // L2 prefetch of the skip lines two tiles ahead (one 128-byte line per column and warp)
         const int tl = tile + 2 * (int)gridDim.x;
         if (tl < p.total_tiles) {
@@ -444,6 +454,8 @@ __global__ void wn_first_conv_kernel(const float* __restrict__ z, int cin, const
   }
 }
 
+int g_wn_variant = 0;
+
 static int wn_plan(const pwgb_wnstack_desc* d, WnK& p, size_t& smem_bytes) {
   if (!d || d->batch < 0 || d->t <= 0 || d->kernel <= 0 || d->kernel % 2 == 0 || d->halo < 0) return 0;
   const int R = d->residual_channels, G = d->gate_channels, S = d->skip_channels, A = d->aux_channels;
@@ -493,6 +505,7 @@ static int wn_plan(const pwgb_wnstack_desc* d, WnK& p, size_t& smem_bytes) {
   p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N2 >> 3) << 17) | ((128u >> 4) << 24);
   p.write_x = 1;
   p.skip_init = 0;
+  p.variant = g_wn_variant;
   return 1;
 }
 
@@ -599,15 +612,17 @@ extern "C" int pwgb_wnstack_layer_forward(const pwgb_wnstack_desc* d, int dilati
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  // tensor maps of the packed streams: dims (8 ch, rows, 8-channel groups, batch x hi|lo), box = one operand window
+  // tensor maps of the packed streams.  A plane ([rows][8 ch] bf16) is contiguous, so it is described as a vector of
+  // 8-byte elements (2 per row): dims (2 * rows, 8-channel groups, batch x hi|lo), box (256, 4, 2) = one 16 KB operand
+  // window with a 2 KB inner extent
   CUtensorMap tm_x, tm_c;
   {
-    const unsigned long long dx[4] = {8ull, (unsigned long long)p.Tp, (unsigned long long)p.ngx, 2ull * p.B};
-    const unsigned long long dc[4] = {8ull, (unsigned long long)p.Tc, (unsigned long long)p.ngc, 2ull * p.B};
-    const unsigned box[4] = {8u, (unsigned)WN_TT, 4u, 2u};
-    int rc = tma_make_4d(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xpk_in, dx, box);
+    const unsigned long long dx[3] = {2ull * p.Tp, (unsigned long long)p.ngx, 2ull * p.B};
+    const unsigned long long dc[3] = {2ull * p.Tc, (unsigned long long)p.ngc, 2ull * p.B};
+    const unsigned box[3] = {2u * WN_TT, 4u, 2u};
+    int rc = tma_make(&tm_x, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, 3, xpk_in, dx, box);
     if (rc) return rc;
-    rc = tma_make_4d(&tm_c, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cpk, dc, box);
+    rc = tma_make(&tm_c, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, 3, cpk, dc, box);
     if (rc) return rc;
   }
   wavenet_fused_kernel<<<(unsigned)grid, WN_THREADS, bytes, (cudaStream_t)stream>>>(

@@ -449,3 +449,54 @@ def test_graphed_decode_matches_eager(dev):
         assert torch.equal(ours[i], ref), i
     part = decode.decode_utterances(m, mels, rank=1, world=2, use_graphs=False)
     assert sorted(part) == [1, 3]
+
+
+def test_decoder_pcm16_normalize_and_buckets(dev):
+    """Decode driver (bin/decode.py:214-243 on the GPU): on-device normalize_before + transpose, equal-length
+    batching bit-identical to ``inference``, PCM16 by libsndfile's rule, async D2H; bucketed mode is exact away from
+    the utterance end."""
+    import numpy as np
+
+    from parallelwavegan_b200 import decode
+
+    meta, g, m = _load_mirror("hifigan_small", dev)
+    m.remove_weight_norm()
+    m.register_buffer("mean", synth.randn((80,), 70, 0.3).to(dev))
+    m.register_buffer("scale", (synth.randn((80,), 71, 0.1).abs() + 0.5).to(dev))
+    mels = [synth.randn((n, 80), 900 + k).numpy() for k, n in enumerate((12, 20, 12, 31, 20, 12))]
+    dec = decode.Decoder(m, use_graphs=True, max_batch=2)
+    wav = dec.decode(mels, normalize_before=True, to_pcm16=True)
+    flt = dec.decode(mels, normalize_before=True, to_pcm16=False)
+    for i, mel in enumerate(mels):
+        with torch.no_grad():
+            ref = m.inference(torch.from_numpy(mel).to(dev), normalize_before=True)
+        assert torch.equal(flt[i], ref), i
+        exp = np.clip(np.rint(ref[:, 0].cpu().numpy() * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+        assert wav[i].dtype == np.int16 and wav[i].shape == exp.shape and np.array_equal(wav[i], exp), i
+    # length buckets (approximate at the tail only): compare everything further than one receptive field from the end
+    decb = decode.Decoder(m, use_graphs=False, max_batch=8, exact=False, bucket_frames=16)
+    fb = decb.decode(mels, normalize_before=True, to_pcm16=False)
+    hop = 256
+    for i, mel in enumerate(mels):
+        n = mel.shape[0] * hop
+        assert fb[i].shape == flt[i].shape
+        keep = n - 6 * hop
+        assert rel_l2(fb[i][:keep].cpu(), flt[i][:keep].cpu()) < 1e-5, i
+
+
+def test_decoder_parallel_wavegan_path(dev):
+    """Decoder dispatch for ParallelWaveGANGenerator: replicate-padded conditioning + noise as static graph inputs;
+    with the noise pinned the result equals ``inference(c, x)``."""
+    from parallelwavegan_b200 import decode
+
+    meta, g, m = _load_mirror("pwg_small", dev)
+    hop = m.upsample_factor
+    mels = [synth.randn((n, m.aux_channels), 950 + k) for k, n in enumerate((9, 14, 9))]
+    noises = {i: synth.randn((mel.shape[0] * hop, 1), 980 + i) for i, mel in enumerate(mels)}
+    dec = decode.Decoder(m, use_graphs=True, max_batch=4, seed=3)
+    out = dec.decode(mels, to_pcm16=False, noises=noises)
+    for i, mel in enumerate(mels):
+        with torch.no_grad():
+            ref = m.inference(c=mel.to(dev), x=noises[i].to(dev))
+        assert tuple(out[i].shape) == tuple(ref.shape)
+        assert rel_l2(out[i].cpu(), ref.cpu()) < 1e-6, i

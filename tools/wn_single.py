@@ -13,6 +13,11 @@ from parallelwavegan_b200 import layers, ops
 from parallelwavegan_b200 import synth_weights as synth
 
 dev = torch.device("cuda:0")
+if os.environ.get("PWGB_WN_VARIANT"):
+    from parallelwavegan_b200 import capi
+
+    capi.lib().pwgb_debug_set(2, int(os.environ["PWGB_WN_VARIANT"]))  # timing experiments: outputs are not valid
+    print("WN variant", os.environ["PWGB_WN_VARIANT"])
 try:
     HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
