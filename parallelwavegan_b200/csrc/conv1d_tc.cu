@@ -45,7 +45,9 @@ struct TcK {
   int tma_act;           // 1: raw stages are filled by cp.async.bulk row copies (warp W_LDA), 0: by cp.async (producers)
   int nmma;              // MMA issuer warps: 2 = one per 128-row m-tile (MT == 2)
   int shuffle_vec;       // pixel-shuffle epilogue may use 16-byte stores
-  int nco;               // column chunks of Cout channels sharing this launch (conv-transpose: cout * stride > 256)
+  int nco;               // column chunks of Cout channels sharing this launch (conv-transpose: cout * stride > 256; wide / grouped convs)
+  int cpg;               // column chunks per group (grouped convs: chunk cc reads the input channels of group cc / cpg)
+  long long xgs;         // input offset between groups (elements): cin_per_group * T_in, 0 for dense convs
   long long xbs, ybs, rbs;
   unsigned idesc;
   int tmem_cols;
@@ -63,10 +65,13 @@ struct TcK {
 // w (rows, cin_real, K) fp32 -> rows [co_begin, co_begin + rows) of the operand image
 // [chunk][tap][hi|lo][ci8][co (cout_total)][8] bf16 (the smem image of a stage); input channels
 // >= cin_real (zero padding up to cin_pad, a multiple of KC) pack as zeros.
-__global__ void tc_pack_weight_kernel(const float* __restrict__ w, uint4* __restrict__ packed, int cin_real,
-                                      int cin_pad, int rows, int K, int co_begin, int cout_total) {
+__global__ void tc_pack_weight_kernel(const float* __restrict__ w, uint4* __restrict__ packed, int cin_real, int cin_pad, int rows,
+                                      int K, int co_begin, int cout_total, int chunk) {
+  // chunk > 0: `rows` output channels are split into consecutive images of `chunk` columns each (wide / grouped convs:
+  // one image per (group, column chunk)); chunk == 0: rows [co_begin, co_begin + rows) of ONE image of cout_total columns
   const int nchunks = cin_pad / KC;
   const long long n = (long long)nchunks * K * (KC / 8) * rows;
+  const long long img16 = (long long)nchunks * K * 2 * (KC / 8) * (chunk > 0 ? chunk : cout_total);  // uint4 per image
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int co = (int)(i % rows);
     long long t = i / rows;
@@ -82,9 +87,12 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w, uint4* __rest
     }
     uint4 hi, lo;
     split8(v, hi, lo);
-    const long long base = ((long long)(c * K + k) * 2) * (KC / 8) * cout_total;
-    packed[base + (long long)g * cout_total + co_begin + co] = hi;
-    packed[base + (long long)(KC / 8) * cout_total + (long long)g * cout_total + co_begin + co] = lo;
+    const int ct = chunk > 0 ? chunk : cout_total;
+    const int col = chunk > 0 ? co % chunk : co_begin + co;
+    uint4* img = packed + (chunk > 0 ? (long long)(co / chunk) * img16 : 0);
+    const long long base = ((long long)(c * K + k) * 2) * (KC / 8) * ct;
+    img[base + (long long)g * ct + col] = hi;
+    img[base + (long long)(KC / 8) * ct + (long long)g * ct + col] = lo;
   }
 }
 
@@ -94,14 +102,14 @@ void tc_pack_rows(const float* w, void* packed, int cin_real, int cin_pad, int r
   int blocks = (int)((n + 127) / 128);
   if (blocks > 8192) blocks = 8192;
   if (blocks < 1) blocks = 1;
-  tc_pack_weight_kernel<<<blocks, 128, 0, st>>>(w, (uint4*)packed, cin_real, cin_pad, rows, K, co_begin, cout_total);
+  tc_pack_weight_kernel<<<blocks, 128, 0, st>>>(w, (uint4*)packed, cin_real, cin_pad, rows, K, co_begin, cout_total, 0);
 }
 
 // Generic epilogue for W (16 or 32) accumulator columns of one row: every independent global load
 // (residual, and the accumulate read-modify-write) is issued before the TMEM load is waited for, so
 // W (2W) requests per thread are in flight.
 template <int W>
-__device__ __forceinline__ void epi_generic(const TcK& p, unsigned taddr, const float* __restrict__ bias_s, int col,
+__device__ __forceinline__ void epi_generic(const TcK& p, unsigned taddr, const float* bias_s, int col,
                                             const float* rq, float* yq, long long st, bool tv) {
   unsigned r[W];
   {
@@ -131,17 +139,17 @@ __device__ __forceinline__ void epi_generic(const TcK& p, unsigned taddr, const 
     for (int j = 0; j < W; ++j, q2 += st) yv[j] = *q2;
 #pragma unroll
     for (int j = 0; j < W; ++j, q += st) {
-      float v = __uint_as_float(r[j]) + bias_s[col + j];
+      float v = __uint_as_float(r[j]) + (bias_s ? bias_s[col + j] : 0.f);
       if (p.post_act != PWGB_ACT_NONE) v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
       *q = (v + rv[j]) * p.out_scale + yv[j];
     }
   } else if (p.post_act == PWGB_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < W; ++j, q += st) *q = (__uint_as_float(r[j]) + bias_s[col + j] + rv[j]) * p.out_scale;
+    for (int j = 0; j < W; ++j, q += st) *q = (__uint_as_float(r[j]) + (bias_s ? bias_s[col + j] : 0.f) + rv[j]) * p.out_scale;
   } else {
 #pragma unroll
     for (int j = 0; j < W; ++j, q += st) {
-      float v = __uint_as_float(r[j]) + bias_s[col + j];
+      float v = __uint_as_float(r[j]) + (bias_s ? bias_s[col + j] : 0.f);
       v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
       *q = (v + rv[j]) * p.out_scale;
     }
@@ -342,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int t0 = (tr - b * p.tiles_per_seq) * TT;
       const unsigned raw = smem_u32(raw_buf + (size_t)(q % p.ns) * p.raw_bytes);
       if (c < p.nchunks) {
-        const float* xc = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in;
+        const float* xc = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in + (p.nco > 1 ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
         for (int r = tid; r < p.R; r += NPROD) {
           long long ts;
           if (p.win_mode) {
@@ -423,7 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int tr = p.nco > 1 ? tile % pct : tile;  // tile within its column chunk
       const int b = tr / p.tiles_per_seq;
       const int t0 = (tr - b * p.tiles_per_seq) * TT;
-      const float* xb = x + (long long)b * p.xbs;
+      const float* xb = x + (long long)b * p.xbs + (p.nco > 1 ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
       for (int c = 0; c < nc_total; ++c, ++ca) {
         const int buf = ca % p.na;
         mbar_wait(A_EMPTY(buf), ((ca / p.na) & 1) ^ 1);
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int col = col_begin + (i - mt * ncol);
             const int tp = tt0 + mt * 128 + ew * 32;
             if (tp < p.T_out) {
-              const long long off = (long long)(p.co_off + col) * st + tp;
+              const long long off = (long long)(p.co_off + (p.nco > 1 ? (tl / pct) * p.Cout : 0) + col) * st + tp;
               if (res) prefetch_l2(res + (long long)bb * p.rbs + off);
               if (p.accumulate) prefetch_l2(y + (long long)bb * p.ybs + off);
             }
@@ -573,11 +581,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         } else {
           // generic: running 64-bit pointers (2 integer instructions per element instead of a full
           // address recomputation), every independent load of a 16-column group issued before use
-          float* yq = y + (long long)b * p.ybs + (long long)(p.co_off + col_begin) * st + t;
-          const float* rq = res ? res + (long long)b * p.rbs + (long long)(p.co_off + col_begin) * st + t : nullptr;
+          float* yq = y + (long long)b * p.ybs + (long long)(co_base + col_begin) * st + t;
+          const float* rq = res ? res + (long long)b * p.rbs + (long long)(co_base + col_begin) * st + t : nullptr;
+          // several column chunks per launch: the chunk's bias comes straight from global memory (L1-resident)
+          const float* bptr = p.nco > 1 ? (bias ? bias + co_base : nullptr) : bias_s;
           // (32-column groups were tried: they spill at the register budget of this block size)
           for (int col = col_begin; col < col_end; col += 16, yq += 16 * st) {
-            epi_generic<16>(p, tacc + (unsigned)(mt * p.Cout + col), bias_s, col, rq, yq, st, tv);
+            epi_generic<16>(p, tacc + (unsigned)(mt * p.Cout + col), bptr, col, rq, yq, st, tv);
             if (rq) rq += 16 * st;
           }
         }
@@ -621,7 +631,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             end = ts0 + p.R4 < p.T_in ? ts0 + p.R4 : p.T_in;
             rowstride = p.T_in;
             dst_off = start - ts0;
-            src = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in;
+            src = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in + (p.nco > 1 ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
           } else {
             start = t0;
             end = t0 + TT < p.T_out ? t0 + TT : p.T_out;
@@ -710,6 +720,8 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
   p.variant = g_tc_variant;
   p.co_off = 0;
   p.nco = 1;
+  p.cpg = 1;
+  p.xgs = 0;
   const int P = d->period < 1 ? 1 : d->period;
   if (d->stride != 1 || d->groups != 1 || P != 1) return 0;
   if (d->cin % KC != 0 || d->cout % 16 != 0 || d->cout < 16 || d->cout > 256) return 0;
@@ -907,14 +919,13 @@ extern "C" int pwgb_conv1d_tc_pack_weight_grouped(const float* w, int cin_g, int
                  "conv1d_tc_pack_weight: channels per group must be a multiple of %d", KC);
   const int chunk = tc_cout_chunk(cout / groups);
   PWGB_CHECK_ARG(chunk > 0, "conv1d_tc_pack_weight: cout / groups must be a multiple of 16");
-  const size_t img = (size_t)(cin_g / KC) * kernel * 2 * (KC / 8) * chunk * 16;
-  for (int co = 0; co < cout; co += chunk) {
-    tc_pack_rows(w + (size_t)co * cin_g * kernel, (unsigned char*)packed + (size_t)(co / chunk) * img, cin_g, cin_g, chunk, kernel,
-                 0, chunk, (cudaStream_t)stream);
-    int rc = check_launch("tc_pack_weight_kernel");
-    if (rc) return rc;
-  }
-  return PWGB_OK;
+  // ONE launch packs every (group, column chunk) image: row co of w lands in image co / chunk, column co % chunk
+  const long long n = (long long)(cin_g / KC) * kernel * (KC / 8) * cout;
+  int blocks = (int)((n + 127) / 128);
+  if (blocks > 8192) blocks = 8192;
+  if (blocks < 1) blocks = 1;
+  tc_pack_weight_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(w, (uint4*)packed, cin_g, cin_g, cout, kernel, 0, chunk, chunk);
+  return check_launch("tc_pack_weight_kernel");
 }
 
 extern "C" int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream) {
@@ -925,7 +936,9 @@ extern "C" int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int
 // (one launch each, re-reading x): chunk = largest multiple of 16 that is <= 256 and divides cout.
 static int tc_cout_chunk(int cout) {
   if (cout <= 256) return cout;
-  for (int c = 256; c >= 16; c -= 16)
+  // wide layers (discriminator towers, 512 / 1024 channels on short sequences): 128-column chunks double the number
+  // of (chunk, batch, time tile) work items of the single launch, i.e. the number of SMs that have work
+  for (int c = 128; c >= 16; c -= 16)
     if (cout % c == 0) return c;
   return 0;
 }
@@ -958,23 +971,27 @@ extern "C" int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x,
   c.cout = chunk;
   c.cin = cin_g;
   c.groups = 1;
-  const size_t img = (size_t)(cin_g / KC) * d->kernel * 2 * (KC / 8) * chunk * 16;
-  for (int g = 0; g < G; ++g) {
-    for (int co = 0; co < cout_g; co += chunk) {
-      TcK p;
-      size_t bytes = 0;
-      tc_plan(&c, p, bytes);
-      p.co_off = g * cout_g + co;
-      p.xbs = (long long)d->cin * (d->pre_gate ? 2 : 1) * d->t_in;
-      p.ybs = (long long)d->cout * d->t_out;
-      p.rbs = p.ybs;
-      const size_t iidx = (size_t)g * (cout_g / chunk) + co / chunk;
-      int rc = tc_launch(p, bytes, x + (size_t)g * cin_g * d->t_in, (const unsigned char*)packed_w + iidx * img, bias, residual,
-                         y, (cudaStream_t)stream);
-      if (rc) return rc;
-    }
+  // ONE launch walks every (group, column chunk, batch, time tile) item: the operand images of the chunks are
+  // consecutive in `packed_w` (group-major), chunk cc writes output channels [cc * chunk, (cc + 1) * chunk) and reads
+  // the input channels of group cc / (cout_g / chunk)
+  TcK p;
+  size_t bytes = 0;
+  tc_plan(&c, p, bytes);
+  const int nco = G * (cout_g / chunk);
+  if ((long long)p.total_tiles * nco > 0x7fffffffLL) {
+    set_error("conv1d_tc: too many tiles");
+    return PWGB_UNSUPPORTED;
   }
-  return PWGB_OK;
+  p.xbs = (long long)d->cin * (d->pre_gate ? 2 : 1) * d->t_in;
+  p.ybs = (long long)d->cout * d->t_out;
+  p.rbs = p.ybs;
+  if (nco > 1) {
+    p.nco = nco;
+    p.cpg = cout_g / chunk;
+    p.xgs = G > 1 ? (long long)cin_g * d->t_in : 0;
+    p.total_tiles *= nco;
+  }
+  return tc_launch(p, bytes, x, packed_w, bias, residual, y, (cudaStream_t)stream);
 }
 
 // ======================================================================================
@@ -1109,6 +1126,7 @@ constexpr int WT_THREADS = 160;
 
 struct WtK {
   int B, Cin, Cout, T_in, T_out, K, D, padL;
+  int G, Cin_g, Cout_g;  // groups: an M tile never straddles two groups (rows beyond the group's channels are zero)
   float x_slope, g_slope;
   int chunks_per_seq, nsplit, RX, ntg, tg;  // tg = taps per CTA (<= WT_TG), ntg = tap groups
   unsigned idesc;
@@ -1125,8 +1143,11 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(b_buf + 2 * b_img);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int co0 = blockIdx.x * 128;
-  const int ci0 = (blockIdx.y / p.ntg) * WT_NC;
+  const int tpg = (p.Cout_g + 127) / 128;  // M tiles per group
+  const int grp = blockIdx.x / tpg;
+  const int co0 = grp * p.Cout_g + (blockIdx.x - grp * tpg) * 128;
+  const int co_end = (grp + 1) * p.Cout_g;
+  const int ci0 = (blockIdx.y / p.ntg) * WT_NC;  // within the group
   const int k0 = (blockIdx.y % p.ntg) * p.tg;
   const int ntap = min(p.tg, p.K - k0);
   const int split = blockIdx.z;
@@ -1163,7 +1184,7 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
 #pragma unroll 4
         for (int g = 0; g < 16; ++g) {
           float u[8];
-          const bool cok = ok && (co0 + g * 8 < p.Cout);  // Cout % 8 == 0: whole 8-channel groups are in or out
+          const bool cok = ok && (co0 + g * 8 < co_end);  // Cout_g % 8 == 0: whole 8-channel groups are in or out
 #pragma unroll
           for (int j = 0; j < 8; ++j) u[j] = cok ? lrelu(__ldg(gb + (long long)(g * 8 + j) * p.T_out + t), p.g_slope) : 0.f;
           uint4 hi, lo;
@@ -1173,7 +1194,7 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
         }
       }
       // activation tile: rows t0 + k0*D - pad ... (+ RX)
-      const float* xb = x + ((long long)b * p.Cin + ci0) * p.T_in;
+      const float* xb = x + ((long long)b * p.Cin + grp * p.Cin_g + ci0) * p.T_in;
       for (int r = tid; r < p.RX; r += 128) {
         const long long ts = (long long)t0 + (long long)k0 * p.D - p.padL + r;
         const bool ok = ts >= 0 && ts < p.T_in;
@@ -1195,8 +1216,8 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
     mbar_wait(ACC, 0);
     tc_fence_after();
     const int co = co0 + warp * 32 + lane;
-    const bool co_ok = co < p.Cout;
-    float* dst = part + (((long long)split * p.Cout + (co_ok ? co : 0)) * p.Cin + ci0) * p.K + k0;
+    const bool co_ok = co < co_end;
+    float* dst = part + (((long long)split * p.Cout + (co_ok ? co : 0)) * p.Cin_g + ci0) * p.K + k0;
     for (int tp = 0; tp < ntap; ++tp) {
       for (int c16 = 0; c16 < WT_NC; c16 += 16) {
         unsigned r[16];
@@ -1250,8 +1271,10 @@ __global__ void wt_reduce_kernel(const float* __restrict__ part, float* __restri
 }
 
 static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
-  if (!d || d->stride != 1 || d->groups != 1 || (d->period > 1) || d->pre_gate || d->pad_mode != PWGB_PAD_ZERO) return 0;
-  if (d->cout % 8 != 0 || d->cout < 32 || d->cin % WT_NC != 0 || d->kernel <= 0 || d->dilation <= 0) return 0;
+  if (!d || d->stride != 1 || d->groups < 1 || (d->period > 1) || d->pre_gate || d->pad_mode != PWGB_PAD_ZERO) return 0;
+  if (d->cin % d->groups || d->cout % d->groups) return 0;
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  if (cout_g % 8 != 0 || cout_g < 32 || cin_g % WT_NC != 0 || d->kernel <= 0 || d->dilation <= 0) return 0;
   if (d->t_valid > 0 && d->t_valid != d->t_in) return 0;
   p.B = d->batch;
   p.Cin = d->cin;
@@ -1261,6 +1284,9 @@ static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
   p.K = d->kernel;
   p.D = d->dilation;
   p.padL = d->pad_left;
+  p.G = d->groups;
+  p.Cin_g = cin_g;
+  p.Cout_g = cout_g;
   p.x_slope = d->pre_slope;
   p.g_slope = 1.f;
   p.chunks_per_seq = ceil_div(d->t_out, WT_TK);
@@ -1274,7 +1300,7 @@ static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
   p.tg = tg;
   p.ntg = ceil_div(d->kernel, tg);
   const long long items = (long long)p.B * p.chunks_per_seq;
-  const long long gxy = (long long)ceil_div(d->cout, 128) * (d->cin / WT_NC) * p.ntg;
+  const long long gxy = (long long)d->groups * ceil_div(cout_g, 128) * (cin_g / WT_NC) * p.ntg;
   long long ns = (2 * 296 + gxy - 1) / gxy;
   if (ns > items) ns = items;
   if (ns > 64) ns = 64;
@@ -1295,7 +1321,7 @@ extern "C" int pwgb_conv1d_wgrad_tc_supported(const pwgb_conv1d_desc* d) {
 extern "C" size_t pwgb_conv1d_wgrad_tc_workspace(const pwgb_conv1d_desc* d) {
   pwgb::WtK p;
   if (!pwgb::wt_plan(d, p)) return 0;
-  return (size_t)p.nsplit * d->cout * d->cin * d->kernel * sizeof(float);
+  return (size_t)p.nsplit * d->cout * (d->cin / d->groups) * d->kernel * sizeof(float);
 }
 
 extern "C" int pwgb_conv1d_wgrad_tc(const pwgb_conv1d_desc* d, const float* x, const float* gy, float g_slope, float* dw,
@@ -1308,7 +1334,7 @@ extern "C" int pwgb_conv1d_wgrad_tc(const pwgb_conv1d_desc* d, const float* x, c
   const size_t need = pwgb_conv1d_wgrad_tc_workspace(d);
   PWGB_CHECK_ARG(ws_bytes >= need, "conv1d_wgrad_tc: workspace too small (%zu < %zu)", ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
-  const long long n = (long long)d->cout * d->cin * d->kernel;
+  const long long n = (long long)d->cout * (d->cin / d->groups) * d->kernel;
   if (p.B == 0 || p.T_out == 0) {
     cudaMemsetAsync(dw, 0, n * sizeof(float), st);
     return PWGB_OK;
@@ -1323,7 +1349,7 @@ extern "C" int pwgb_conv1d_wgrad_tc(const pwgb_conv1d_desc* d, const float* x, c
     }
     attr_set = true;
   }
-  dim3 grid(ceil_div(d->cout, 128), (d->cin / WT_NC) * p.ntg, p.nsplit);
+  dim3 grid(p.G * ceil_div(p.Cout_g, 128), (p.Cin_g / WT_NC) * p.ntg, p.nsplit);
   wgrad_tc_kernel<<<grid, WT_THREADS, smem, st>>>(p, x, gy, (float*)ws);
   int rc = check_launch("wgrad_tc_kernel");
   if (rc) return rc;

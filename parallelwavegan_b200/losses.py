@@ -23,18 +23,37 @@ def stft(x, fft_size, hop_size, win_length, window):
     return ax
 
 
+def _stft_loss_terms(x_mag, y_mag):
+    """[sc, mag] of losses/stft_loss.py:50-61, 71-82 on materialised magnitudes -- pwgb_stft_loss_terms."""
+    import ctypes as C
+
+    from . import capi
+
+    if x_mag.shape != y_mag.shape:
+        raise PwgbError("stft loss: magnitude shapes differ")
+    if torch.is_grad_enabled() and (x_mag.requires_grad or y_mag.requires_grad):
+        raise PwgbError("the standalone magnitude losses have no backward kernel; train through STFTLoss / MultiResolutionSTFTLoss")
+    xm, ym = ops._dev(x_mag, "x_mag"), ops._dev(y_mag, "y_mag")
+    out = torch.zeros(2, device=xm.device, dtype=torch.float32)
+    sums = torch.empty(3, device=xm.device, dtype=torch.float64)
+    ws = torch.empty(3 * 1024, device=xm.device, dtype=torch.float64)
+    rc = capi.lib().pwgb_stft_loss_terms(ops._p(xm), ops._p(ym), xm.numel(), 1.0, 0, ops._p(out), ops._p(sums), ops._p(ws), 3 * 1024, ops._stream())
+    capi.check(rc, "pwgb_stft_loss_terms")
+    return out
+
+
 class SpectralConvergenceLoss(torch.nn.Module):
-    """losses/stft_loss.py:43-61 on precomputed magnitudes (kept for API parity)."""
+    """losses/stft_loss.py:43-61 on precomputed magnitudes (B, #frames, #bins): ||y - x||_F / ||y||_F."""
 
     def forward(self, x_mag, y_mag):
-        raise PwgbError("SpectralConvergenceLoss on materialised magnitudes is not part of the fused path; use STFTLoss / MultiResolutionSTFTLoss")
+        return _stft_loss_terms(x_mag, y_mag)[0]
 
 
 class LogSTFTMagnitudeLoss(torch.nn.Module):
-    """losses/stft_loss.py:64-82 (kept for API parity)."""
+    """losses/stft_loss.py:64-82 on precomputed magnitudes: mean |log y - log x|."""
 
     def forward(self, x_mag, y_mag):
-        raise PwgbError("LogSTFTMagnitudeLoss on materialised magnitudes is not part of the fused path; use STFTLoss / MultiResolutionSTFTLoss")
+        return _stft_loss_terms(x_mag, y_mag)[1]
 
 
 class STFTLoss(torch.nn.Module):

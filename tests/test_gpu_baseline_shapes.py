@@ -199,3 +199,54 @@ def test_wgrad_tc_c5_sizes(dev, cin, cout, k, dil, T, B):
     with torch.enable_grad():
         F.conv1d(x, w, None, padding=pad, dilation=dil).backward(gy)
     _check(dw.cpu(), w.grad, f"wgrad_tc {cin}->{cout} k{k}", TC_TOL)
+
+
+@pytest.mark.parametrize(
+    "cin,cout,k,groups,T,B,expect",
+    [
+        (1024, 1024, 41, 16, 128, 16, "conv1d_wgrad_tc"),  # MSD layer 5 (grouped, stride 1) at the C5 batch
+        (256, 128, 21, 4, 4096, 4, "conv1d_wgrad_tc"),     # MSD layer 1 after space-to-depth (cin_g 64, cout_g 32)
+        (1, 128, 15, 1, 8192, 16, "conv1d_wgrad"),         # MSD input conv: narrow kernel, 131k-long reduction
+        (1024, 1, 3, 1, 128, 16, "conv1d_wgrad"),          # logit conv: narrow kernel
+    ],
+)
+def test_wgrad_grouped_and_narrow_c5_sizes(dev, cin, cout, k, groups, T, B, expect):
+    from parallelwavegan_b200 import ops
+
+    pad = (k - 1) // 2
+    x = synth.randn((B, cin, T), 18)
+    gy = synth.randn((B, cout, T), 19)
+    ops.PROFILE = []
+    try:
+        dw = ops.conv1d_wgrad(x.to(dev), gy.to(dev), (cout, cin // groups, k), padding=pad, groups=groups)
+        torch.cuda.synchronize()
+        assert ops.PROFILE[0][0] == expect
+    finally:
+        ops.PROFILE = None
+    w = torch.zeros(cout, cin // groups, k, requires_grad=True)
+    with torch.enable_grad():
+        F.conv1d(x, w, None, padding=pad, groups=groups).backward(gy)
+    _check(dw.cpu(), w.grad, f"wgrad {cin}->{cout} k{k} g{groups}", TC_TOL)
+
+
+def test_wide_short_convs_single_launch(dev):
+    """1024-channel discriminator layers on ~100-sample rows: every (group, 128-column chunk, batch, tile) item runs in
+    ONE launch (dense 1024 -> 1024 k5 as the MPD does it on the flat period view, and the grouped MSD k41 layer)."""
+    from parallelwavegan_b200 import capi, ops
+
+    for cin, cout, k, groups, dil, T, B in ((1024, 1024, 5, 1, 2, 104, 16), (1024, 1024, 41, 16, 1, 128, 16), (512, 1024, 3, 1, 1, 52, 3)):
+        pad = (k - 1) // 2 * dil
+        x = synth.randn((B, cin, T), 28)
+        w = synth.randn((cout, cin // groups, k), 29, 1.0 / (cin // groups * k) ** 0.5)
+        b = synth.randn((cout,), 30, 0.1)
+        capi.reset_launch_count()
+        ops.PROFILE = []
+        try:
+            y = ops.conv1d(x.to(dev), w.to(dev), b.to(dev), padding=pad, dilation=dil, groups=groups, post_act="lrelu", post_slope=0.1)
+            torch.cuda.synchronize()
+            assert ops.PROFILE[0][0] == "conv1d_tc"
+        finally:
+            ops.PROFILE = None
+        assert capi.launch_count() == 2  # weight pack + ONE conv launch
+        ref = F.leaky_relu(F.conv1d(x, w, b, padding=pad, dilation=dil, groups=groups), 0.1)
+        _check(y.cpu(), ref, f"wide conv {cin}->{cout} k{k} g{groups}", TC_TOL)
