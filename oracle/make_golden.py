@@ -221,14 +221,16 @@ def summarize(outs):
     return arrays, shapes
 
 
-def gen_discriminator(name, cls_name, kwargs, B, T, seed, gain, train_mode=False):
+def gen_discriminator(name, cls_name, kwargs, B, T, seed, gain, train_mode=False, np_seed=None, keep=()):
     import parallel_wavegan.models as M
 
     torch.manual_seed(0)
     m = getattr(M, cls_name)(**json.loads(json.dumps(kwargs)))
     m.train(train_mode)
-    spec, sd = load_synth(m, seed, gain)
+    spec, sd = load_synth(m, seed, gain, keep=keep)
     x = synth.randn((B, 1, T), seed + 1, 0.5)
+    if np_seed is not None:  # StyleMelGANDiscriminator draws its window positions with np.random.randint (style_melgan.py:330)
+        np.random.seed(np_seed)
     with torch.no_grad():
         outs = m(x)
     if isinstance(outs, torch.Tensor):
@@ -242,7 +244,7 @@ def gen_discriminator(name, cls_name, kwargs, B, T, seed, gain, train_mode=False
             if k.endswith("weight_u"):
                 arrays["u__" + k.replace(".", "__")] = v
     meta = dict(kind="discriminator", cls=cls_name, kwargs=kwargs, spec=spec, seed=seed, gain=gain, checksum=synth.checksum(sd),
-                x_shape=list(x.shape), x_seed=seed + 1, x_scale=0.5, shapes=shapes, train_mode=train_mode)
+                x_shape=list(x.shape), x_seed=seed + 1, x_scale=0.5, shapes=shapes, train_mode=train_mode, np_seed=np_seed)
     save(name, meta, **arrays)
 
 
@@ -285,7 +287,11 @@ def gen_losses():
 
 def main():
     import_reference()
+    if "style_disc" in sys.argv[1:]:  # regenerate only the fixture added in round 2
+        gen_discriminator("style_melgan_disc", "StyleMelGANDiscriminator", {}, B=2, T=6000, seed=65, gain=1.4, np_seed=21, keep=("_filter",))
+        return
     gen_losses()
+    gen_discriminator("style_melgan_disc", "StyleMelGANDiscriminator", {}, B=2, T=6000, seed=65, gain=1.4, np_seed=21, keep=("_filter",))
     gen_discriminator("hifigan_msmpd_v1", "HiFiGANMultiScaleMultiPeriodDiscriminator", {}, B=2, T=8192, seed=61, gain=1.4)
     gen_discriminator("hifigan_msmpd_v1_train", "HiFiGANMultiScaleMultiPeriodDiscriminator", {}, B=1, T=4099, seed=62, gain=1.4, train_mode=True)
     gen_discriminator("melgan_msd", "MelGANMultiScaleDiscriminator", dict(downsample_scales=[4, 4, 4], max_downsample_channels=512), B=2, T=16200, seed=63, gain=1.4)

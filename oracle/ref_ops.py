@@ -688,6 +688,24 @@ def melgan_msd(w, x, scales=3, **kw):
     return outs
 
 
+def style_melgan_discriminator(w, x, starts, window_sizes=(512, 1024, 2048, 4096),
+                               pqmf_params=((1, None, None, None), (2, 62, 0.26700, 9.0), (4, 62, 0.14200, 9.0), (8, 62, 0.07949, 9.0)),
+                               downsample_scales=(4, 4, 4, 1), max_ch=512):
+    """StyleMelGANDiscriminator.forward (style_melgan.py:310-337).  ``starts``: the window positions in call order
+    (repeats * len(window_sizes) values of ``np.random.randint(T - ws)``)."""
+    outs = []
+    n = len(window_sizes)
+    for r, s0 in enumerate(starts):
+        idx = r % n
+        ws = window_sizes[idx]
+        x_ = x[:, :, s0 : s0 + ws]
+        if idx > 0:
+            an, _ = pqmf_filters(*pqmf_params[idx])
+            x_ = pqmf_analysis(x_, an)
+        outs.append(melgan_discriminator(w, f"discriminators.{idx}", x_, downsample_scales=downsample_scales, max_ch=max_ch))
+    return outs
+
+
 def pwg_discriminator(w, x, layers=10, kernel_size=3, slope=0.2):
     """ParallelWaveGANDiscriminator.forward (parallel_wavegan.py:337-349): dilation i for layer i>0."""
     for i in range(layers - 1):

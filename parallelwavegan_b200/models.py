@@ -1030,3 +1030,71 @@ class MelGANMultiScaleDiscriminator(torch.nn.Module, _NormMixin):
                 m.weight.data.normal_(0.0, 0.02)
 
         self.apply(_reset_parameters)
+
+
+class StyleMelGANDiscriminator(torch.nn.Module, _NormMixin):
+    """models/style_melgan.py:243-378: random-window discriminators -- for every window size a random crop of the
+    waveform (``np.random.randint(T - ws)``, the reference's host RNG call, style_melgan.py:330) goes through a PQMF
+    analysis bank (1, 2, 4, 8 sub-bands) into a MelGANDiscriminator; repeated ``repeats`` times.  The crop is a view,
+    the analysis one strided FIR launch, every discriminator layer one fused conv launch."""
+
+    def __init__(
+        self,
+        repeats=2,
+        window_sizes=[512, 1024, 2048, 4096],
+        pqmf_params=[[1, None, None, None], [2, 62, 0.26700, 9.0], [4, 62, 0.14200, 9.0], [8, 62, 0.07949, 9.0]],
+        discriminator_params={
+            "out_channels": 1, "kernel_sizes": [5, 3], "channels": 16, "max_downsample_channels": 512, "bias": True,
+            "downsample_scales": [4, 4, 4, 1], "nonlinear_activation": "LeakyReLU",
+            "nonlinear_activation_params": {"negative_slope": 0.2}, "pad": "ReflectionPad1d", "pad_params": {},
+        },
+        use_weight_norm=True,
+    ):
+        super().__init__()
+        from .layers import PQMF
+
+        assert len(window_sizes) == len(pqmf_params)
+        sizes = [ws // p[0] for ws, p in zip(window_sizes, pqmf_params)]
+        assert len(window_sizes) == sum([sizes[0] == size for size in sizes])
+        self.repeats = repeats
+        self.window_sizes = window_sizes
+        self.pqmfs = torch.nn.ModuleList()
+        self.discriminators = torch.nn.ModuleList()
+        for pqmf_param in pqmf_params:
+            d_params = copy.deepcopy(discriminator_params)
+            d_params["in_channels"] = pqmf_param[0]
+            self.pqmfs += [torch.nn.Identity() if pqmf_param[0] == 1 else PQMF(*pqmf_param)]
+            self.discriminators += [MelGANDiscriminator(**d_params)]
+        if use_weight_norm:
+            self.apply_weight_norm()
+        self.reset_parameters()
+
+    def forward(self, x):
+        """(B, 1, T) -> list of repeats * #discriminators lists of feature maps (last = logits)."""
+        outs = []
+        for _ in range(self.repeats):
+            outs += self._forward(x)
+        return outs
+
+    def _forward(self, x):
+        outs = []
+        for idx, (ws, pqmf, disc) in enumerate(zip(self.window_sizes, self.pqmfs, self.discriminators)):
+            start_idx = np.random.randint(x.size(-1) - ws)
+            x_ = x[:, :, start_idx : start_idx + ws].contiguous()
+            x_ = pqmf(x_) if idx == 0 else pqmf.analysis(x_)
+            outs += [disc(x_)]
+        return outs
+
+    def apply_weight_norm(self):
+        def _apply_weight_norm(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                torch.nn.utils.weight_norm(m)
+
+        self.apply(_apply_weight_norm)
+
+    def reset_parameters(self):
+        def _reset_parameters(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+                m.weight.data.normal_(0.0, 0.02)
+
+        self.apply(_reset_parameters)

@@ -26,6 +26,21 @@ def test_melgan_msd():
     check_fingerprint(outs, meta, g, 5e-5)
 
 
+def test_style_melgan_discriminator():
+    """Random-window discriminator (style_melgan.py:243-337): same np.random seed as the fixture -> same windows."""
+    import numpy as np
+
+    meta, g = load_golden("style_melgan_disc")
+    x = synth.randn(meta["x_shape"], meta["x_seed"], meta["x_scale"])
+    T = x.shape[-1]
+    np.random.seed(meta["np_seed"])
+    starts = [np.random.randint(T - ws) for _ in range(2) for ws in (512, 1024, 2048, 4096)]
+    outs = ref_ops.style_melgan_discriminator(_eff(meta), x, starts)
+    check_fingerprint(outs, meta, g, 5e-5)
+    for i, o in enumerate(outs):
+        assert rel_l2(o[-1], g[f"final{i}"]) < 5e-5
+
+
 def test_pwg_discriminator():
     meta, g = load_golden("pwg_disc")
     x = synth.randn(meta["x_shape"], meta["x_seed"], meta["x_scale"])
