@@ -64,6 +64,10 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm,
                "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// L2 prefetch of a box (no shared memory, no barrier): later loads of the same box hit L2 instead of HBM
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }

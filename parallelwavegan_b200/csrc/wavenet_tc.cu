@@ -51,7 +51,7 @@ struct WnK {
   int nslot, a_bytes, b_bytes, slot_bytes, z_bytes;
   int nset, set_cols, tmem_cols;
   int write_x, skip_init;
-  int variant;  // timing experiments only (pwgb_debug_set(2, v)): 1 no activation TMA, 2 no weight copies, 4 no gate math, 8 no epilogue memory traffic, 16 no MMAs
+  int variant;  // timing experiments only (pwgb_debug_set(2, v)): 1 no activation TMA, 2 no weight copies, 4 no gate math, 8 no epilogue memory traffic, 16 no MMAs, 32 no L2 prefetch
   unsigned idesc1, idesc2;
 };
 
@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
     for (int i = 0; i < 4; ++i) {
       mbar_init(G_FULL(i), 1);
       mbar_init(SO_FULL(i), 1);
-      mbar_init(ACC_EMPTY(i), WN_NEPI);
+      mbar_init(ACC_EMPTY(i), WN_NEPI / 32);
     }
-    mbar_init(Z_FULL, WN_NGATE);
+    mbar_init(Z_FULL, WN_NGATE / 32);
     mbar_init(Z_EMPTY, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -163,6 +163,21 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       const int tile = blockIdx.x + n * gridDim.x;
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
+      if (n + 1 < ntl && !(p.variant & 32) && lane < conv_stages) {
+        // the NEXT tile's activation windows go to L2 now (one box prefetch per lane): when their turn comes the loads
+        // below see the L2 latency, which the ring depth covers, instead of the HBM latency, which it does not
+        const int tl = tile + (int)gridDim.x;
+        const int bb = tl / p.tiles_per_seq;
+        const int tt0 = (tl - bb * p.tiles_per_seq) * WN_TT;
+        const bool px = lane < p.nxc * p.K;
+        const int chunk = px ? lane / p.K : lane - p.nxc * p.K;
+        const int tap = px ? lane - chunk * p.K : 0;
+        if (px)
+          tma_prefetch_3d(&tm_x, 2 * (p.halo + tt0 + (tap - p.K / 2) * p.D), chunk * 4, 2 * bb);
+        else
+          tma_prefetch_3d(&tm_c, 2 * tt0, chunk * 4, 2 * bb);
+      }
+      __syncwarp();
       for (int j = 0; j < conv_stages; ++j) {
         const bool is_x = j < p.nxc * p.K;
         const int chunk = is_x ? j / p.K : j - p.nxc * p.K;
@@ -256,7 +271,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
     const int g_begin = (gw >> 2) ? ngrp / 2 : 0, g_end = (gw >> 2) ? ngrp : ngrp / 2;
     for (int n = 0; n < ntl; ++n) {
       const int set = n % p.nset;
-      mbar_wait(G_FULL(set), (n / p.nset) & 1);
+      mbar_wait_spin(G_FULL(set), (n / p.nset) & 1);
       tc_fence_after();
       const unsigned tacc = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(set * p.set_cols);
       bool z_free = false;
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         for (int j = 0; j < 16; ++j)
           zv[j] = gate_fast(__uint_as_float(ra[j]) + bias1[g16 * 16 + j], __uint_as_float(rb[j]) + bias1[p.H + g16 * 16 + j]);
         if (!z_free) {  // the previous tile's skip/out MMAs must have retired before z is overwritten
-          mbar_wait(Z_EMPTY, (n & 1) ^ 1);
+          mbar_wait_spin(Z_EMPTY, (n & 1) ^ 1);
           z_free = true;
         }
 #pragma unroll
@@ -285,10 +300,11 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
           *reinterpret_cast<uint4*>(z_buf + ((size_t)(p.H / 8 + grp) * WN_TT + m) * 16) = lo;
         }
       }
-      if (!z_free) mbar_wait(Z_EMPTY, (n & 1) ^ 1);
+      if (!z_free) mbar_wait_spin(Z_EMPTY, (n & 1) ^ 1);
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(Z_FULL);
+      __syncwarp();  // one arrival per warp: every lane's z stores and TMEM loads are ordered before it
+      if (lane == 0) mbar_arrive(Z_FULL);
     }
   } else {
     // ===================== epilogue: SO (TMEM) -> skips (fp32 RMW), x' (packed hi/lo) =====================
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         float sv[16], sn[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) sv[j] = ld ? sq[(long long)j * p.T] : 0.f;
-        mbar_wait(SO_FULL(set), (n / p.nset) & 1);
+        mbar_wait_spin(SO_FULL(set), (n / p.nset) & 1);
         tc_fence_after();
         for (int col = 0; col < p.S; col += 16) {
           unsigned r[16];
@@ -350,7 +366,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
           xh[h8] = tv ? ldg16(xh_base + (long long)h8 * p.Tp) : make_uint4(0, 0, 0, 0);
           xl[h8] = tv ? ldg16(xl_base + (long long)h8 * p.Tp) : make_uint4(0, 0, 0, 0);
         }
-        mbar_wait(SO_FULL(set), (n / p.nset) & 1);
+        mbar_wait_spin(SO_FULL(set), (n / p.nset) & 1);
         tc_fence_after();
         for (int col = 0; col < p.R; col += 16) {
           unsigned r[16];
@@ -386,11 +402,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
           }
         }
       } else {
-        mbar_wait(SO_FULL(set), (n / p.nset) & 1);
+        mbar_wait_spin(SO_FULL(set), (n / p.nset) & 1);
         tc_fence_after();
       }
       tc_fence_before();
-      mbar_arrive(ACC_EMPTY(set));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ACC_EMPTY(set));
     }
   }
   __syncthreads();
