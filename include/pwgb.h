@@ -201,12 +201,14 @@ PWGB_API int pwgb_mt_adam_step(const void* table, const void* chunks, int n_chun
  * stride (3,1), hifigan.py:354-381):  y[b, g*s*Cg + r*Cg + cl, u, p] = x[b, g*Cg + cl, s*u + r - pad_left, p]
  * (zero outside [0, rows_in)), so that  conv_stride_s(x, w) = conv_stride_1(y, w') with
  * w'[co, r*Cg + cl, j] = w[co, cl, s*j + r]  (ceil(K/s) taps, no padding, rows_out = t_out + ceil(K/s) - 1).
- * x: (batch, channels, rows_in, period) -> y: (batch, channels*stride, rows_out, period); backward is the adjoint.
+ * x: (batch, channels, rows_in, period) -> y: (batch, groups*Cgo, rows_out, period); backward is the adjoint.
+ * Cgo = group_channels_out (0: stride * Cg): output channels per group; channels beyond stride * Cg are zero
+ * (padding up to the tensor cores' 32-channel granularity, matched by zero weight columns).
  * ---------------------------------------------------------------------- */
 PWGB_API int pwgb_s2d_forward(const float* x, float* y, int batch, int channels, int groups, long long rows_in, int period, int stride,
-                     int pad_left, long long rows_out, void* stream);
+                     int pad_left, long long rows_out, int group_channels_out, void* stream);
 PWGB_API int pwgb_s2d_backward(const float* gy, float* gx, int batch, int channels, int groups, long long rows_in, int period, int stride,
-                      int pad_left, long long rows_out, void* stream);
+                      int pad_left, long long rows_out, int group_channels_out, void* stream);
 
 /* ------------------------------------------------------------------------
  * Packed WaveNet residual stack: the fused ONE-kernel form of WaveNetResidualBlock.forward

@@ -153,7 +153,7 @@ class ConvTranspose1dFn(torch.autograd.Function):
             gw = ops.conv1d_wgrad(gy, x, (cin, cout, K), stride=stride, padding=padding, g_slope=pre_slope)
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = ops.conv1d_raw(gy, w.detach(), None, stride=stride, padding=padding)  # (cin, cout, K) read as a conv weight
+            gx = ops.conv1d(gy, w.detach(), None, stride=stride, padding=padding)  # (cin, cout, K) read as a conv weight; strided -> space-to-depth + tcgen05
             if gx.shape[-1] != x.shape[-1]:
                 raise PwgbError("conv_transpose dgrad: length mismatch")
             if pre_slope != 1.0:
@@ -171,14 +171,14 @@ class S2DFn(torch.autograd.Function):
     """Space-to-depth along time (strided convs on the tensor-core path); backward = the adjoint gather."""
 
     @staticmethod
-    def forward(ctx, x, groups, stride, pad_left, rows_out, period):
-        ctx.cfg = (tuple(x.shape), groups, stride, pad_left, period)
-        return ops.s2d_raw(x, groups, stride, pad_left, rows_out, period)
+    def forward(ctx, x, groups, stride, pad_left, rows_out, period, cgo=0):
+        ctx.cfg = (tuple(x.shape), groups, stride, pad_left, period, cgo)
+        return ops.s2d_raw(x, groups, stride, pad_left, rows_out, period, cgo)
 
     @staticmethod
     def backward(ctx, gy):
-        shape, groups, stride, pad_left, period = ctx.cfg
-        return ops.s2d_backward_raw(gy.contiguous(), shape, groups, stride, pad_left, period), None, None, None, None, None
+        shape, groups, stride, pad_left, period, cgo = ctx.cfg
+        return ops.s2d_backward_raw(gy.contiguous(), shape, groups, stride, pad_left, period, cgo), None, None, None, None, None, None
 
 
 class AvgPool1dFn(torch.autograd.Function):

@@ -125,7 +125,7 @@ def lib():
     L.pwgb_mt_adam_step.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int] + [C.c_float] * 7 + [vp, C.c_int, vp]
     for fn in (L.pwgb_s2d_forward, L.pwgb_s2d_backward):
         fn.restype = C.c_int
-        fn.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_longlong, vp]
+        fn.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, vp]
     L.pwgb_upsample_fir_forward.restype = C.c_int
     L.pwgb_upsample_fir_forward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_longlong, vp]
     L.pwgb_mr_stft_loss_workspace.restype = C.c_size_t

@@ -109,7 +109,7 @@ void tc_pack_rows(const float* w, void* packed, int cin_real, int cin_pad, int r
 // (residual, and the accumulate read-modify-write) is issued before the TMEM load is waited for, so
 // W (2W) requests per thread are in flight.
 template <int W>
-__device__ __forceinline__ void epi_generic(const TcK& p, unsigned taddr, const float* bias_s, int col,
+__device__ __forceinline__ void epi_generic(const TcK& p, unsigned taddr, const float* __restrict__ bias_s, int col,
                                             const float* rq, float* yq, long long st, bool tv) {
   unsigned r[W];
   {
@@ -139,17 +139,17 @@ __device__ __forceinline__ void epi_generic(const TcK& p, unsigned taddr, const 
     for (int j = 0; j < W; ++j, q2 += st) yv[j] = *q2;
 #pragma unroll
     for (int j = 0; j < W; ++j, q += st) {
-      float v = __uint_as_float(r[j]) + (bias_s ? bias_s[col + j] : 0.f);
+      float v = __uint_as_float(r[j]) + bias_s[col + j];
       if (p.post_act != PWGB_ACT_NONE) v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
       *q = (v + rv[j]) * p.out_scale + yv[j];
     }
   } else if (p.post_act == PWGB_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < W; ++j, q += st) *q = (__uint_as_float(r[j]) + (bias_s ? bias_s[col + j] : 0.f) + rv[j]) * p.out_scale;
+    for (int j = 0; j < W; ++j, q += st) *q = (__uint_as_float(r[j]) + bias_s[col + j] + rv[j]) * p.out_scale;
   } else {
 #pragma unroll
     for (int j = 0; j < W; ++j, q += st) {
-      float v = __uint_as_float(r[j]) + (bias_s ? bias_s[col + j] : 0.f);
+      float v = __uint_as_float(r[j]) + bias_s[col + j];
       v = p.post_act == PWGB_ACT_TANH ? tanhf(v) : lrelu(v, p.post_slope);
       *q = (v + rv[j]) * p.out_scale;
     }
@@ -226,6 +226,9 @@ __device__ __forceinline__ void fill_main_chunk(const TcK& p, const float* __res
   }
 }
 
+// MC = 1: several column chunks / groups of a plain (non pixel-shuffle) conv share the launch -- the extra index
+// arithmetic (group input offset, per-chunk bias and output channel base) is compiled only into that instantiation
+template <int MC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     conv1d_tc_kernel(const TcK p, const float* __restrict__ x, const float* __restrict__ x2,
                      const uint4* __restrict__ wpk, const float* __restrict__ bias, const float* __restrict__ res,
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < p.Cout; i += TC_THREADS)
+  for (int i = tid; i < p.Cout * (MC ? p.nco : 1); i += TC_THREADS)
     bias_s[i] = bias ? __ldg(bias + (p.shuffle > 1 ? (p.co_off + i) / p.shuffle : p.co_off + i)) : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int t0 = (tr - b * p.tiles_per_seq) * TT;
       const unsigned raw = smem_u32(raw_buf + (size_t)(q % p.ns) * p.raw_bytes);
       if (c < p.nchunks) {
-        const float* xc = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in + (p.nco > 1 ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
+        const float* xc = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in + (MC ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
         for (int r = tid; r < p.R; r += NPROD) {
           long long ts;
           if (p.win_mode) {
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int tr = p.nco > 1 ? tile % pct : tile;  // tile within its column chunk
       const int b = tr / p.tiles_per_seq;
       const int t0 = (tr - b * p.tiles_per_seq) * TT;
-      const float* xb = x + (long long)b * p.xbs + (p.nco > 1 ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
+      const float* xb = x + (long long)b * p.xbs + (MC ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
       for (int c = 0; c < nc_total; ++c, ++ca) {
         const int buf = ca % p.na;
         mbar_wait(A_EMPTY(buf), ((ca / p.na) & 1) ^ 1);
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int col = col_begin + (i - mt * ncol);
             const int tp = tt0 + mt * 128 + ew * 32;
             if (tp < p.T_out) {
-              const long long off = (long long)(p.co_off + (p.nco > 1 ? (tl / pct) * p.Cout : 0) + col) * st + tp;
+              const long long off = (long long)(p.co_off + (MC ? (tl / pct) * p.Cout : 0) + col) * st + tp;
               if (res) prefetch_l2(res + (long long)bb * p.rbs + off);
               if (p.accumulate) prefetch_l2(y + (long long)bb * p.ybs + off);
             }
@@ -581,10 +584,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         } else {
           // generic: running 64-bit pointers (2 integer instructions per element instead of a full
           // address recomputation), every independent load of a 16-column group issued before use
-          float* yq = y + (long long)b * p.ybs + (long long)(co_base + col_begin) * st + t;
-          const float* rq = res ? res + (long long)b * p.rbs + (long long)(co_base + col_begin) * st + t : nullptr;
-          // several column chunks per launch: the chunk's bias comes straight from global memory (L1-resident)
-          const float* bptr = p.nco > 1 ? (bias ? bias + co_base : nullptr) : bias_s;
+          const int cb = MC ? co_base : p.co_off;
+          float* yq = y + (long long)b * p.ybs + (long long)(cb + col_begin) * st + t;
+          const float* rq = res ? res + (long long)b * p.rbs + (long long)(cb + col_begin) * st + t : nullptr;
+          // several column chunks per launch: bias_s holds the bias of every chunk
+          const float* bptr = MC ? bias_s + (co_base - p.co_off) : bias_s;
           // (32-column groups were tried: they spill at the register budget of this block size)
           for (int col = col_begin; col < col_end; col += 16, yq += 16 * st) {
             epi_generic<16>(p, tacc + (unsigned)(mt * p.Cout + col), bptr, col, rq, yq, st, tv);
@@ -631,7 +635,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             end = ts0 + p.R4 < p.T_in ? ts0 + p.R4 : p.T_in;
             rowstride = p.T_in;
             dst_off = start - ts0;
-            src = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in + (p.nco > 1 ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
+            src = x + (long long)b * p.xbs + (long long)(c * KC) * p.T_in + (MC ? (long long)((tile / pct) / p.cpg) * p.xgs : 0);
           } else {
             start = t0;
             end = t0 + TT < p.T_out ? t0 + TT : p.T_out;
@@ -716,7 +720,7 @@ static int g_tc_variant = 0;
 
 // aux_c2: channels of the auxiliary 1x1 source (0 = none, else multiple of KC); split > 0 selects the
 // WaveNet epilogue.  pre_gate: d->cin is the number of gated channels, x holds 2*cin channels.
-static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int aux_c2 = 0, int split = 0) {
+static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int aux_c2 = 0, int split = 0, int nco_bias = 1) {
   p.variant = g_tc_variant;
   p.co_off = 0;
   p.nco = 1;
@@ -794,7 +798,8 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
                     d->shuffle_tout % 4 == 0 && !(p.variant & 16);
     // shared-memory split: [na operand buffers][nb weight stages][ns raw staging buffers]
     int na = 0, nb = 0, ns = 0;
-    const size_t A = (size_t)p.a_bytes, Bs = (size_t)p.b_bytes, S = (size_t)p.raw_bytes, slack = 2048;
+    const size_t bias_bytes = 4 * (size_t)(nco_bias > 1 ? nco_bias * d->cout : 256);  // bias of every column chunk of the launch
+    const size_t A = (size_t)p.a_bytes, Bs = (size_t)p.b_bytes, S = (size_t)p.raw_bytes, slack = 1024 + bias_bytes;
     if (p.tma_act && 2 * A + 3 * S + 3 * Bs + slack <= budget) {
       ns = 3;
       na = 2;
@@ -824,7 +829,7 @@ static int tc_plan(const pwgb_conv1d_desc* d, TcK& p, size_t& smem_bytes, int au
     int alloc = 32;
     while (alloc < p.nacc * cols) alloc <<= 1;
     p.tmem_cols = alloc;
-    smem_bytes = (size_t)na * p.a_bytes + (size_t)ns * p.raw_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4 + 2 * NS_MAX) + 16 + 4 * 256;
+    smem_bytes = (size_t)na * p.a_bytes + (size_t)ns * p.raw_bytes + (size_t)nb * p.b_bytes + 8 * (2 * na + 2 * nb + 4 + 2 * NS_MAX) + 16 + bias_bytes;
     return 1;
   }
   return 0;
@@ -836,7 +841,8 @@ static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w,
   if (p.B == 0 || p.T_out == 0) return PWGB_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv1d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) {
       set_error("conv1d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PWGB_CUDA_ERROR;
@@ -858,7 +864,10 @@ static int tc_launch(TcK& p, size_t bytes, const float* x, const void* packed_w,
     p.tma_act = 0;  // unaligned base pointer: the producers stage with cp.async instead
   if (p.shuffle_vec && ((reinterpret_cast<uintptr_t>(y) & 15) || p.co_off % 16 != 0)) p.shuffle_vec = 0;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv1d_tc_kernel<<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, x2, (const uint4*)packed_w, bias, residual, y, y2);
+  if (p.nco > 1 && p.shuffle <= 1)
+    conv1d_tc_kernel<1><<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, x2, (const uint4*)packed_w, bias, residual, y, y2);
+  else
+    conv1d_tc_kernel<0><<<(unsigned)grid, TC_THREADS, bytes, st>>>(p, x, x2, (const uint4*)packed_w, bias, residual, y, y2);
   return check_launch("conv1d_tc_kernel");
 }
 
@@ -958,7 +967,7 @@ extern "C" int pwgb_conv1d_tc_supported(const pwgb_conv1d_desc* d) {
   c.groups = 1;
   TcK p;
   size_t bytes;
-  return tc_plan(&c, p, bytes);
+  return tc_plan(&c, p, bytes, 0, 0, G * ((d->cout / G) / chunk));
 }
 
 extern "C" int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x, const void* packed_w,
@@ -976,8 +985,11 @@ extern "C" int pwgb_conv1d_tc_forward(const pwgb_conv1d_desc* d, const float* x,
   // the input channels of group cc / (cout_g / chunk)
   TcK p;
   size_t bytes = 0;
-  tc_plan(&c, p, bytes);
   const int nco = G * (cout_g / chunk);
+  if (!tc_plan(&c, p, bytes, 0, 0, nco)) {
+    set_error("conv1d_tc: no tile plan for this configuration");
+    return PWGB_UNSUPPORTED;
+  }
   if ((long long)p.total_tiles * nco > 0x7fffffffLL) {
     set_error("conv1d_tc: too many tiles");
     return PWGB_UNSUPPORTED;

@@ -8,29 +8,31 @@
 namespace pwgb {
 
 // x: (B, C, rows_in, P)   y: (B, C*s, rows_out, P); channel (g, r, cl) = g*s*Cg + r*Cg + cl
-__global__ void s2d_forward_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cg, long long rows_in, int P, int s,
-                                   int pad, long long rows_out, long long total) {
+__global__ void s2d_forward_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Cg, int Cgo, long long rows_in, int P,
+                                   int s, int pad, long long rows_out, long long total) {
+  const int G = C / Cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long inner = rows_out * P;
     const long long f = i % inner;
     long long t = i / inner;
-    const int ch = (int)(t % ((long long)C * s));
-    const long long b = t / ((long long)C * s);
+    const int ch = (int)(t % ((long long)G * Cgo));
+    const long long b = t / ((long long)G * Cgo);
     const long long u = f / P;
     const int pp = (int)(f - u * P);
-    const int g = ch / (s * Cg);
-    const int rem = ch - g * s * Cg;
+    const int g = ch / Cgo;
+    const int rem = ch - g * Cgo;  // channels >= s * Cg of a group are zero padding (tensor-core channel granularity)
     const int r = rem / Cg, cl = rem - r * Cg;
     const long long row = (long long)s * u + r - pad;
     float v = 0.f;
-    if (row >= 0 && row < rows_in) v = __ldg(x + ((b * C + g * Cg + cl) * rows_in + row) * P + pp);
+    if (rem < s * Cg && row >= 0 && row < rows_in) v = __ldg(x + ((b * C + g * Cg + cl) * rows_in + row) * P + pp);
     y[i] = v;
   }
 }
 
 // gx: (B, C, rows_in, P) <- gy: (B, C*s, rows_out, P)
-__global__ void s2d_backward_kernel(const float* __restrict__ gy, float* __restrict__ gx, int C, int Cg, long long rows_in, int P, int s,
-                                    int pad, long long rows_out, long long total) {
+__global__ void s2d_backward_kernel(const float* __restrict__ gy, float* __restrict__ gx, int C, int Cg, int Cgo, long long rows_in, int P,
+                                    int s, int pad, long long rows_out, long long total) {
+  const int G = C / Cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long inner = rows_in * P;
     const long long f = i % inner;
@@ -44,7 +46,7 @@ __global__ void s2d_backward_kernel(const float* __restrict__ gy, float* __restr
     const int r = (int)(q - u * s);
     const int g = c / Cg, cl = c - g * Cg;
     float v = 0.f;
-    if (u < rows_out) v = __ldg(gy + ((b * C * s + (long long)g * s * Cg + (long long)r * Cg + cl) * rows_out + u) * P + pp);
+    if (u < rows_out) v = __ldg(gy + ((b * G * Cgo + (long long)g * Cgo + (long long)r * Cg + cl) * rows_out + u) * P + pp);
     gx[i] = v;
   }
 }
@@ -59,23 +61,27 @@ static int s2d_args_ok(int batch, int channels, int groups, long long rows_in, i
 }
 
 extern "C" int pwgb_s2d_forward(const float* x, float* y, int batch, int channels, int groups, long long rows_in, int period, int stride,
-                                int pad_left, long long rows_out, void* stream) {
+                                int pad_left, long long rows_out, int group_channels_out, void* stream) {
   PWGB_CHECK_ARG(x && y && s2d_args_ok(batch, channels, groups, rows_in, period, stride, pad_left, rows_out), "s2d_forward: bad argument");
-  const long long total = (long long)batch * channels * stride * rows_out * period;
+  const int cgo = group_channels_out > 0 ? group_channels_out : channels / groups * stride;
+  PWGB_CHECK_ARG(cgo >= channels / groups * stride, "s2d_forward: group_channels_out smaller than stride * channels per group");
+  const long long total = (long long)batch * groups * cgo * rows_out * period;
   if (total == 0) return PWGB_OK;
   int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  s2d_forward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, channels, channels / groups, rows_in, period, stride, pad_left, rows_out,
-                                                             total);
+  s2d_forward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, channels, channels / groups, cgo, rows_in, period, stride, pad_left,
+                                                             rows_out, total);
   return check_launch("s2d_forward_kernel");
 }
 
 extern "C" int pwgb_s2d_backward(const float* gy, float* gx, int batch, int channels, int groups, long long rows_in, int period, int stride,
-                                 int pad_left, long long rows_out, void* stream) {
+                                 int pad_left, long long rows_out, int group_channels_out, void* stream) {
   PWGB_CHECK_ARG(gy && gx && s2d_args_ok(batch, channels, groups, rows_in, period, stride, pad_left, rows_out), "s2d_backward: bad argument");
+  const int cgo = group_channels_out > 0 ? group_channels_out : channels / groups * stride;
+  PWGB_CHECK_ARG(cgo >= channels / groups * stride, "s2d_backward: group_channels_out smaller than stride * channels per group");
   const long long total = (long long)batch * channels * rows_in * period;
   if (total == 0) return PWGB_OK;
   int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  s2d_backward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gy, gx, channels, channels / groups, rows_in, period, stride, pad_left,
+  s2d_backward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gy, gx, channels, channels / groups, cgo, rows_in, period, stride, pad_left,
                                                               rows_out, total);
   return check_launch("s2d_backward_kernel");
 }

@@ -675,22 +675,24 @@ def _needs_grad(*ts):
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
 
 
-def s2d_raw(x, groups, stride, pad_left, rows_out, period=1):
-    """Space-to-depth along time (pwgb_s2d_forward): (B, C, rows[, P]) -> (B, C*stride, rows_out[, P])."""
+def s2d_raw(x, groups, stride, pad_left, rows_out, period=1, cgo=0):
+    """Space-to-depth along time (pwgb_s2d_forward): (B, C, rows[, P]) -> (B, groups*cgo, rows_out[, P]);
+    cgo = output channels per group (0: stride * C / groups; larger: zero channels appended per group)."""
     x = _dev(x, "x")
     B, Cc = x.shape[0], x.shape[1]
     P = int(period)
     rows_in = x.numel() // max(B * Cc * P, 1)
-    shape = (B, Cc * stride, rows_out) if P == 1 else (B, Cc * stride, rows_out, P)
+    co = groups * cgo if cgo else Cc * stride
+    shape = (B, co, rows_out) if P == 1 else (B, co, rows_out, P)
     y = torch.empty(shape, device=x.device, dtype=torch.float32)
     prof = _Prof("s2d", 0.0, 4.0 * (x.numel() + y.numel()), f"B{B} C{Cc} rows{rows_in} P{P} s{stride}")
-    rc = capi.lib().pwgb_s2d_forward(_p(x), _p(y), B, Cc, int(groups), rows_in, P, int(stride), int(pad_left), int(rows_out), _stream())
+    rc = capi.lib().pwgb_s2d_forward(_p(x), _p(y), B, Cc, int(groups), rows_in, P, int(stride), int(pad_left), int(rows_out), int(cgo), _stream())
     capi.check(rc, "pwgb_s2d_forward")
     prof.done()
     return y
 
 
-def s2d_backward_raw(gy, x_shape, groups, stride, pad_left, period=1):
+def s2d_backward_raw(gy, x_shape, groups, stride, pad_left, period=1, cgo=0):
     gy = _dev(gy, "gy")
     B, Cc = x_shape[0], x_shape[1]
     P = int(period)
@@ -698,9 +700,9 @@ def s2d_backward_raw(gy, x_shape, groups, stride, pad_left, period=1):
     for v in x_shape:
         n *= v
     rows_in = n // max(B * Cc * P, 1)
-    rows_out = gy.numel() // max(B * Cc * stride * P, 1)
+    rows_out = gy.numel() // max(B * (groups * cgo if cgo else Cc * stride) * P, 1)
     gx = torch.empty(x_shape, device=gy.device, dtype=torch.float32)
-    rc = capi.lib().pwgb_s2d_backward(_p(gy), _p(gx), B, Cc, int(groups), rows_in, P, int(stride), int(pad_left), int(rows_out), _stream())
+    rc = capi.lib().pwgb_s2d_backward(_p(gy), _p(gx), B, Cc, int(groups), rows_in, P, int(stride), int(pad_left), int(rows_out), int(cgo), _stream())
     capi.check(rc, "pwgb_s2d_backward")
     return gx
 
@@ -718,7 +720,8 @@ def _conv1d_s2d(x, w, bias, kw):
     groups, P = int(kw.get("groups", 1)), int(kw.get("period", 1))
     wd = w.shape
     cout, cin_g, K = wd[0], wd[1], wd[2]
-    if (cin_g * stride) % 32 or (cout // groups) % 16 or x.dim() < 3:
+    cgo = (cin_g * stride + 31) // 32 * 32  # channels per group after the re-layout, padded to the tensor cores' 32
+    if (cout // groups) % 16 or x.dim() < 3 or cgo > 2 * cin_g * stride:
         return None
     B, cin = x.shape[0], x.shape[1]
     L = x.numel() // max(B * cin, 1)
@@ -736,16 +739,36 @@ def _conv1d_s2d(x, w, bias, kw):
     if Kp * stride != K:
         w3 = torch.nn.functional.pad(w3, (0, Kp * stride - K))
     w2 = w3.reshape(cout, cin_g, Kp, stride).permute(0, 3, 1, 2).reshape(cout, stride * cin_g, Kp)
+    if cgo != stride * cin_g:  # zero weight columns for the zero channels the re-layout appends to every group
+        w2 = torch.nn.functional.pad(w2, (0, 0, 0, cgo - stride * cin_g))
     if w.dim() == 4:
         w2 = w2.unsqueeze(-1)
     if _needs_grad(x):
         from . import autograd as ag
 
-        xs = ag.S2DFn.apply(x, groups, stride, pl, rows_out, P)
+        xs = ag.S2DFn.apply(x, groups, stride, pl, rows_out, P, cgo)
     else:
-        xs = s2d_raw(x, groups, stride, pl, rows_out, P)
+        xs = s2d_raw(x, groups, stride, pl, rows_out, P, cgo)
     inner = {k: v for k, v in kw.items() if k not in ("stride", "padding")}
     return conv1d(xs, w2.contiguous(), bias, stride=1, padding=0, **inner)
+
+
+def _conv1d_fewcout(x, w, bias, kw):
+    """Logit convs of the discriminator towers (1024 -> 1, k3 / (3,1)): wide input, a single output channel.  The weight
+    is zero-padded to 16 output channels so that the contraction runs on the tensor cores (N = 16), and channel 0 of the
+    result is returned; the padding / slicing are torch indexing on small tensors (differentiable by autograd)."""
+    cout, cin_g = w.shape[0], w.shape[1]
+    if ENGINE == "simt" or cout >= 16 or cin_g < 256 or cin_g % 32 or kw.get("groups", 1) != 1 or kw.get("stride", 1) != 1:
+        return None
+    if kw.get("out") is not None or kw.get("accumulate") or kw.get("residual") is not None or kw.get("pre_gate"):
+        return None
+    if kw.get("pad_mode", "zero") not in ("zero", "zeros"):
+        return None
+    pad = [0, 0] * (w.dim() - 1) + [0, 16 - cout]
+    w16 = torch.nn.functional.pad(w, pad)
+    b16 = torch.nn.functional.pad(bias, (0, 16 - cout)) if bias is not None else None
+    y = conv1d(x, w16, b16, **kw)
+    return y[:, :cout].contiguous()
 
 
 def conv1d(x, w, bias=None, **kw):
@@ -754,6 +777,9 @@ def conv1d(x, w, bias=None, **kw):
         y = _conv1d_s2d(x, w, bias, kw)
         if y is not None:
             return y
+    y = _conv1d_fewcout(x, w, bias, kw)
+    if y is not None:
+        return y
     if _needs_grad(x, w, bias, kw.get("residual")):
         from . import autograd as ag
 

@@ -74,3 +74,22 @@ def check_fingerprint(outs, meta, g, tol):
         assert abs(float(v.sum()) - ssum) <= tol * max(snorm * v.numel() ** 0.5, 1e-12), (n, float(v.sum()), ssum)
         assert rel_l2(t.reshape(-1)[:96], g[n + "_head"]) < tol, n
         assert rel_l2(t.reshape(-1)[-96:], g[n + "_tail"]) < tol, n
+
+
+def conditioning_tolerances(grad_fn, leaves, rel_eps=1e-6, k=8.0, floor=1e-3, seed=1234):
+    """Per-tensor tolerance for gradient parity that follows the CONDITIONING of the computation instead of a
+    hand-picked constant.  ``grad_fn(leaves) -> {name: grad}`` runs the CPU oracle with torch autograd.  It is run
+    twice: on ``leaves`` and on ``leaves * (1 + rel_eps * N(0,1))`` -- a perturbation of the size of fp32 input rounding.
+    Whatever change that produces in a gradient tensor (LeakyReLU / clamp masks flipping, log of small magnitudes ...)
+    is a change ANY fp32 implementation with a different rounding order may show; the tolerance is
+    ``max(floor, k * observed relative change)``.  Returns (baseline grads, {name: tol}, {name: observed change})."""
+    base = grad_fn(leaves)
+    g = torch.Generator().manual_seed(seed)
+    pert = {n: (t.detach() * (1.0 + rel_eps * torch.randn(t.shape, generator=g))) for n, t in leaves.items()}
+    moved = grad_fn(pert)
+    tol, obs = {}, {}
+    for n, gb in base.items():
+        d = rel_l2(moved[n], gb)
+        obs[n] = d
+        tol[n] = max(floor, k * d)
+    return base, tol, obs

@@ -6,8 +6,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from helpers import golden_weights, load_golden, rel_l2
-from oracle import ref_ops, synth
+from helpers import conditioning_tolerances, golden_weights, load_golden, rel_l2
+from oracle import ref_optim, ref_ops, synth
 
 pytestmark = pytest.mark.gpu
 GTOL = 1e-3
@@ -154,31 +154,43 @@ def test_hifigan_train_step_gradients(dev):
     c = synth.randn((2, 80, 8), 21)
     y = synth.randn((2, 1, 8 * 256), 22, 0.3)
 
-    # ---- CPU oracle with torch autograd (weights as leaf tensors in the reference layout)
-    leaf_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    leaf_d = {k: v.clone().requires_grad_(True) for k, v in dsd.items()}
-    wg = ref_ops.fold_weight_norm(leaf_g)
-    wd = ref_ops.fold_weight_norm(leaf_d)
-    y_ref = ref_ops.hifigan_generator(wg, c, dict(kw, negative_slope=0.1))
+    # ---- CPU oracle with torch autograd (weights as leaf tensors in the reference layout), as a function of the
+    # leaves so that its conditioning can be measured (helpers.conditioning_tolerances)
     melmat = torch.from_numpy(ref_ops.slaney_mel_filterbank(22050, 1024, 80, 0, 11025).T.copy())
-    mel = ref_ops.mel_loss(y_ref, y, melmat, log_base=None)
+    scalars = {}
 
-    def d_ref(x):
-        outs, xs = [], x
-        for i in range(2):
-            outs.append(ref_ops.hifigan_scale_discriminator(wd, f"msd.discriminators.{i}", xs, strides=(2, 4, 1), groups=(4, 4, 4)))
-            xs = F.avg_pool1d(xs, 4, 2, padding=2)
-        for i, p in enumerate((2, 3)):
-            outs.append(ref_ops.hifigan_period_discriminator(wd, f"mpd.discriminators.{i}", x, p, n_layers=3, strides=(3, 3, 1)))
-        return outs
+    def oracle(leaves):
+        lg = {k[2:]: v.clone().requires_grad_(True) for k, v in leaves.items() if k.startswith("g.")}
+        ld = {k[2:]: v.clone().requires_grad_(True) for k, v in leaves.items() if k.startswith("d.")}
+        wg, wd = ref_ops.fold_weight_norm(lg), ref_ops.fold_weight_norm(ld)
+        y_ref = ref_ops.hifigan_generator(wg, c, dict(kw, negative_slope=0.1))
+        mel = ref_ops.mel_loss(y_ref, y, melmat, log_base=None)
 
-    p_hat = d_ref(y_ref)
-    with torch.no_grad():
-        p_real = d_ref(y)
-    adv = ref_ops.generator_adv_loss(p_hat)
-    fm = ref_ops.feature_match_loss(p_hat, p_real)
-    loss_ref = 45.0 * mel + adv + 2.0 * fm
-    loss_ref.backward()
+        def d_ref(x):
+            outs, xs = [], x
+            for i in range(2):
+                outs.append(ref_ops.hifigan_scale_discriminator(wd, f"msd.discriminators.{i}", xs, strides=(2, 4, 1), groups=(4, 4, 4)))
+                xs = F.avg_pool1d(xs, 4, 2, padding=2)
+            for i, p in enumerate((2, 3)):
+                outs.append(ref_ops.hifigan_period_discriminator(wd, f"mpd.discriminators.{i}", x, p, n_layers=3, strides=(3, 3, 1)))
+            return outs
+
+        p_hat = d_ref(y_ref)
+        with torch.no_grad():
+            p_real = d_ref(y)
+        adv = ref_ops.generator_adv_loss(p_hat)
+        fm = ref_ops.feature_match_loss(p_hat, p_real)
+        (45.0 * mel + adv + 2.0 * fm).backward()
+        scalars.update(y=y_ref.detach(), mel=mel.detach(), adv=adv.detach(), fm=fm.detach())
+        out = {"g." + k: v.grad for k, v in lg.items()}
+        out.update({"d." + k: v.grad for k, v in ld.items()})
+        return out
+
+    leaves = {"g." + k: v for k, v in sd.items()}
+    leaves.update({"d." + k: v for k, v in dsd.items()})
+    scalars_base = {}
+    ref_grads, tol, observed = conditioning_tolerances(lambda lv: (oracle(lv), scalars_base.update(scalars) if not scalars_base else None)[0], leaves)
+    y_ref, mel, adv, fm = scalars_base["y"], scalars_base["mel"], scalars_base["adv"], scalars_base["fm"]
 
     # ---- ours
     g = g.to(dev).train()
@@ -186,26 +198,43 @@ def test_hifigan_train_step_gradients(dev):
     mel_fn = losses.MelSpectrogramLoss(fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80,
                                        fmin=0, fmax=11025, log_base=None).to(dev)
     y_hat = g(c.to(dev))
-    assert rel_l2(y_hat.detach().cpu(), y_ref.detach()) < GTOL
+    assert rel_l2(y_hat.detach().cpu(), y_ref) < GTOL
     mel_o = mel_fn(y_hat, y.to(dev))
     ph = d(y_hat)
     with torch.no_grad():
         pr = d(y.to(dev))
     adv_o = losses.GeneratorAdversarialLoss()(ph)
     fm_o = losses.FeatureMatchLoss()(ph, pr)
-    for name, a, r in (("mel", mel_o, mel), ("adv", adv_o, adv), ("fm", fm_o, fm)):
-        assert abs(float(a) - float(r)) <= GTOL * abs(float(r)), name
+    for name, a, r in (("mel", mel_o, mel), ("adv", adv_o, adv), ("fm", fm_o, fm)):  # logged loss scalars (train.py:213-324)
+        assert abs(float(a.detach()) - float(r)) <= 1e-4 * abs(float(r)), name
     loss = 45.0 * mel_o + adv_o + 2.0 * fm_o
     loss.backward()
-    worst = 0.0
+    worst, loose = 0.0, []
+    for pre, mod in (("g.", g), ("d.", d)):
+        for k, p in mod.named_parameters():
+            e = rel_l2(p.grad.cpu(), ref_grads[pre + k])
+            worst = max(worst, e)
+            # 1e-3 unless the oracle itself moves more than 1.25e-4 under a 1e-6 perturbation of the weights
+            assert e < tol[pre + k], (pre + k, e, tol[pre + k], observed[pre + k])
+            if tol[pre + k] > 1e-3:
+                loose.append((pre + k, round(e, 5), round(tol[pre + k], 5)))
+    print(f"worst grad rel-L2 {worst:.2e}; {len(loose)} of {len(tol)} tensors needed a conditioning bound above 1e-3: {loose[:6]}")
+
+    # ---- parameters after optimizer.step() (train.py:295): Adam on the generator, fused kernel vs the oracle update
+    from parallelwavegan_b200 import optimizers
+
+    opt = optimizers.FusedAdam(g.parameters(), lr=2e-4, betas=(0.5, 0.9))
+    before = {k: p.detach().clone() for k, p in g.named_parameters()}
+    opt.step()
     for k, p in g.named_parameters():
-        e = rel_l2(p.grad.cpu(), leaf_g[k].grad)
-        worst = max(worst, e)
-        assert e < 5e-3, (k, e)
-    for k, p in d.named_parameters():
-        e = rel_l2(p.grad.cpu(), leaf_d[k].grad)
-        assert e < 5e-3, (k, e)
-    print("worst generator grad rel-L2", worst)
+        pr_ = sd[k].clone()
+        gr = ref_grads["g." + k]
+        ref_optim.adam_step(pr_, gr, torch.zeros_like(pr_), torch.zeros_like(pr_), 1, 2e-4, (0.5, 0.9), 1e-8, 0.0)
+        assert rel_l2(p.detach().cpu(), pr_) < GTOL, k
+        # the first Adam update is lr * sign(g) wherever |g| >> eps: it only differs where the gradient sign differs
+        upd_o, upd_r = (p.detach() - before[k]).cpu(), pr_ - sd[k]
+        agree = float(((upd_o * upd_r) > 0).float().mean())
+        assert agree > 0.98, (k, agree)
 
 
 @pytest.mark.parametrize("mode", ["reflect", "replicate"])

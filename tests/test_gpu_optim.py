@@ -1,6 +1,8 @@
 """Fused multi-tensor optimizers (pwgb_mt_*) vs the pinned oracle restatement of the reference RAdam
 (optimizers/radam.py:27-99) / torch.optim.Adam and of clip_grad_norm_ (bin/train.py:289-293): parameters after
 every one of 12 steps (the RAdam rectification switches on at step 6), state_dict layout."""
+import copy
+
 import pytest
 import torch
 
@@ -59,7 +61,7 @@ def test_fused_optimizer_matches_reference(dev, kind, lr, betas, eps, wd, clip):
     # round trip into a fresh optimizer, one more step gives identical parameters
     ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
     opt2 = cls(ps2, lr=lr, betas=betas, eps=eps, weight_decay=wd)
-    opt2.load_state_dict(sd)
+    opt2.load_state_dict(copy.deepcopy(sd))  # as after torch.save / torch.load: load_state_dict itself does not copy tensors
     for p, p2, g in zip(ps, ps2, grads_for(STEPS + 1)):
         p.grad = g.clone().to(dev)
         p2.grad = g.clone().to(dev)

@@ -29,6 +29,7 @@ CASES = [
     (128, 128, 41, 2, 4, 20, 4096, 1, 4),  # MSD layer 1 (grouped, stride 2)
     (256, 512, 41, 4, 16, 20, 1024, 1, 4),  # MSD layer 3 (cin_g * s = 64)
     (512, 1024, 41, 4, 16, 20, 259, 1, 2),  # MSD layer 4, ragged length
+    (128, 256, 41, 2, 16, 20, 2048, 1, 4),  # MSD layer 2: cin_g * s = 16 -> zero-padded to 32 channels per group
 ]
 
 
@@ -70,3 +71,61 @@ def test_strided_conv_s2d_forward_backward(dev, cin, cout, K, stride, groups, pa
     with torch.no_grad():
         y2 = ops.conv1d(xin.detach(), wq.detach(), bd.detach(), stride=stride, padding=pad, groups=groups, period=P, post_act="lrelu", post_slope=0.1)
     assert rel_l2(y2.cpu(), F.leaky_relu(ref.detach(), 0.1)) < TC_TOL
+
+
+@pytest.mark.parametrize("P,rows,B", [(1, 128, 16), (3, 37, 4)])
+def test_logit_conv_on_tensor_cores(dev, P, rows, B):
+    """1024 -> 1 logit convs (MSD k3, MPD (3,1)): zero-padded to 16 output channels for the tcgen05 path; forward and
+    gradients vs torch autograd."""
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((B, 1024, rows * P), 5)
+    w = synth.randn((1, 1024, 3), 6, 0.02)
+    b = synth.randn((1,), 7, 0.1)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    if P == 1:
+        ref = F.conv1d(xr, wr, br, padding=1)
+    else:
+        ref = F.conv2d(xr.view(B, 1024, rows, P), wr.unsqueeze(-1), br, padding=(1, 0))
+    gy = synth.randn(tuple(ref.shape), 8)
+    ref.backward(gy)
+    xd, wd, bd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    ops.PROFILE = []
+    try:
+        y = ops.conv1d(xd if P == 1 else xd.view(B, 1024, rows, P), wd if P == 1 else wd.unsqueeze(-1), bd, padding=1, period=P)
+        y.backward(gy.to(dev))
+        torch.cuda.synchronize()
+        names = [q[0] for q in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert "conv1d_tc" in names and "conv1d" not in names, names
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert rel_l2(y.detach().cpu(), ref.detach()) < TC_TOL
+    assert rel_l2(xd.grad.cpu(), xr.grad) < TC_TOL and rel_l2(wd.grad.cpu(), wr.grad) < TC_TOL and rel_l2(bd.grad.cpu(), br.grad) < TC_TOL
+
+
+def test_conv_transpose_dgrad_on_tensor_cores(dev):
+    """Generator upsampler backward (ConvTranspose1d k16 s8): its data gradient is a stride-8 conv -> space-to-depth path."""
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((4, 512, 32), 15)
+    w = synth.randn((512, 256, 16), 16, 0.02)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = F.conv_transpose1d(F.leaky_relu(xr, 0.1), wr, None, stride=8, padding=4)
+    gy = synth.randn(tuple(ref.shape), 17)
+    ref.backward(gy)
+    xd, wd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+    ops.PROFILE = []
+    try:
+        y = ops.conv_transpose1d(xd, wd, None, stride=8, padding=4, pre_slope=0.1)
+        y.backward(gy.to(dev))
+        torch.cuda.synchronize()
+        names = [q[0] for q in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert "s2d" in names, names
+    assert rel_l2(y.detach().cpu(), ref.detach()) < TC_TOL
+    assert rel_l2(wd.grad.cpu(), wr.grad) < TC_TOL
+    # the pre-LeakyReLU mask makes a handful of x-gradient elements flip with rounding: compare where |x| is not tiny
+    m = x.abs() > 1e-3
+    assert rel_l2(xd.grad.cpu()[m], xr.grad[m]) < TC_TOL
