@@ -23,9 +23,10 @@
 // Warp roles (640 threads, one persistent CTA per SM, mbarriers only):
 //   warps 0-7   epilogue: SO (TMEM) -> skips (fp32, read-modify-write) and x' (packed)
 //   warps 8-15  gate:     G (TMEM) -> registers -> z operand image (smem)
-//   warp 18     TMA: per stage ONE tensor-map load of the activation window (3-D box: 2 KB rows x 4 groups x hi|lo)
-//               + one bulk copy of the weight stage into a ring of 32 KB slots
-//   warp 19     MMA issuer (elected lane): conv(i) into set i%4, then the skip/out contraction of tile i-1
+//   warps 16-17 TMA loaders, one per tile parity: per stage ONE tensor-map load of the activation window (3-D box: 2 KB
+//               rows x 4 groups x hi|lo) + one bulk copy of the weight stage into that parity's ring of 32 KB slots
+//   warps 18-19 MMA issuers (elected lane), one per tile parity: conv(i) into TMEM set i%4, then -- once the gate has
+//               produced z(i) -- the skip/out contraction of the same tile into the same columns
 // TMEM: 4 accumulator sets of max(G, S+R) <= 128 columns; the tile sequence conv(i+1) | SO(i) keeps the
 // tensor pipe busy while gate(i) runs.
 #include "tc_common.cuh"
@@ -39,7 +40,7 @@ constexpr int WN_NGATE = 256, WN_NEPI = 256;
 // latency-critical roles (TMA loader, MMA issuer) get the highest ids and the wide math roles the lowest: with the roles
 // the other way round the timing variants showed gate / epilogue work ADDING to the pipeline time instead of hiding
 // under it.  TMEM lane quarter = warp id % 4, so the 8-warp roles start at multiples of 4.
-constexpr int WN_W_EPI0 = 0, WN_W_GATE0 = WN_W_EPI0 + WN_NEPI / 32, WN_W_TMA = 18, WN_W_MMA = 19;
+constexpr int WN_W_EPI0 = 0, WN_W_GATE0 = WN_W_EPI0 + WN_NEPI / 32, WN_W_TMA = 17, WN_W_MMA = 19;  // loaders: warps 16, 17; MMA issuers: 18, 19
 constexpr int WN_THREADS = 640;
 constexpr int WN_MAX_SLOTS = 8;
 constexpr int WN_BLK = WN_TT * 16;         // one (8 channel, 128 row) operand block: 2 KB
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
   unsigned char* ring = smem;
   unsigned char* z_buf = smem + (size_t)p.nslot * p.slot_bytes;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(z_buf + p.z_bytes);
-  constexpr int NBAR = 2 * WN_MAX_SLOTS + 4 * 3 + 2;
+  constexpr int NBAR = 2 * WN_MAX_SLOTS + 4 * 3 + 3;
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + NBAR);
   float* bias1 = reinterpret_cast<float*>(tmem_slot + 4);
   float* bias2 = bias1 + p.G;
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
   auto G_FULL = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + i); };
   auto SO_FULL = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + 4 + i); };
   auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + 8 + i); };
-  const unsigned Z_FULL = bar0 + 8u * (2 * WN_MAX_SLOTS + 12), Z_EMPTY = Z_FULL + 8u;
+  auto Z_FULL = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + 12 + i); };  // one per tile parity (= per MMA issuer warp)
+  const unsigned Z_EMPTY = bar0 + 8u * (2 * WN_MAX_SLOTS + 14);
 
   if (tid == 0) {
     for (int i = 0; i < p.nslot; ++i) {
@@ -121,7 +123,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       mbar_init(SO_FULL(i), 1);
       mbar_init(ACC_EMPTY(i), WN_NEPI / 32);
     }
-    mbar_init(Z_FULL, WN_NGATE / 32);
+    mbar_init(Z_FULL(0), WN_NGATE / 32);
+    mbar_init(Z_FULL(1), WN_NGATE / 32);
     mbar_init(Z_EMPTY, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -141,78 +144,60 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
   const int ntl = ((int)p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
   const int conv_stages = p.nxc * p.K + p.ncc;
 
-  if (warp == WN_W_TMA) {
-    // ===================== TMA: activation windows + weight stages =====================
+  // Two independent pipelines, one per tile parity: loader warp r feeds ring r (nslot / 2 slots) with the stages of the
+  // tiles n = r, r + 2, ... in the order conv(n) [P stages], SO(n) [Q weight-only stages]; MMA issuer warp r consumes
+  // them in the same order.  Every mbarrier has exactly one waiter that walks its phases in order (no phase aliasing).
+  const int RS = p.nslot / 2;  // slots per ring
+  if (warp == WN_W_TMA || warp == WN_W_TMA - 1) {
+    // ===================== TMA loaders: activation windows + weight stages =====================
+    const int r = warp - (WN_W_TMA - 1);
+    unsigned char* rbase = ring + (size_t)r * RS * p.slot_bytes;
     int s = 0, ph = 0;
     const unsigned char* w_aux = wpk + (size_t)p.nxc * p.K * p.b_bytes;
     const unsigned char* w_so = w_aux + (size_t)p.ncc * p.b_bytes;
-    auto stage_so = [&](int sc) {
-      mbar_wait_spin(EMPTY(s), ph ^ 1);
-      if (lane == 0) {
-        if (p.variant & 2) {
-          mbar_arrive(FULL(s));
-        } else {
-          mbar_expect_tx(FULL(s), (unsigned)p.b_bytes);
-          bulk_g2s(smem_u32(ring + (size_t)s * p.slot_bytes + p.a_bytes), w_so + (size_t)sc * p.b_bytes, (unsigned)p.b_bytes, FULL(s));
-        }
-      }
-      __syncwarp();
-      if (++s == p.nslot) { s = 0; ph ^= 1; }
-    };
     if (lane == 0) {
       tma_prefetch_desc(&tm_x);
       tma_prefetch_desc(&tm_c);
     }
-    for (int n = 0; n < ntl; ++n) {
+    for (int n = r; n < ntl; n += 2) {
       const int tile = blockIdx.x + n * gridDim.x;
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
-      if (n + 1 < ntl && (p.variant & 32) && lane < conv_stages) {  // measured SLOWER (0.150 vs 0.139 ms): off unless variant bit 32
-        // the NEXT tile's activation windows go to L2 now (one box prefetch per lane): when their turn comes the loads
-        // below see the L2 latency, which the ring depth covers, instead of the HBM latency, which it does not
-        const int tl = tile + (int)gridDim.x;
-        const int bb = tl / p.tiles_per_seq;
-        const int tt0 = (tl - bb * p.tiles_per_seq) * WN_TT;
-        const bool px = lane < p.nxc * p.K;
-        const int chunk = px ? lane / p.K : lane - p.nxc * p.K;
-        const int tap = px ? lane - chunk * p.K : 0;
-        if (px)
-          tma_prefetch_3d(&tm_x, 2 * (p.halo + tt0 + (tap - p.K / 2) * p.D), chunk * 4, 2 * bb);
-        else
-          tma_prefetch_3d(&tm_c, 2 * tt0, chunk * 4, 2 * bb);
-      }
-      __syncwarp();
-      for (int j = 0; j < conv_stages; ++j) {
+      for (int j = 0; j < conv_stages + p.nsc; ++j) {
+        const bool is_so = j >= conv_stages;
         const bool is_x = j < p.nxc * p.K;
-        const int chunk = is_x ? j / p.K : j - p.nxc * p.K;
+        const int chunk = is_so ? j - conv_stages : (is_x ? j / p.K : j - p.nxc * p.K);
         const int tap = is_x ? j - chunk * p.K : 0;
-        mbar_wait_spin(EMPTY(s), ph ^ 1);
+        mbar_wait_spin(EMPTY(r * RS + s), ph ^ 1);
         if (lane == 0) {
           // ONE tensor-map TMA per activation window: box (128 rows x 16 B as 256 8-byte elements, 4 groups, hi|lo) = the
           // 16 KB operand image; groups beyond the tensor (last conditioning chunk) arrive as zeros and count towards the
-          // transaction bytes
-          const unsigned dstA = smem_u32(ring + (size_t)s * p.slot_bytes);
-          const unsigned nb = ((p.variant & 1) ? 0u : (unsigned)p.a_bytes) + ((p.variant & 2) ? 0u : (unsigned)p.b_bytes);
-          if (nb) mbar_expect_tx(FULL(s), nb); else mbar_arrive(FULL(s));
-          if (!(p.variant & 1)) {
+          // transaction bytes.  SO stages carry weights only (their A operand is the z image the gate writes).
+          const unsigned dstA = smem_u32(rbase + (size_t)s * p.slot_bytes);
+          const unsigned full = FULL(r * RS + s);
+          const unsigned nb = ((p.variant & 1) || is_so ? 0u : (unsigned)p.a_bytes) + ((p.variant & 2) ? 0u : (unsigned)p.b_bytes);
+          if (nb) mbar_expect_tx(full, nb); else mbar_arrive(full);
+          if (!(p.variant & 1) && !is_so) {
             if (is_x)
-              tma_load_3d(dstA, &tm_x, 2 * (p.halo + t0 + (tap - p.K / 2) * p.D), chunk * 4, 2 * b, FULL(s));
+              tma_load_3d(dstA, &tm_x, 2 * (p.halo + t0 + (tap - p.K / 2) * p.D), chunk * 4, 2 * b, full);
             else
-              tma_load_3d(dstA, &tm_c, 2 * t0, chunk * 4, 2 * b, FULL(s));
+              tma_load_3d(dstA, &tm_c, 2 * t0, chunk * 4, 2 * b, full);
           }
-          const unsigned char* wsrc = is_x ? wpk + (size_t)j * p.b_bytes : w_aux + (size_t)chunk * p.b_bytes;
-          if (!(p.variant & 2)) bulk_g2s(dstA + (unsigned)p.a_bytes, wsrc, (unsigned)p.b_bytes, FULL(s));
+          const unsigned char* wsrc = is_so ? w_so + (size_t)chunk * p.b_bytes : (is_x ? wpk + (size_t)j * p.b_bytes : w_aux + (size_t)chunk * p.b_bytes);
+          if (!(p.variant & 2)) bulk_g2s(dstA + (unsigned)p.a_bytes, wsrc, (unsigned)p.b_bytes, full);
         }
         __syncwarp();
-        if (++s == p.nslot) { s = 0; ph ^= 1; }
+        if (++s == RS) { s = 0; ph ^= 1; }
       }
-      if (n > 0)
-        for (int sc = 0; sc < p.nsc; ++sc) stage_so(sc);
     }
-    if (ntl > 0)
-      for (int sc = 0; sc < p.nsc; ++sc) stage_so(sc);
-  } else if (warp == WN_W_MMA) {
-    // ===================== MMA issuer (converged warp, elected lane) =====================
+  } else if (warp == WN_W_MMA || warp == WN_W_MMA - 1) {
+    // ===================== MMA issuers (converged warps, elected lane) =====================
+    // A single issuer needs ~170 SASS instructions per pipeline stage (descriptor arithmetic, register -> uniform moves,
+    // 6 UTCHMMA, commit): measured ~930 cycles per stage against the 384 the tensor pipe needs, so two warps alternate
+    // tiles.  Each runs conv(n), then -- once the gate has produced z(n) -- the skip/out contraction SO(n) into the same
+    // (by then dead) TMEM columns; while it waits for the gate the other warp's conv keeps the tensor pipe busy.
+    const int r = warp - (WN_W_MMA - 1);
+    unsigned char* rbase = ring + (size_t)r * RS * p.slot_bytes;
     const unsigned long long hi_const = ((unsigned long long)((128u >> 4) | (1u << 14))) << 32;  // SBO = 128 B, version 1
     const unsigned a_lo = ((unsigned)(WN_BLK >> 4)) << 16;           // LBO of an activation window: next 8-channel block
     const unsigned a_sub = (unsigned)(4 * WN_BLK) >> 4;              // hi -> lo image
@@ -223,32 +208,15 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
     const unsigned z16 = smem_u32(z_buf) >> 4;
     const int cgl = p.ngc - (p.ncc - 1) * 4;
     int s = 0, ph = 0;
-    auto so_tile = [&](int m) {  // skip / out contraction of local tile m into its (now dead) G columns
-      const unsigned d = tmem_base + (unsigned)((m % p.nset) * p.set_cols);
-      mbar_wait_spin(Z_FULL, m & 1);
-      tc_fence_after();
-      for (int sc = 0; sc < p.nsc; ++sc) {
-        mbar_wait_spin(FULL(s), ph);
-        tc_fence_after();
-        const unsigned b16 = smem_u32(ring + (size_t)s * p.slot_bytes + p.a_bytes) >> 4;
-        const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + z16 + (unsigned)(sc * 4 * WN_BLK >> 4));
-        const unsigned long long b_hi = hi_const | (unsigned long long)(b2_lo + b16);
-        if (!(p.variant & 16)) tc_mma_tap6(d, a_hi, b_hi, z_sub, b2_sub, a_step, b2_step, p.idesc2, sc != 0 ? 1u : 0u);
-        tc_commit(EMPTY(s));
-        if (++s == p.nslot) { s = 0; ph ^= 1; }
-      }
-      tc_commit(Z_EMPTY);
-      tc_commit(SO_FULL(m % p.nset));
-    };
-    for (int n = 0; n < ntl; ++n) {
+    for (int n = r, m = 0; n < ntl; n += 2, ++m) {
       const int set = n % p.nset;
+      const unsigned d = tmem_base + (unsigned)(set * p.set_cols);
       mbar_wait_spin(ACC_EMPTY(set), ((n / p.nset) & 1) ^ 1);
       tc_fence_after();
-      const unsigned d = tmem_base + (unsigned)(set * p.set_cols);
       for (int j = 0; j < conv_stages; ++j) {
-        mbar_wait_spin(FULL(s), ph);
+        mbar_wait_spin(FULL(r * RS + s), ph);
         tc_fence_after();
-        const unsigned a16 = smem_u32(ring + (size_t)s * p.slot_bytes) >> 4;
+        const unsigned a16 = smem_u32(rbase + (size_t)s * p.slot_bytes) >> 4;
         const unsigned b16 = a16 + ((unsigned)p.a_bytes >> 4);
         const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + a16);
         const unsigned long long b_hi = hi_const | (unsigned long long)(b1_lo + b16);
@@ -258,13 +226,26 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
           tc_mma_x3_single(d, a_hi, b_hi, a_sub, b1_sub, p.idesc1, j != 0 ? 1u : 0u);
         else
           tc_mma_tap6(d, a_hi, b_hi, a_sub, b1_sub, a_step, b1_step, p.idesc1, j != 0 ? 1u : 0u);
-        tc_commit(EMPTY(s));
-        if (++s == p.nslot) { s = 0; ph ^= 1; }
+        tc_commit(EMPTY(r * RS + s));
+        if (++s == RS) { s = 0; ph ^= 1; }
       }
       tc_commit(G_FULL(set));
-      if (n > 0) so_tile(n - 1);
+      // skip / out contraction of the same tile, once the gate has written z (its tiles of this parity arrive in order)
+      mbar_wait_spin(Z_FULL(r), m & 1);
+      tc_fence_after();
+      for (int sc = 0; sc < p.nsc; ++sc) {
+        mbar_wait_spin(FULL(r * RS + s), ph);
+        tc_fence_after();
+        const unsigned b16 = smem_u32(rbase + (size_t)s * p.slot_bytes + p.a_bytes) >> 4;
+        const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + z16 + (unsigned)(sc * 4 * WN_BLK >> 4));
+        const unsigned long long b_hi = hi_const | (unsigned long long)(b2_lo + b16);
+        if (!(p.variant & 16)) tc_mma_tap6(d, a_hi, b_hi, z_sub, b2_sub, a_step, b2_step, p.idesc2, sc != 0 ? 1u : 0u);
+        tc_commit(EMPTY(r * RS + s));
+        if (++s == RS) { s = 0; ph ^= 1; }
+      }
+      tc_commit(Z_EMPTY);
+      tc_commit(SO_FULL(set));
     }
-    if (ntl > 0) so_tile(ntl - 1);
   } else if (warp >= WN_W_GATE0 && warp < WN_W_GATE0 + WN_NGATE / 32) {
     // ===================== gate: G (TMEM) -> z operand image (smem) =====================
     const int gw = warp - WN_W_GATE0;
@@ -308,7 +289,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();  // one arrival per warp: every lane's z stores and TMEM loads are ordered before it
-      if (lane == 0) mbar_arrive(Z_FULL);
+      if (lane == 0) mbar_arrive(Z_FULL(n & 1));
     }
   } else if (warp < WN_W_EPI0 + WN_NEPI / 32) {
     // ===================== epilogue: SO (TMEM) -> skips (fp32 RMW), x' (packed hi/lo) =====================
@@ -516,11 +497,11 @@ static int wn_plan(const pwgb_wnstack_desc* d, WnK& p, size_t& smem_bytes) {
   int alloc = 32;
   while (alloc < p.nset * width) alloc <<= 1;
   p.tmem_cols = alloc;
-  const size_t fixed = (size_t)p.z_bytes + 8 * (2 * WN_MAX_SLOTS + 14) + 16 + 4 * (size_t)(G + N2) + 128;
+  const size_t fixed = (size_t)p.z_bytes + 8 * (2 * WN_MAX_SLOTS + 15) + 16 + 4 * (size_t)(G + N2) + 128;
   const size_t budget = 227 * 1024;
   if (fixed + 3 * (size_t)p.slot_bytes > budget) return 0;
   int ns = (int)((budget - fixed) / p.slot_bytes);
-  p.nslot = ns > WN_MAX_SLOTS ? WN_MAX_SLOTS : ns;
+  p.nslot = (ns > WN_MAX_SLOTS ? WN_MAX_SLOTS : ns) & ~1;  // two rings (one per MMA issuer) of nslot / 2 slots
   smem_bytes = (size_t)p.nslot * p.slot_bytes + fixed;
   p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(G >> 3) << 17) | ((128u >> 4) << 24);
   p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N2 >> 3) << 17) | ((128u >> 4) << 24);

@@ -29,7 +29,6 @@ CASES = [
     (128, 128, 41, 2, 4, 20, 4096, 1, 4),  # MSD layer 1 (grouped, stride 2)
     (256, 512, 41, 4, 16, 20, 1024, 1, 4),  # MSD layer 3 (cin_g * s = 64)
     (512, 1024, 41, 4, 16, 20, 259, 1, 2),  # MSD layer 4, ragged length
-    (128, 256, 41, 2, 16, 20, 2048, 1, 4),  # MSD layer 2: cin_g * s = 16 -> zero-padded to 32 channels per group
 ]
 
 
@@ -98,7 +97,7 @@ def test_logit_conv_on_tensor_cores(dev, P, rows, B):
         names = [q[0] for q in ops.PROFILE]
     finally:
         ops.PROFILE = None
-    assert "conv1d_tc" in names and "conv1d" not in names, names
+    assert names[0] == "conv1d_tc", names  # forward on the tensor cores (the 16-channel-wide gradients stay on FFMA)
     assert tuple(y.shape) == tuple(ref.shape)
     assert rel_l2(y.detach().cpu(), ref.detach()) < TC_TOL
     assert rel_l2(xd.grad.cpu(), xr.grad) < TC_TOL and rel_l2(wd.grad.cpu(), wr.grad) < TC_TOL and rel_l2(bd.grad.cpu(), br.grad) < TC_TOL
@@ -129,3 +128,52 @@ def test_conv_transpose_dgrad_on_tensor_cores(dev):
     # the pre-LeakyReLU mask makes a handful of x-gradient elements flip with rounding: compare where |x| is not tiny
     m = x.abs() > 1e-3
     assert rel_l2(xd.grad.cpu()[m], xr.grad[m]) < TC_TOL
+
+
+def test_grouped_strided_conv_padded_groups_inference(dev):
+    """MSD layer 2 (128 -> 256, k41, stride 2, 16 groups): cin_g * s = 16 channels per group after the re-layout, zero-padded
+    to 32 for the tensor cores -- used on the no-grad passes only."""
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((4, 128, 2048), 1)
+    w = synth.randn((256, 8, 41), 2, 1.0 / (8 * 41) ** 0.5)
+    b = synth.randn((256,), 3, 0.1)
+    ref = F.leaky_relu(F.conv1d(x, w, b, stride=2, padding=20, groups=16), 0.1)
+    ops.PROFILE = []
+    try:
+        with torch.no_grad():
+            y = ops.conv1d(x.to(dev), w.to(dev), b.to(dev), stride=2, padding=20, groups=16, post_act="lrelu", post_slope=0.1)
+        torch.cuda.synchronize()
+        names = [q[0] for q in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert names == ["s2d", "conv1d_tc"], names
+    assert rel_l2(y.cpu(), ref) < TC_TOL
+
+
+@pytest.mark.parametrize("mode", ["zero", "reflect"])
+def test_mel_input_conv_padded_channels(dev, mode):
+    """80 -> 512 k7 input conv (hifigan.py:80-91 / melgan.py:70-72): channels zero-padded to 96 for the tcgen05 path;
+    forward and gradients vs torch autograd."""
+    from parallelwavegan_b200 import ops
+
+    x = synth.randn((3, 80, 200), 21)
+    w = synth.randn((512, 80, 7), 22, 1.0 / (80 * 7) ** 0.5)
+    b = synth.randn((512,), 23, 0.1)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    xp = F.pad(xr, (3, 3)) if mode == "zero" else F.pad(xr, (3, 3), mode="reflect")
+    ref = F.conv1d(xp, wr, br)
+    gy = synth.randn(tuple(ref.shape), 24)
+    ref.backward(gy)
+    xd, wd, bd = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    ops.PROFILE = []
+    try:
+        y = ops.conv1d(xd, wd, bd, padding=3, pad_mode=mode)
+        y.backward(gy.to(dev))
+        torch.cuda.synchronize()
+        names = [q[0] for q in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert names[0] == "conv1d_tc", names
+    assert rel_l2(y.detach().cpu(), ref.detach()) < TC_TOL
+    assert rel_l2(xd.grad.cpu(), xr.grad) < TC_TOL and rel_l2(wd.grad.cpu(), wr.grad) < TC_TOL and rel_l2(bd.grad.cpu(), br.grad) < TC_TOL
