@@ -117,8 +117,11 @@ PWGB_API int pwgb_conv_transpose1d_forward(const pwgb_convtr1d_desc* d, const fl
  * memory; cout/groups > 256 and groups > 1 run as several launches); everything else stays on
  * pwgb_conv1d_forward.
  * ---------------------------------------------------------------------- */
-/* bring-up aid (not part of the product contract): key 1 = tcgen05 descriptor variant */
+/* bring-up / measurement aids (not part of the product contract): set key 1 = tcgen05 descriptor variant, key 2 = timing
+ * variants of the fused WaveNet kernel (bit 64: record a per-role timeline of CTA 0); get key 2 = that timeline
+ * (8 roles x 32 tiles x 4 stamps, int64 SM clocks), returns bytes copied or -1. */
 PWGB_API void pwgb_debug_set(int key, int value);
+PWGB_API int pwgb_debug_get(int key, void* dst, size_t bytes);
 PWGB_API size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kernel);
 PWGB_API int pwgb_conv1d_tc_pack_weight(const float* w, int cin, int cout, int kernel, void* packed, void* stream);
 /* grouped weights (cout, cin/groups, kernel): one image per (group, <=256-column chunk) */

@@ -907,11 +907,18 @@ static int tc_cout_chunk(int cout);
 
 namespace pwgb {
 extern int g_wn_variant;
+int wn_trace_read(void* dst, size_t bytes);
 }
 
 extern "C" void pwgb_debug_set(int key, int value) {
   if (key == 1) g_tc_variant = value;
   if (key == 2) pwgb::g_wn_variant = value;  // timing experiments of the fused WaveNet kernel (results are NOT valid)
+}
+
+// key 2: timeline of CTA 0 of the last traced fused WaveNet launch (synchronises the device; see wavenet_tc.cu)
+extern "C" int pwgb_debug_get(int key, void* dst, size_t bytes) {
+  if (key == 2 && dst) return pwgb::wn_trace_read(dst, bytes);
+  return -1;
 }
 
 extern "C" size_t pwgb_conv1d_tc_packed_weight_bytes(int cin, int cout, int kernel) {

@@ -89,6 +89,15 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
   }
 }
 
+// Timeline of CTA 0 (pwgb_debug_set(2, 64); read back with pwgb_debug_get(2, ...)): [role][tile][stamp] in SM clocks.
+// roles: 0 epilogue skip half, 1 epilogue residual half, 2 gate, 3 -, 4 / 5 MMA issuers, 6 / 7 loaders
+constexpr int WN_TRACE_TILES = 32;
+__device__ long long g_wn_trace[8][WN_TRACE_TILES][4];
+#define WN_TRACE(role, n, k)                                                                      \
+  do {                                                                                            \
+    if ((p.variant & 64) && blockIdx.x == 0 && lane == 0 && (n) < WN_TRACE_TILES) g_wn_trace[role][n][k] = clock64(); \
+  } while (0)
+
 __global__ void __launch_bounds__(WN_THREADS, 1)
     wavenet_fused_kernel(const WnK p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
                          const uint4* __restrict__ xin, const unsigned char* __restrict__ wpk, const float* __restrict__ b_conv,
@@ -163,8 +172,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       const int tile = blockIdx.x + n * gridDim.x;
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
+      WN_TRACE(6 + r, n, 0);
       for (int j = 0; j < conv_stages + p.nsc; ++j) {
         const bool is_so = j >= conv_stages;
+        if (j == conv_stages) WN_TRACE(6 + r, n, 1);
         const bool is_x = j < p.nxc * p.K;
         const int chunk = is_so ? j - conv_stages : (is_x ? j / p.K : j - p.nxc * p.K);
         const int tap = is_x ? j - chunk * p.K : 0;
@@ -189,6 +200,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         __syncwarp();
         if (++s == RS) { s = 0; ph ^= 1; }
       }
+      WN_TRACE(6 + r, n, 2);
     }
   } else if (warp == WN_W_MMA || warp == WN_W_MMA - 1) {
     // ===================== MMA issuers (converged warps, elected lane) =====================
@@ -213,6 +225,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       const unsigned d = tmem_base + (unsigned)(set * p.set_cols);
       mbar_wait_spin(ACC_EMPTY(set), ((n / p.nset) & 1) ^ 1);
       tc_fence_after();
+      WN_TRACE(4 + r, n, 0);
       for (int j = 0; j < conv_stages; ++j) {
         mbar_wait_spin(FULL(r * RS + s), ph);
         tc_fence_after();
@@ -230,9 +243,11 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         if (++s == RS) { s = 0; ph ^= 1; }
       }
       tc_commit(G_FULL(set));
+      WN_TRACE(4 + r, n, 1);
       // skip / out contraction of the same tile, once the gate has written z (its tiles of this parity arrive in order)
       mbar_wait_spin(Z_FULL(r), m & 1);
       tc_fence_after();
+      WN_TRACE(4 + r, n, 2);
       for (int sc = 0; sc < p.nsc; ++sc) {
         mbar_wait_spin(FULL(r * RS + s), ph);
         tc_fence_after();
@@ -245,6 +260,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       }
       tc_commit(Z_EMPTY);
       tc_commit(SO_FULL(set));
+      WN_TRACE(4 + r, n, 3);
     }
   } else if (warp >= WN_W_GATE0 && warp < WN_W_GATE0 + WN_NGATE / 32) {
     // ===================== gate: G (TMEM) -> z operand image (smem) =====================
@@ -256,8 +272,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
     const int g_begin = (gw >> 2) ? ngrp / 2 : 0, g_end = (gw >> 2) ? ngrp : ngrp / 2;
     for (int n = 0; n < ntl; ++n) {
       const int set = n % p.nset;
+      if (gw == 0) WN_TRACE(2, n, 0);
       mbar_wait_spin(G_FULL(set), (n / p.nset) & 1);
       tc_fence_after();
+      if (gw == 0) WN_TRACE(2, n, 1);
       const unsigned tacc = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(set * p.set_cols);
       bool z_free = false;
       for (int g16 = g_begin; g16 < ((p.variant & 4) ? g_begin : g_end); ++g16) {
@@ -272,6 +290,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         if (!z_free) {  // the previous tile's skip/out MMAs must have retired before z is overwritten
           mbar_wait_spin(Z_EMPTY, (n & 1) ^ 1);
           z_free = true;
+          if (gw == 0) WN_TRACE(2, n, 2);
         }
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
@@ -290,6 +309,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       fence_proxy_async();
       __syncwarp();  // one arrival per warp: every lane's z stores and TMEM loads are ordered before it
       if (lane == 0) mbar_arrive(Z_FULL(n & 1));
+      if (gw == 0) WN_TRACE(2, n, 3);
     }
   } else if (warp < WN_W_EPI0 + WN_NEPI / 32) {
     // ===================== epilogue: SO (TMEM) -> skips (fp32 RMW), x' (packed hi/lo) =====================
@@ -305,6 +325,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
       const int t = t0 + m;
       const bool tv = t < p.T && !(p.variant & 8);
+      if ((ew & 3) == 0) WN_TRACE(ew >> 2, n, 0);
       if (!out_half && !p.skip_init && !(p.variant & 8)) {
         // L2 prefetch of the skip lines two tiles ahead (one 128-byte line per column and warp)
         const int tl = tile + 2 * (int)gridDim.x;
@@ -327,6 +348,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         for (int j = 0; j < 16; ++j) sv[j] = ld ? sq[(long long)j * p.T] : 0.f;
         mbar_wait_spin(SO_FULL(set), (n / p.nset) & 1);
         tc_fence_after();
+        if (ew == 0) WN_TRACE(0, n, 1);
         for (int col = 0; col < p.S; col += 16) {
           unsigned r[16];
           tc_ld16(tacc + (unsigned)col, r);
@@ -353,6 +375,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         }
         mbar_wait_spin(SO_FULL(set), (n / p.nset) & 1);
         tc_fence_after();
+        if (ew == 4) WN_TRACE(1, n, 1);
         for (int col = 0; col < p.R; col += 16) {
           unsigned r[16];
           tc_ld16(tacc + (unsigned)(p.S + col), r);
@@ -393,6 +416,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ACC_EMPTY(set));
+      if ((ew & 3) == 0) WN_TRACE(ew >> 2, n, 2);
     }
   }
   __syncthreads();
@@ -457,6 +481,11 @@ __global__ void wn_first_conv_kernel(const float* __restrict__ z, int cin, const
 }
 
 int g_wn_variant = 0;
+
+int wn_trace_read(void* dst, size_t bytes) {
+  if (bytes > sizeof(long long) * 8 * WN_TRACE_TILES * 4) bytes = sizeof(long long) * 8 * WN_TRACE_TILES * 4;
+  return cudaMemcpyFromSymbol(dst, g_wn_trace, bytes) == cudaSuccess ? (int)bytes : -1;
+}
 
 static int wn_plan(const pwgb_wnstack_desc* d, WnK& p, size_t& smem_bytes) {
   if (!d || d->batch < 0 || d->t <= 0 || d->kernel <= 0 || d->kernel % 2 == 0 || d->halo < 0) return 0;

@@ -233,7 +233,8 @@ def test_hifigan_train_step_gradients(dev):
         assert rel_l2(p.detach().cpu(), pr_) < GTOL, k
         # the first Adam update is lr * sign(g) wherever |g| >> eps: it only differs where the gradient sign differs
         upd_o, upd_r = (p.detach() - before[k]).cpu(), pr_ - sd[k]
-        agree = float(((upd_o * upd_r) > 0).float().mean())
+        clear = gr.abs() > 0.05 * gr.abs().mean()  # elements whose gradient is not within rounding of zero
+        agree = float(((upd_o * upd_r) > 0)[clear].float().mean())
         assert agree > 0.98, (k, agree)
 
 
@@ -327,23 +328,34 @@ def test_causal_hifigan_gradients(dev):
     g.load_state_dict(sd)
     c = synth.randn((2, 80, 32), 23)
     y = synth.randn((2, 1, 32 * 64), 24, 0.3)
-    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    c_ref = c.clone().requires_grad_(True)
-    y_ref = ref_ops.hifigan_generator(ref_ops.fold_weight_norm(leaf), c_ref, dict(kw, negative_slope=0.1))
     melmat = torch.from_numpy(ref_ops.slaney_mel_filterbank(22050, 1024, 80, 0, 11025).T.copy())
-    ref_ops.mel_loss(y_ref, y, melmat, log_base=None).backward()
+    keep = {}
 
+    def oracle(leaves):
+        leaf = {k: v.clone().requires_grad_(True) for k, v in leaves.items() if k != "__c"}
+        c_ref = leaves["__c"].clone().requires_grad_(True)
+        y_ref = ref_ops.hifigan_generator(ref_ops.fold_weight_norm(leaf), c_ref, dict(kw, negative_slope=0.1))
+        ref_ops.mel_loss(y_ref, y, melmat, log_base=None).backward()
+        keep.setdefault("y", y_ref.detach())
+        out = {k: v.grad for k, v in leaf.items()}
+        out["__c"] = c_ref.grad
+        return out
+
+    ref, tol, obs = conditioning_tolerances(oracle, dict(sd, __c=c))
     g = g.to(dev).train()
     mel_fn = losses.MelSpectrogramLoss(fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80,
                                        fmin=0, fmax=11025, log_base=None).to(dev)
     c_o = c.to(dev).requires_grad_(True)
     y_hat = g(c_o)
-    assert rel_l2(y_hat.detach().cpu(), y_ref.detach()) < GTOL
+    assert rel_l2(y_hat.detach().cpu(), keep["y"]) < GTOL
     mel_fn(y_hat, y.to(dev)).backward()
-    assert rel_l2(c_o.grad.cpu(), c_ref.grad) < 5e-3
-    for k, p in g.named_parameters():
-        e = rel_l2(p.grad.cpu(), leaf[k].grad)
-        assert e < 5e-3, (k, e)
+    bad = []
+    for k, gr in [("__c", c_o.grad)] + [(k, p.grad) for k, p in g.named_parameters()]:
+        e = rel_l2(gr.cpu(), ref[k])
+        if e >= tol[k]:
+            bad.append((k, round(e, 5), round(tol[k], 5), round(obs[k], 6)))
+    print("CAUSAL-HIFIGAN loose bounds", [(k, round(t, 5)) for k, t in tol.items() if t > 1e-3][:8])
+    assert not bad, bad
 
 
 def test_pwg_train_step_gradients(dev):
@@ -366,21 +378,31 @@ def test_pwg_train_step_gradients(dev):
     z = synth.randn((B, 1, frames * 256), 54)
     y = synth.randn((B, 1, frames * 256), 55, 0.3)
 
-    leaf_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     leaf_d = {k: v.clone() for k, v in dsd.items()}
-    wg = ref_ops.fold_weight_norm(leaf_g)
     wd = ref_ops.fold_weight_norm(leaf_d)
     cfg = dict(kw, upsample_scales=[4, 4, 4, 4])
-    y_ref = ref_ops.pwg_generator(wg, z, c, cfg)
-    sc, mag = ref_ops.mr_stft_loss(y_ref.squeeze(1), y.squeeze(1))
-    adv = F.mse_loss(ref_ops.pwg_discriminator(wd, y_ref, layers=5), torch.ones(B, 1, frames * 256))
-    names = list(leaf_g)
+    names = list(sd)
+    keep = {}
 
-    def grads_ref(loss):
-        gs = torch.autograd.grad(loss, [leaf_g[k] for k in names], retain_graph=True, allow_unused=True)
-        return {k: (v if v is not None else torch.zeros_like(leaf_g[k])) for k, v in zip(names, gs)}
+    def oracle(leaves):
+        leaf_g = {k: v.clone().requires_grad_(True) for k, v in leaves.items()}
+        y_ref = ref_ops.pwg_generator(ref_ops.fold_weight_norm(leaf_g), z, c, cfg)
+        sc, mag = ref_ops.mr_stft_loss(y_ref.squeeze(1), y.squeeze(1))
+        adv = F.mse_loss(ref_ops.pwg_discriminator(wd, y_ref, layers=5), torch.ones(B, 1, frames * 256))
+        keep.setdefault("v", (y_ref.detach(), sc.detach(), mag.detach(), adv.detach()))
+        out = {}
+        for term, loss in (("stft", sc + mag), ("adv", adv), ("out", (y_ref * y).sum())):
+            gs = torch.autograd.grad(loss, [leaf_g[k] for k in names], retain_graph=True, allow_unused=True)
+            for k, v in zip(names, gs):
+                out[term + "/" + k] = v if v is not None else torch.zeros_like(leaf_g[k])
+        return out
 
-    ref_terms = {"stft": grads_ref(sc + mag), "adv": grads_ref(adv), "out": grads_ref((y_ref * y).sum())}
+    # tolerance per (loss term, tensor): 1e-3 unless the oracle itself moves more under fp32-rounding-sized
+    # perturbations of the weights (weight_g gradients of the 1-channel upsampling convs are <dL/dc, c>/g:
+    # one cancelling sum shared by all four layers; the STFT loss goes through sign(log ratio) and 1/x)
+    ref_all, tol, obs = conditioning_tolerances(oracle, sd)
+    y_ref, sc, mag, adv = keep["v"]
+    ref_terms = {t: {k: ref_all[t + "/" + k] for k in names} for t in ("stft", "adv", "out")}
 
     g = g.to(dev).train()
     d = d.to(dev).train()
@@ -413,9 +435,9 @@ def test_pwg_train_step_gradients(dev):
                 assert float(ours[term][k].abs().max()) < 1e-5, (term, k)
                 continue
             e = rel_l2(ours[term][k].cpu(), r)
-            # 2e-2: weight_g gradients are cancelling sums and the STFT-loss gradient goes through sign(log ratio)
-            # and 1/x terms ("numerically touchy"); typical error is 1e-4
-            if e >= 2e-2:
-                bad.append((term, k, round(e, 4)))
-    print("PWG-GRAD-BAD", len(bad), bad)
+            t_ = tol[term + "/" + k]
+            if e >= t_:
+                bad.append((term, k, round(e, 5), round(t_, 5), round(obs[term + "/" + k], 6)))
+    loose = [(n, round(t_, 4)) for n, t_ in tol.items() if t_ > 1e-3]
+    print("PWG-GRAD-BAD", len(bad), bad, "; bounds above 1e-3:", len(loose), "of", len(tol), loose[:8])
     assert not bad, bad[:12]
