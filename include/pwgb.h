@@ -218,10 +218,10 @@ PWGB_API int pwgb_s2d_backward(const float* gy, float* gx, int batch, int channe
  * (layers/residual_block.py:102-140) used by ParallelWaveGANGenerator.forward's layer loop
  * (models/parallel_wavegan.py:161-166).  Between layers the residual stream x and the conditioning c
  * stay in the tensor core's operand layout, split bf16 hi/lo (same bytes per sample as fp32):
- *   xpk [batch][hi|lo][residual_channels/8][t_pad][8] bf16, t_pad = 2*halo + round_up(t,128); rows
+ *   xpk [batch][hi|lo][residual_channels/8][t_pad][8] bf16, t_pad = 2*halo + round_up(t,256); rows
  *       [halo, halo+t) hold the samples; every other row MUST be zero (allocate zero-filled once; the
  *       kernels only ever write rows [halo, halo+t));
- *   cpk [batch][hi|lo][ceil(aux_channels/8)][round_up(t,128)][8] bf16 (written completely by pack_c).
+ *   cpk [batch][hi|lo][ceil(aux_channels/8)][round_up(t,256)][8] bf16 (written completely by pack_c).
  * halo >= (kernel-1)/2 * (largest dilation of the stack).  Weights: the image written by
  * pwgb_wavenet_pack() for the same channel counts with the aux weight padded to a multiple of 32
  * channels (desc.aux_channels there = round_up(aux_channels, 32)).  b_skip_out = concat(b_skip, b_out).

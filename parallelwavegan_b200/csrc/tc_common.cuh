@@ -47,6 +47,27 @@ __device__ __forceinline__ void mbar_wait_spin(unsigned bar, unsigned parity) {
     }
   }
 }
+// Long waits of the wide roles: the thread is suspended in hardware until the phase completes (or `hint_ns` passed), so a
+// waiting warp issues almost nothing -- plain try_wait loops were 35-40 % of the executed instructions of the fused
+// WaveNet kernel's gate / epilogue warps.
+__device__ __forceinline__ void mbar_wait_hint(unsigned bar, unsigned parity, unsigned hint_ns = 20000u) {
+  unsigned n = 0;
+  for (;;) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    if (ok) break;
+    if (++n > SPIN_LIMIT) {
+      printf("pwgb: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
 // Same with a sleep back-off: waiting warps must not steal issue slots from the working ones
 // (spin loops were 17% of all executed instructions in the first persistent version).
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {

@@ -11,24 +11,31 @@
 //
 // Data layout: between layers the residual stream and the conditioning live in HBM in the tensor core's
 // operand layout, split bf16 hi/lo (the same bytes per sample as fp32):
-//   xpk [batch][hi|lo][R/8][t_pad][8 ch] bf16,  t_pad = 2*halo + round_up(t, 128); rows [halo, halo + t) hold
-//       the samples, every other row is zero (the conv's zero padding and the tail of the last tile);
-//   cpk [batch][hi|lo][ceil(A/8)][round_up(t, 128)][8 ch] bf16.
-// A (32 channel, 128 row) operand window of any tap / dilation is then a 4-D box of the packed tensor: the
-// activation side of a pipeline stage is ONE cp.async.bulk.tensor (TMA), the weight side one 16 KB bulk copy, and no
-// thread ever converts or re-lays-out an input (the conversion happens once, in the epilogue that
-// produces the value).  x = hi + lo carries 16 mantissa bits -- exactly what the bf16x3 MMA consumes;
-// the residual add sees the same value.
+//   xpk [batch][hi|lo][R/8][t_pad][8 ch] bf16,  t_pad = 2*halo + round_up(t, 256); rows [halo, halo + t) hold
+//       the samples, every other row is zero (the conv's zero padding and the tail of the last tile pair);
+//   cpk [batch][hi|lo][ceil(A/8)][round_up(t, 256)][8 ch] bf16.
+// A (32 channel, 128 row) operand window of any tap / dilation is then a 3-D box of the packed tensor (planes described
+// as vectors of 8-byte elements: 2 KB inner extent): the activation side of a pipeline stage is two cp.async.bulk.tensor
+// (TMA), the weight side one 16 KB bulk copy, and no thread ever converts or re-lays-out an input (the conversion
+// happens once, in the epilogue that produces the value).  x = hi + lo carries 16 mantissa bits -- exactly what the
+// bf16x3 MMA consumes; the residual add sees the same value.
 //
-// Warp roles (640 threads, one persistent CTA per SM, mbarriers only):
-//   warps 0-7   epilogue: SO (TMEM) -> skips (fp32, read-modify-write) and x' (packed)
+// What bounds the kernel (timeline of a CTA, tools/wn_trace.py): the L2 -> SM path.  With one 128-sample tile per
+// weight stage an SM ingests 384 KB per tile (3 taps x 2 chunks of x, 3 chunks of c, 11 weight stages of 16 KB, the
+// epilogue's skip / residual reads) against 104 KB of algorithmic input -- ~6000 cycles at the SM's 64 B/clk port, the
+// whole HBM-roofline budget of a tile.  So a work item is a PAIR of adjacent tiles that shares every weight stage, and
+// the skip / out weights stay resident in shared memory: 272 KB per tile.
+//
+// Warp roles (640 threads, one persistent CTA per SM, mbarriers only; setmaxnreg moves registers from the single-warp
+// roles and the gate to the epilogue):
+//   warps 0-7   epilogue: SO (TMEM) -> skips (fp32, read-modify-write) and x' (packed); all global reads of a tile are
+//               requested before its accumulator is waited for
 //   warps 8-15  gate:     G (TMEM) -> registers -> z operand image (smem)
-//   warps 16-17 TMA loaders, one per tile parity: per stage ONE tensor-map load of the activation window (3-D box: 2 KB
-//               rows x 4 groups x hi|lo) + one bulk copy of the weight stage into that parity's ring of 32 KB slots
-//   warps 18-19 MMA issuers (elected lane), one per tile parity: conv(i) into TMEM set i%4, then -- once the gate has
-//               produced z(i) -- the skip/out contraction of the same tile into the same columns
-// TMEM: 4 accumulator sets of max(G, S+R) <= 128 columns; the tile sequence conv(i+1) | SO(i) keeps the
-// tensor pipe busy while gate(i) runs.
+//   warp  16    TMA loader: per stage two tensor-map loads (the pair's activation windows) + one bulk copy of the weight
+//               stage into a ring of 48 KB slots
+//   warps 17-18 conv issuers (elected lane): warp r issues tile r of every pair into TMEM set 2 (pair & 1) + r
+//   warp  19    skip / out issuer: once the gate has produced z(i), SO(i) = z(i) x resident weights into the columns of G(i)
+// TMEM: 4 accumulator sets of max(G, S+R) <= 128 columns = two tile pairs in flight.
 #include "tc_common.cuh"
 #include "tma.cuh"
 
@@ -40,10 +47,11 @@ constexpr int WN_NGATE = 256, WN_NEPI = 256;
 // latency-critical roles (TMA loader, MMA issuer) get the highest ids and the wide math roles the lowest: with the roles
 // the other way round the timing variants showed gate / epilogue work ADDING to the pipeline time instead of hiding
 // under it.  TMEM lane quarter = warp id % 4, so the 8-warp roles start at multiples of 4.
-constexpr int WN_W_EPI0 = 0, WN_W_GATE0 = WN_W_EPI0 + WN_NEPI / 32, WN_W_TMA = 17, WN_W_MMA = 19;  // loaders: warps 16, 17; MMA issuers: 18, 19
+constexpr int WN_W_GATE0 = 0, WN_W_EPI0 = WN_W_GATE0 + WN_NGATE / 32, WN_W_TMA = 16, WN_W_CONV = 17, WN_W_SO = 19;  // loader 16; conv issuers 17, 18; skip/out issuer 19
 constexpr int WN_THREADS = 640;
 constexpr int WN_MAX_SLOTS = 8;
 constexpr int WN_BLK = WN_TT * 16;         // one (8 channel, 128 row) operand block: 2 KB
+constexpr int WN_STAGE_BYTES = 16 * WN_TT * 4;  // epilogue staging: 16 channels x 128 samples x 4 B
 
 struct WnK {
   int B, T, R, G, S, A, K, D, halo;
@@ -52,11 +60,12 @@ struct WnK {
   int ngx, ngc;          // 8-channel groups of x / c
   int nxc, ncc, nsc;     // 32-channel chunks of x, c and z
   int N2;                // S + R
-  int tiles_per_seq, total_tiles;
-  int nslot, a_bytes, b_bytes, slot_bytes, z_bytes;
+  int pairs_per_seq, total_pairs;  // work item: a pair of adjacent 128-sample tiles
+  int nslot, a_bytes, b_bytes, slot_bytes, z_bytes, wso_bytes;
   int nset, set_cols, tmem_cols;
   int write_x, skip_init;
-  int variant;  // timing experiments only (pwgb_debug_set(2, v)): 1 no activation TMA, 2 no weight copies, 4 no gate math, 8 no epilogue memory traffic, 16 no MMAs, 32 WITH L2 prefetch of the next tile's windows
+  int skip_tma;          // skips through the staging buffer + TMA reduce (needs T % 4 == 0: 16-byte row pitch)
+  int variant;  // timing experiments only (pwgb_debug_set(2, v)): 1 no activation TMA, 2 no weight copies, 4 no gate math, 8 no epilogue memory traffic, 16 no MMAs, 32 no x' stores, 64 timeline of CTA 0, 128 no skip stores, 256 skips stored instead of reduced
   unsigned idesc1, idesc2;
 };
 
@@ -66,12 +75,13 @@ __device__ __forceinline__ float ex2_approx(float v) {
   return r;
 }
 // tanh(a) * sigmoid(b) = (Ea - 1) / ((Ea + 1)(1 + Eb)), Ea = e^{2a}, Eb = e^{-b}: two ex2 and one rcp.
-// Absolute error ~3e-7 (ex2.approx: 2^-22 relative); |a| is clamped where tanh is 1 to fp32 precision.
-__device__ __forceinline__ float gate_fast(float a, float b) {
-  a = fminf(fmaxf(a, -15.f), 15.f);
-  b = fmaxf(b, -80.f);
-  const float ea = ex2_approx(a * 2.8853900817779268f);
-  const float eb = ex2_approx(b * -1.4426950408889634f);
+// Absolute error ~3e-7 (ex2.approx: 2^-22 relative).  The accumulators arrive without bias; the biases are pre-scaled
+// (ba = 2 log2(e) b_a, bb = -log2(e) b_b) so that one FFMA per operand produces the ex2 argument.  Only a needs a clamp
+// (Ea = inf would give inf * 0); b -> -inf gives Eb = inf and the quotient 0, the correct limit.
+__device__ __forceinline__ float gate_fast(float ga, float gb, float ba, float bb) {
+  const float a2 = fminf(fmaf(ga, 2.8853900817779268f, ba), 43.28f);
+  const float ea = ex2_approx(a2);
+  const float eb = ex2_approx(fmaf(gb, -1.4426950408889634f, bb));
   return __fdividef(ea - 1.f, (ea + 1.f) * (1.f + eb));
 }
 
@@ -89,27 +99,45 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
   }
 }
 
-// Timeline of CTA 0 (pwgb_debug_set(2, 64); read back with pwgb_debug_get(2, ...)): [role][tile][stamp] in SM clocks.
-// roles: 0 epilogue skip half, 1 epilogue residual half, 2 gate, 3 -, 4 / 5 MMA issuers, 6 / 7 loaders
+// Timeline of CTA 0 (pwgb_debug_set(2, 64); read back with pwgb_debug_get(2, ...)): [role][index][stamp] in SM clocks.
+// roles: 0 epilogue skip half, 1 epilogue residual half, 2 gate, 3 skip/out issuer (index = tile of this CTA);
+//        4 / 5 conv issuers, 6 loader (index = tile pair of this CTA)
 constexpr int WN_TRACE_TILES = 32;
 __device__ long long g_wn_trace[8][WN_TRACE_TILES][4];
 #define WN_TRACE(role, n, k)                                                                      \
   do {                                                                                            \
-    if ((p.variant & 64) && blockIdx.x == 0 && lane == 0 && (n) < WN_TRACE_TILES) g_wn_trace[role][n][k] = clock64(); \
+    if (TRACE && blockIdx.x == 0 && lane == 0 && (n) < WN_TRACE_TILES) g_wn_trace[role][n][k] = clock64(); \
   } while (0)
 
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+      "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// CR / CS: compile-time residual / skip channel counts (0 = read them from the descriptor)
+template <int CR, int CS, bool TRACE>
 __global__ void __launch_bounds__(WN_THREADS, 1)
     wavenet_fused_kernel(const WnK p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_c,
+                         const __grid_constant__ CUtensorMap tm_xo, const __grid_constant__ CUtensorMap tm_s,
                          const uint4* __restrict__ xin, const unsigned char* __restrict__ wpk, const float* __restrict__ b_conv,
                          const float* __restrict__ b_so, uint4* __restrict__ xout, float* __restrict__ skips) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: ring[nslot] (A 16 KB | B) | z image | barriers | tmem slot | bias (G + N2 floats)
+  // layout: ring[nslot] (A0 16 KB | A1 16 KB | B 16 KB) | resident skip/out weights | z image | barriers | tmem slot | bias
   unsigned char* ring = smem;
-  unsigned char* z_buf = smem + (size_t)p.nslot * p.slot_bytes;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(z_buf + p.z_bytes);
-  constexpr int NBAR = 2 * WN_MAX_SLOTS + 4 * 3 + 3;
+  unsigned char* wso_buf = smem + (size_t)p.nslot * p.slot_bytes;
+  unsigned char* z_buf = wso_buf + p.wso_bytes;
+  unsigned char* stage_s = z_buf + p.z_bytes;  // 16 KB: one 2 KB slice per epilogue warp (32 samples x 16 channels; TMA store / reduce source)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(stage_s + 2 * WN_STAGE_BYTES);
+  constexpr int NBAR = 2 * WN_MAX_SLOTS + 16;  // 15 used; 256 bytes keep the bias arrays 16-byte aligned
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + NBAR);
-  float* bias1 = reinterpret_cast<float*>(tmem_slot + 4);
+  float* bias1 = reinterpret_cast<float*>(tmem_slot + 4);  // 16-byte aligned (float4 reads)
   float* bias2 = bias1 + p.G;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -119,118 +147,133 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
   auto G_FULL = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + i); };
   auto SO_FULL = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + 4 + i); };
   auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + 8 + i); };
-  auto Z_FULL = [&](int i) { return bar0 + 8u * (2 * WN_MAX_SLOTS + 12 + i); };  // one per tile parity (= per MMA issuer warp)
-  const unsigned Z_EMPTY = bar0 + 8u * (2 * WN_MAX_SLOTS + 14);
+  const unsigned Z_FULL = bar0 + 8u * (2 * WN_MAX_SLOTS + 12);
+  const unsigned Z_EMPTY = bar0 + 8u * (2 * WN_MAX_SLOTS + 13);
+  const unsigned WSO_FULL = bar0 + 8u * (2 * WN_MAX_SLOTS + 14);
 
   if (tid == 0) {
     for (int i = 0; i < p.nslot; ++i) {
       mbar_init(FULL(i), 1);
-      mbar_init(EMPTY(i), 1);
+      mbar_init(EMPTY(i), 2);  // one tcgen05.commit per conv issuer
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(G_FULL(i), 1);
       mbar_init(SO_FULL(i), 1);
       mbar_init(ACC_EMPTY(i), WN_NEPI / 32);
     }
-    mbar_init(Z_FULL(0), WN_NGATE / 32);
-    mbar_init(Z_FULL(1), WN_NGATE / 32);
+    mbar_init(Z_FULL, WN_NGATE / 32);
     mbar_init(Z_EMPTY, 1);
+    mbar_init(WSO_FULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == WN_W_MMA) {
+  if (warp == WN_W_SO) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((unsigned)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < p.G; i += WN_THREADS) bias1[i] = b_conv ? __ldg(b_conv + i) : 0.f;
-  for (int i = tid; i < p.N2; i += WN_THREADS) bias2[i] = b_so ? __ldg(b_so + i) : 0.f;
+  const int R = CR ? CR : p.R, S = CS ? CS : p.S, H = (CR && CS) ? (CR + CS) / 2 : p.H;
+  // biases, pre-scaled for their consumers: gate a-half by 2 log2(e), b-half by -log2(e); residual half of the output by sqrt(1/2)
+  for (int i = tid; i < p.G; i += WN_THREADS) bias1[i] = (b_conv ? __ldg(b_conv + i) : 0.f) * (i < H ? 2.8853900817779268f : -1.4426950408889634f);
+  for (int i = tid; i < p.N2; i += WN_THREADS) bias2[i] = (b_so ? __ldg(b_so + i) : 0.f) * (i < S ? 1.f : 0.70710678118654752440f);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
 
-  const int ntl = ((int)p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  // Work item = a PAIR of adjacent 128-sample tiles (256 samples): every weight stage is fetched once and multiplied with
+  // both tiles' activation windows.  Pair n of this CTA uses the TMEM sets 2 (n & 1) + {0, 1}: two pairs are in flight.
+  const int npairs = ((int)p.total_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int conv_stages = p.nxc * p.K + p.ncc;
+  const unsigned char* w_aux = wpk + (size_t)p.nxc * p.K * p.b_bytes;
+  const unsigned char* w_so = w_aux + (size_t)p.ncc * p.b_bytes;
 
-  // Two independent pipelines, one per tile parity: loader warp r feeds ring r (nslot / 2 slots) with the stages of the
-  // tiles n = r, r + 2, ... in the order conv(n) [P stages], SO(n) [Q weight-only stages]; MMA issuer warp r consumes
-  // them in the same order.  Every mbarrier has exactly one waiter that walks its phases in order (no phase aliasing).
-  const int RS = p.nslot / 2;  // slots per ring
-  if (warp == WN_W_TMA || warp == WN_W_TMA - 1) {
-    // ===================== TMA loaders: activation windows + weight stages =====================
-    const int r = warp - (WN_W_TMA - 1);
-    unsigned char* rbase = ring + (size_t)r * RS * p.slot_bytes;
-    int s = 0, ph = 0;
-    const unsigned char* w_aux = wpk + (size_t)p.nxc * p.K * p.b_bytes;
-    const unsigned char* w_so = w_aux + (size_t)p.ncc * p.b_bytes;
+  if (warp >= WN_W_TMA) {
+    // the four single-warp roles form one warpgroup: hand their registers to the epilogue warpgroups
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  }
+  if (warp == WN_W_TMA) {
+    // ===================== TMA loader: activation windows + weight stages (every mbarrier below has in-order waiters only)
     if (lane == 0) {
       tma_prefetch_desc(&tm_x);
       tma_prefetch_desc(&tm_c);
+      // skip / out weights stay resident for the whole kernel
+      mbar_expect_tx(WSO_FULL, (unsigned)p.wso_bytes);
+      for (int sc = 0; sc < p.nsc; ++sc)
+        bulk_g2s(smem_u32(wso_buf) + (unsigned)(sc * p.b_bytes), w_so + (size_t)sc * p.b_bytes, (unsigned)p.b_bytes, WSO_FULL);
     }
-    for (int n = r; n < ntl; n += 2) {
-      const int tile = blockIdx.x + n * gridDim.x;
-      const int b = tile / p.tiles_per_seq;
-      const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
-      WN_TRACE(6 + r, n, 0);
-      for (int j = 0; j < conv_stages + p.nsc; ++j) {
-        const bool is_so = j >= conv_stages;
-        if (j == conv_stages) WN_TRACE(6 + r, n, 1);
+    int s = 0, ph = 0;
+    for (int n = 0; n < npairs; ++n) {
+      const int pair = blockIdx.x + n * gridDim.x;
+      const int b = pair / p.pairs_per_seq;
+      const int t0 = (pair - b * p.pairs_per_seq) * (2 * WN_TT);
+      WN_TRACE(6, n, 0);
+      long long w_empty = 0;
+      for (int j = 0; j < conv_stages; ++j) {
         const bool is_x = j < p.nxc * p.K;
-        const int chunk = is_so ? j - conv_stages : (is_x ? j / p.K : j - p.nxc * p.K);
+        const int chunk = is_x ? j / p.K : j - p.nxc * p.K;
         const int tap = is_x ? j - chunk * p.K : 0;
-        mbar_wait_spin(EMPTY(r * RS + s), ph ^ 1);
+        {
+          const long long w0 = TRACE ? clock64() : 0;
+          mbar_wait_spin(EMPTY(s), ph ^ 1);
+          if (TRACE) w_empty += clock64() - w0;
+        }
         if (lane == 0) {
-          // ONE tensor-map TMA per activation window: box (128 rows x 16 B as 256 8-byte elements, 4 groups, hi|lo) = the
-          // 16 KB operand image; groups beyond the tensor (last conditioning chunk) arrive as zeros and count towards the
-          // transaction bytes.  SO stages carry weights only (their A operand is the z image the gate writes).
-          const unsigned dstA = smem_u32(rbase + (size_t)s * p.slot_bytes);
-          const unsigned full = FULL(r * RS + s);
-          const unsigned nb = ((p.variant & 1) || is_so ? 0u : (unsigned)p.a_bytes) + ((p.variant & 2) ? 0u : (unsigned)p.b_bytes);
+          // Two tensor-map TMAs per stage (one per tile of the pair): box (128 rows x 16 B as 256 8-byte elements, 4 groups,
+          // hi|lo) = a 16 KB operand image; groups beyond the tensor (last conditioning chunk) arrive as zeros and
+          // count towards the transaction bytes.  One 16 KB bulk copy brings the weight stage both tiles share.
+          const unsigned dstA = smem_u32(ring + (size_t)s * p.slot_bytes);
+          const unsigned full = FULL(s);
+          const unsigned nb = ((p.variant & 1) ? 0u : 2u * (unsigned)p.a_bytes) + ((p.variant & 2) ? 0u : (unsigned)p.b_bytes);
           if (nb) mbar_expect_tx(full, nb); else mbar_arrive(full);
-          if (!(p.variant & 1) && !is_so) {
-            if (is_x)
-              tma_load_3d(dstA, &tm_x, 2 * (p.halo + t0 + (tap - p.K / 2) * p.D), chunk * 4, 2 * b, full);
-            else
+          if (!(p.variant & 1)) {
+            if (is_x) {
+              const int row = 2 * (p.halo + t0 + (tap - p.K / 2) * p.D);
+              tma_load_3d(dstA, &tm_x, row, chunk * 4, 2 * b, full);
+              tma_load_3d(dstA + (unsigned)p.a_bytes, &tm_x, row + 2 * WN_TT, chunk * 4, 2 * b, full);
+            } else {
               tma_load_3d(dstA, &tm_c, 2 * t0, chunk * 4, 2 * b, full);
+              tma_load_3d(dstA + (unsigned)p.a_bytes, &tm_c, 2 * t0 + 2 * WN_TT, chunk * 4, 2 * b, full);
+            }
           }
-          const unsigned char* wsrc = is_so ? w_so + (size_t)chunk * p.b_bytes : (is_x ? wpk + (size_t)j * p.b_bytes : w_aux + (size_t)chunk * p.b_bytes);
-          if (!(p.variant & 2)) bulk_g2s(dstA + (unsigned)p.a_bytes, wsrc, (unsigned)p.b_bytes, full);
+          const unsigned char* wsrc = is_x ? wpk + (size_t)j * p.b_bytes : w_aux + (size_t)chunk * p.b_bytes;
+          if (!(p.variant & 2)) bulk_g2s(dstA + 2u * (unsigned)p.a_bytes, wsrc, (unsigned)p.b_bytes, full);
         }
         __syncwarp();
-        if (++s == RS) { s = 0; ph ^= 1; }
+        if (++s == p.nslot) { s = 0; ph ^= 1; }
       }
-      WN_TRACE(6 + r, n, 2);
+      WN_TRACE(6, n, 1);
+      if (TRACE && blockIdx.x == 0 && lane == 0 && n < WN_TRACE_TILES) g_wn_trace[6][n][2] = w_empty;
     }
-  } else if (warp == WN_W_MMA || warp == WN_W_MMA - 1) {
-    // ===================== MMA issuers (converged warps, elected lane) =====================
-    // A single issuer needs ~170 SASS instructions per pipeline stage (descriptor arithmetic, register -> uniform moves,
-    // 6 UTCHMMA, commit): measured ~930 cycles per stage against the 384 the tensor pipe needs, so two warps alternate
-    // tiles.  Each runs conv(n), then -- once the gate has produced z(n) -- the skip/out contraction SO(n) into the same
-    // (by then dead) TMEM columns; while it waits for the gate the other warp's conv keeps the tensor pipe busy.
-    const int r = warp - (WN_W_MMA - 1);
-    unsigned char* rbase = ring + (size_t)r * RS * p.slot_bytes;
+  } else if (warp == WN_W_CONV || warp == WN_W_CONV + 1) {
+    // ===================== conv issuers (converged warps, elected lane): warp r owns tile r of every pair =====================
+    // One warp needs ~170 SASS instructions per 6-MMA stage (descriptor arithmetic, register -> uniform moves, commit), more
+    // than twice the 384 cycles the tensor pipe needs for them, so the two tiles of a pair are issued by two warps that
+    // walk the same ring; a slot is released when both have committed (EMPTY count 2).
+    const int r = warp - WN_W_CONV;
     const unsigned long long hi_const = ((unsigned long long)((128u >> 4) | (1u << 14))) << 32;  // SBO = 128 B, version 1
     const unsigned a_lo = ((unsigned)(WN_BLK >> 4)) << 16;           // LBO of an activation window: next 8-channel block
     const unsigned a_sub = (unsigned)(4 * WN_BLK) >> 4;              // hi -> lo image
     const unsigned a_step = (unsigned)(2 * WN_BLK) >> 4;             // second 16-channel K-step
-    const unsigned z_sub = (unsigned)(p.H / 8 * WN_BLK) >> 4;
-    const unsigned b1_lo = (((unsigned)p.G) & 0x3FFFu) << 16, b2_lo = (((unsigned)p.N2) & 0x3FFFu) << 16;
-    const unsigned b1_sub = 4u * p.G, b2_sub = 4u * p.N2, b1_step = 2u * p.G, b2_step = 2u * p.N2;
-    const unsigned z16 = smem_u32(z_buf) >> 4;
+    const unsigned b1_lo = (((unsigned)p.G) & 0x3FFFu) << 16;
+    const unsigned b1_sub = 4u * p.G, b1_step = 2u * p.G;
     const int cgl = p.ngc - (p.ncc - 1) * 4;
     int s = 0, ph = 0;
-    for (int n = r, m = 0; n < ntl; n += 2, ++m) {
-      const int set = n % p.nset;
+    for (int n = 0; n < npairs; ++n) {
+      const int set = 2 * (n & 1) + r;
       const unsigned d = tmem_base + (unsigned)(set * p.set_cols);
-      mbar_wait_spin(ACC_EMPTY(set), ((n / p.nset) & 1) ^ 1);
+      mbar_wait_spin(ACC_EMPTY(set), ((n >> 1) & 1) ^ 1);
       tc_fence_after();
       WN_TRACE(4 + r, n, 0);
+      long long w_full = 0;
       for (int j = 0; j < conv_stages; ++j) {
-        mbar_wait_spin(FULL(r * RS + s), ph);
+        const long long w0 = TRACE ? clock64() : 0;
+        mbar_wait_spin(FULL(s), ph);
+        if (TRACE) w_full += clock64() - w0;
         tc_fence_after();
-        const unsigned a16 = smem_u32(rbase + (size_t)s * p.slot_bytes) >> 4;
-        const unsigned b16 = a16 + ((unsigned)p.a_bytes >> 4);
+        const unsigned s16 = smem_u32(ring + (size_t)s * p.slot_bytes) >> 4;
+        const unsigned a16 = s16 + (unsigned)r * ((unsigned)p.a_bytes >> 4);
+        const unsigned b16 = s16 + (2u * (unsigned)p.a_bytes >> 4);
         const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + a16);
         const unsigned long long b_hi = hi_const | (unsigned long long)(b1_lo + b16);
         const bool half = j >= p.nxc * p.K && (j - p.nxc * p.K) == p.ncc - 1 && cgl <= 2;  // one K-step only
@@ -239,58 +282,76 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
           tc_mma_x3_single(d, a_hi, b_hi, a_sub, b1_sub, p.idesc1, j != 0 ? 1u : 0u);
         else
           tc_mma_tap6(d, a_hi, b_hi, a_sub, b1_sub, a_step, b1_step, p.idesc1, j != 0 ? 1u : 0u);
-        tc_commit(EMPTY(r * RS + s));
-        if (++s == RS) { s = 0; ph ^= 1; }
+        tc_commit(EMPTY(s));
+        if (++s == p.nslot) { s = 0; ph ^= 1; }
       }
       tc_commit(G_FULL(set));
       WN_TRACE(4 + r, n, 1);
-      // skip / out contraction of the same tile, once the gate has written z (its tiles of this parity arrive in order)
-      mbar_wait_spin(Z_FULL(r), m & 1);
+      if (TRACE && blockIdx.x == 0 && lane == 0 && n < WN_TRACE_TILES) g_wn_trace[4 + r][n][2] = w_full;
+    }
+  } else if (warp == WN_W_SO) {
+    // ===================== skip / out issuer: SO(i) = z(i) x resident weights into the (dead) columns of G(i) =====================
+    const unsigned long long hi_const = ((unsigned long long)((128u >> 4) | (1u << 14))) << 32;
+    const unsigned a_lo = ((unsigned)(WN_BLK >> 4)) << 16;
+    const unsigned z_sub = (unsigned)(p.H / 8 * WN_BLK) >> 4;
+    const unsigned a_step = (unsigned)(2 * WN_BLK) >> 4;
+    const unsigned b2_lo = (((unsigned)p.N2) & 0x3FFFu) << 16;
+    const unsigned b2_sub = 4u * p.N2, b2_step = 2u * p.N2;
+    const unsigned z16 = smem_u32(z_buf) >> 4, w16 = smem_u32(wso_buf) >> 4;
+    mbar_wait_spin(WSO_FULL, 0);
+    for (int i = 0; i < 2 * npairs; ++i) {
+      const int n = i >> 1, set = 2 * (n & 1) + (i & 1);
+      const unsigned d = tmem_base + (unsigned)(set * p.set_cols);
+      WN_TRACE(3, i, 0);
+      mbar_wait_spin(Z_FULL, i & 1);
       tc_fence_after();
-      WN_TRACE(4 + r, n, 2);
+      WN_TRACE(3, i, 1);
       for (int sc = 0; sc < p.nsc; ++sc) {
-        mbar_wait_spin(FULL(r * RS + s), ph);
-        tc_fence_after();
-        const unsigned b16 = smem_u32(rbase + (size_t)s * p.slot_bytes + p.a_bytes) >> 4;
         const unsigned long long a_hi = hi_const | (unsigned long long)(a_lo + z16 + (unsigned)(sc * 4 * WN_BLK >> 4));
-        const unsigned long long b_hi = hi_const | (unsigned long long)(b2_lo + b16);
+        const unsigned long long b_hi = hi_const | (unsigned long long)(b2_lo + w16 + (unsigned)(sc * p.b_bytes >> 4));
         if (!(p.variant & 16)) tc_mma_tap6(d, a_hi, b_hi, z_sub, b2_sub, a_step, b2_step, p.idesc2, sc != 0 ? 1u : 0u);
-        tc_commit(EMPTY(r * RS + s));
-        if (++s == RS) { s = 0; ph ^= 1; }
       }
       tc_commit(Z_EMPTY);
       tc_commit(SO_FULL(set));
-      WN_TRACE(4 + r, n, 3);
+      WN_TRACE(3, i, 2);
     }
   } else if (warp >= WN_W_GATE0 && warp < WN_W_GATE0 + WN_NGATE / 32) {
     // ===================== gate: G (TMEM) -> z operand image (smem) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");  // (96 - 80) x 256 + (96 - 64) x 128 >= (128 - 96) x 256: the CTA's pool balances
     const int gw = warp - WN_W_GATE0;
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;         // row of the tile
     // the 8 warps split the H gate channels into two halves (by 16-channel groups)
-    const int ngrp = p.H / 16;
+    const int ngrp = H / 16;
     const int g_begin = (gw >> 2) ? ngrp / 2 : 0, g_end = (gw >> 2) ? ngrp : ngrp / 2;
-    for (int n = 0; n < ntl; ++n) {
-      const int set = n % p.nset;
-      if (gw == 0) WN_TRACE(2, n, 0);
-      mbar_wait_spin(G_FULL(set), (n / p.nset) & 1);
+    const float4* b1v = reinterpret_cast<const float4*>(bias1);
+    uint4* zq = reinterpret_cast<uint4*>(z_buf) + m;
+    for (int i = 0; i < 2 * npairs; ++i) {
+      const int n = i >> 1, set = 2 * (n & 1) + (i & 1);
+      if (gw == 0) WN_TRACE(2, i, 0);
+      mbar_wait_hint(G_FULL(set), (n >> 1) & 1);
       tc_fence_after();
-      if (gw == 0) WN_TRACE(2, n, 1);
+      if (gw == 0) WN_TRACE(2, i, 1);
       const unsigned tacc = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(set * p.set_cols);
       bool z_free = false;
       for (int g16 = g_begin; g16 < ((p.variant & 4) ? g_begin : g_end); ++g16) {
         unsigned ra[16], rb[16];
         tc_ld16(tacc + (unsigned)(g16 * 16), ra);
-        tc_ld16(tacc + (unsigned)(p.H + g16 * 16), rb);
+        tc_ld16(tacc + (unsigned)(H + g16 * 16), rb);
         tc_wait_ld();
         float zv[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          zv[j] = gate_fast(__uint_as_float(ra[j]) + bias1[g16 * 16 + j], __uint_as_float(rb[j]) + bias1[p.H + g16 * 16 + j]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 ba = b1v[g16 * 4 + j4], bb = b1v[(H + g16 * 16) / 4 + j4];
+          zv[j4 * 4 + 0] = gate_fast(__uint_as_float(ra[j4 * 4 + 0]), __uint_as_float(rb[j4 * 4 + 0]), ba.x, bb.x);
+          zv[j4 * 4 + 1] = gate_fast(__uint_as_float(ra[j4 * 4 + 1]), __uint_as_float(rb[j4 * 4 + 1]), ba.y, bb.y);
+          zv[j4 * 4 + 2] = gate_fast(__uint_as_float(ra[j4 * 4 + 2]), __uint_as_float(rb[j4 * 4 + 2]), ba.z, bb.z);
+          zv[j4 * 4 + 3] = gate_fast(__uint_as_float(ra[j4 * 4 + 3]), __uint_as_float(rb[j4 * 4 + 3]), ba.w, bb.w);
+        }
         if (!z_free) {  // the previous tile's skip/out MMAs must have retired before z is overwritten
-          mbar_wait_spin(Z_EMPTY, (n & 1) ^ 1);
+          mbar_wait_hint(Z_EMPTY, (i & 1) ^ 1);
           z_free = true;
-          if (gw == 0) WN_TRACE(2, n, 2);
+          if (gw == 0) WN_TRACE(2, i, 2);
         }
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
@@ -300,127 +361,221 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
           uint4 hi, lo;
           split8(u, hi, lo);
           const int grp = g16 * 2 + h8;
-          *reinterpret_cast<uint4*>(z_buf + ((size_t)grp * WN_TT + m) * 16) = hi;
-          *reinterpret_cast<uint4*>(z_buf + ((size_t)(p.H / 8 + grp) * WN_TT + m) * 16) = lo;
+          zq[grp * WN_TT] = hi;
+          zq[(H / 8 + grp) * WN_TT] = lo;
         }
       }
-      if (!z_free) mbar_wait_spin(Z_EMPTY, (n & 1) ^ 1);
+      if (!z_free) mbar_wait_hint(Z_EMPTY, (i & 1) ^ 1);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();  // one arrival per warp: every lane's z stores and TMEM loads are ordered before it
-      if (lane == 0) mbar_arrive(Z_FULL(n & 1));
-      if (gw == 0) WN_TRACE(2, n, 3);
+      if (lane == 0) mbar_arrive(Z_FULL);
+      if (gw == 0) WN_TRACE(2, i, 3);
     }
-  } else if (warp < WN_W_EPI0 + WN_NEPI / 32) {
-    // ===================== epilogue: SO (TMEM) -> skips (fp32 RMW), x' (packed hi/lo) =====================
+  } else if (warp >= WN_W_EPI0 && warp < WN_W_EPI0 + WN_NEPI / 32) {
+    // ===================== epilogue: SO (TMEM) -> skips (fp32 accumulate), x' (packed hi/lo) =====================
+    // Global WRITES leave through an 8 KB staging buffer per half and ONE bulk tensor store per 16 columns (skips: an fp32
+    // add performed by the L2, so the skip tensor is never read by the SM).  The accumulator columns go to registers
+    // first and the TMEM set is handed back BEFORE the stores: the memory latency stays out of the TMEM recycling loop.
+    // The gate and the epilogue are instruction-issue bound (ncu: ~4700 useful warp instructions per tile and scheduler
+    // against a 6400-cycle HBM budget in the first version), so the channel counts are compile-time constants, biases
+    // come as float4, waits are hardware-suspended and the tile coordinates are tracked incrementally.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     const int ew = warp - WN_W_EPI0;
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const bool out_half = (ew >> 2) != 0;  // warps 0-3: skip columns [0, S); warps 4-7: residual columns [S, S + R)
     const float rs = 0.70710678118654752440f;
-    for (int n = 0; n < ntl; ++n) {
-      const int set = n % p.nset;
-      const int tile = blockIdx.x + n * gridDim.x;
-      const int b = tile / p.tiles_per_seq;
-      const int t0 = (tile - b * p.tiles_per_seq) * WN_TT;
+    const float4* b2v = reinterpret_cast<const float4*>(bias2);
+    int pair = blockIdx.x;
+    int b = pair / p.pairs_per_seq;
+    int pin = pair - b * p.pairs_per_seq;  // pair within its sequence
+    uint4 xr[2][4];                        // residual rows of the current / next 16-channel round: [hi g0, hi g1, lo g0, lo g1]
+    const long long tp_el = p.Tp, lo_off = (long long)p.ngx * p.Tp;  // plane pitches in 16-byte elements
+    for (int i = 0; i < 2 * npairs; ++i) {
+      const int n = i >> 1, set = 2 * (n & 1) + (i & 1);
+      const int t0 = pin * (2 * WN_TT) + (i & 1) * WN_TT;
       const int t = t0 + m;
-      const bool tv = t < p.T && !(p.variant & 8);
-      if ((ew & 3) == 0) WN_TRACE(ew >> 2, n, 0);
-      if (!out_half && !p.skip_init && !(p.variant & 8)) {
-        // L2 prefetch of the skip lines two tiles ahead (one 128-byte line per column and warp)
-        const int tl = tile + 2 * (int)gridDim.x;
-        if (tl < p.total_tiles) {
-          const int bb = tl / p.tiles_per_seq;
-          const int tt = (tl - bb * p.tiles_per_seq) * WN_TT + q * 32;
-          if (tt < p.T)
-            for (int col = lane; col < p.S; col += 32) prefetch_l2(skips + ((long long)bb * p.S + col) * p.T + tt);
-        }
+      const bool tv = t < p.T;
+      // The two warp groups swap halves every tile (a residual tile costs ~1.6x a skip tile): group g takes the skip
+      // columns [0, S) of the tiles with (i & 1) == g and the residual columns [S, S + R) of the others.
+      const bool out_half = (((ew >> 2) ^ i) & 1) != 0;
+      // coordinates of the next pair of this CTA (the same warp's next residual tile is tile i + 2: same half of it)
+      int nb = b, npin = pin + (int)gridDim.x;
+      while (npin >= p.pairs_per_seq) {
+        npin -= p.pairs_per_seq;
+        ++nb;
       }
-      // The operands that come from HBM / L2 (skip values, residual x) of column group g + 1 are requested while
-      // group g is being processed, and group 0 before the accumulator is even waited for: the epilogue never
-      // sits on a full memory round trip per group.
+      const int nt0 = npin * (2 * WN_TT) + (i & 1) * WN_TT;
+      if ((ew & 3) == 0) WN_TRACE(out_half ? 1 : 0, i, 0);
       const unsigned tacc = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(set * p.set_cols);
-      if (!out_half) {
-        float* sq = skips + (long long)b * p.S * p.T + t;
-        const bool ld = tv && !p.skip_init;
-        float sv[16], sn[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sv[j] = ld ? sq[(long long)j * p.T] : 0.f;
-        mbar_wait_spin(SO_FULL(set), (n / p.nset) & 1);
+      bool waited = false, released = false;
+      long long t_wait = 0;
+      if (!out_half && p.skip_tma) {
+        mbar_wait_hint(SO_FULL(set), (n >> 1) & 1);
         tc_fence_after();
-        if (ew == 0) WN_TRACE(0, n, 1);
-        for (int col = 0; col < p.S; col += 16) {
-          unsigned r[16];
-          tc_ld16(tacc + (unsigned)col, r);
-          const bool more = ld && col + 16 < p.S;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sn[j] = more ? sq[(long long)(col + 16 + j) * p.T] : 0.f;
+        waited = true;
+        if ((ew & 3) == 0) WN_TRACE(0, i, 1);
+        float* st = reinterpret_cast<float*>(stage_s) + ew * (16 * 32) + lane;  // this warp's 2 KB slice: [16 ch][32 samples]
+        for (int c0 = 0; c0 < S; c0 += 64) {
+          unsigned r0[32], r1[32];
+          tc_ld32(tacc + (unsigned)c0, r0);
+          tc_ld32(tacc + (unsigned)min(c0 + 32, p.set_cols - 32), r1);  // unconditional (columns past S are ignored below)
           tc_wait_ld();
-          if (tv) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sq[(long long)(col + j) * p.T] = __uint_as_float(r[j]) + bias2[col + j] + sv[j];
+          if (c0 + 64 >= S) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACC_EMPTY(set));
+            released = true;
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sv[j] = sn[j];
-        }
-      } else if (p.write_x) {
-        const long long row = (long long)p.halo + t;
-        const uint4* xh_base = xin + ((long long)(b * 2 + 0) * p.ngx) * p.Tp + row;
-        const uint4* xl_base = xin + ((long long)(b * 2 + 1) * p.ngx) * p.Tp + row;
-        uint4 xh[2], xl[2], nh[2], nl[2];
+          for (int h = 0; h < 4; ++h) {
+            if (c0 + h * 16 < S) {
+              if (lane == 0) {
+                const long long w0 = TRACE ? clock64() : 0;
+                tma_store_wait_read<0>();  // this warp's previous bulk store has read its staging slice
+                if (TRACE) t_wait += clock64() - w0;
+              }
+              __syncwarp();
+              // rows past the end of the sequence lie outside the tensor map: the bulk store clips them
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          xh[h8] = tv ? ldg16(xh_base + (long long)h8 * p.Tp) : make_uint4(0, 0, 0, 0);
-          xl[h8] = tv ? ldg16(xl_base + (long long)h8 * p.Tp) : make_uint4(0, 0, 0, 0);
-        }
-        mbar_wait_spin(SO_FULL(set), (n / p.nset) & 1);
-        tc_fence_after();
-        if (ew == 4) WN_TRACE(1, n, 1);
-        for (int col = 0; col < p.R; col += 16) {
-          unsigned r[16];
-          tc_ld16(tacc + (unsigned)(p.S + col), r);
-          const bool more = tv && col + 16 < p.R;
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            const long long gi = col / 8 + 2 + h8;
-            nh[h8] = more ? ldg16(xh_base + gi * p.Tp) : make_uint4(0, 0, 0, 0);
-            nl[h8] = more ? ldg16(xl_base + gi * p.Tp) : make_uint4(0, 0, 0, 0);
-          }
-          tc_wait_ld();
-          if (tv) {
-#pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              float fh[8], fl[8], u[8];
-              bf16x8_to_float(xh[h8], fh);
-              bf16x8_to_float(xl[h8], fl);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                u[j] = (__uint_as_float(r[h8 * 8 + j]) + bias2[p.S + col + h8 * 8 + j] + (fh[j] + fl[j])) * rs;
-              uint4 hi, lo;
-              split8(u, hi, lo);
-              const long long gi = col / 8 + h8;
-              xout[((long long)(b * 2 + 0) * p.ngx + gi) * p.Tp + row] = hi;
-              xout[((long long)(b * 2 + 1) * p.ngx + gi) * p.Tp + row] = lo;
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 bv = b2v[(c0 + h * 16) / 4 + j4];
+                const unsigned* rr = h < 2 ? r0 : r1;
+                st[(j4 * 4 + 0) * 32] = __uint_as_float(rr[(h & 1) * 16 + j4 * 4 + 0]) + bv.x;
+                st[(j4 * 4 + 1) * 32] = __uint_as_float(rr[(h & 1) * 16 + j4 * 4 + 1]) + bv.y;
+                st[(j4 * 4 + 2) * 32] = __uint_as_float(rr[(h & 1) * 16 + j4 * 4 + 2]) + bv.z;
+                st[(j4 * 4 + 3) * 32] = __uint_as_float(rr[(h & 1) * 16 + j4 * 4 + 3]) + bv.w;
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && !(p.variant & (8 | 128))) {
+                if (p.skip_init || (p.variant & 256))
+                  tma_store_2d(&tm_s, smem_u32(st - lane), t0 + q * 32, b * S + c0 + h * 16);
+                else
+                  tma_reduce_add_2d(&tm_s, smem_u32(st - lane), t0 + q * 32, b * S + c0 + h * 16);
+                tma_store_commit();
+              }
             }
           }
+        }
+      } else if (!out_half) {
+        // row pitch not a multiple of 16 bytes: per-thread read-modify-write
+        float* sq = skips + (long long)b * S * p.T + t;
+        const bool ld = tv && !p.skip_init;
+        for (int c0 = 0; c0 < S; c0 += 32) {
+          float sv[32];
 #pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            xh[h8] = nh[h8];
-            xl[h8] = nl[h8];
+          for (int j = 0; j < 32; ++j) sv[j] = (ld && c0 + j < S) ? sq[(long long)(c0 + j) * p.T] : 0.f;
+          if (!waited) {
+            mbar_wait_hint(SO_FULL(set), (n >> 1) & 1);
+            tc_fence_after();
+            waited = true;
+            if ((ew & 3) == 0) WN_TRACE(0, i, 1);
+          }
+          unsigned r[32];
+          tc_ld32(tacc + (unsigned)c0, r);
+          tc_wait_ld();
+          if (tv && !(p.variant & 8)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < S) sq[(long long)(c0 + j) * p.T] = __uint_as_float(r[j]) + bias2[c0 + j] + sv[j];
           }
         }
-      } else {
-        mbar_wait_spin(SO_FULL(set), (n / p.nset) & 1);
+      } else if (p.write_x) {
+        // The residual rows (L2 hits: the conv's centre-tap windows) are requested one 16-channel round AHEAD of their
+        // use -- across tile boundaries too -- so their latency hides under the previous round's arithmetic.
+        // running pointer (hi plane, first group of the round to request next); lo plane = + lo_off, next group = + Tp
+        auto x_round_load = [&](const uint4* src, bool ok, uint4 (&dst)[4]) {
+          dst[0] = ok ? ldg16(src) : make_uint4(0, 0, 0, 0);
+          dst[1] = ok ? ldg16(src + tp_el) : make_uint4(0, 0, 0, 0);
+          dst[2] = ok ? ldg16(src + lo_off) : make_uint4(0, 0, 0, 0);
+          dst[3] = ok ? ldg16(src + lo_off + tp_el) : make_uint4(0, 0, 0, 0);
+        };
+        const uint4* tile_base = xin + ((long long)(b * 2) * p.ngx) * p.Tp + p.halo + t;
+        const uint4* next_base = xin + ((long long)(nb * 2) * p.ngx) * p.Tp + p.halo + nt0 + m;
+        const bool ntv = nt0 + m < p.T;
+        if (i < 2) x_round_load(tile_base, tv, xr[0]);  // this warp's first residual tile
+        uint4* sx = reinterpret_cast<uint4*>(stage_s) + ew * (4 * 32) + lane;  // this warp's 2 KB slice: [hi | lo][2 groups][32 rows]
+        for (int c0 = 0; c0 < R; c0 += 64) {
+          if (!waited) {
+            mbar_wait_hint(SO_FULL(set), (n >> 1) & 1);
+            tc_fence_after();
+            waited = true;
+            if ((ew & 3) == 0) WN_TRACE(1, i, 1);
+          }
+          unsigned r0[32], r1[32];
+          tc_ld32(tacc + (unsigned)(S + c0), r0);
+          tc_ld32(tacc + (unsigned)min(S + c0 + 32, p.set_cols - 32), r1);  // unconditional (columns past R are ignored below)
+          tc_wait_ld();
+          if (c0 + 64 >= R) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACC_EMPTY(set));
+            released = true;
+          }
+#pragma unroll
+          for (int rd = 0; rd < 4; ++rd) {  // 16 channels = 2 groups per staging round
+            if (c0 + rd * 16 < R) {
+              // request the next round's rows: this tile's next 16 channels, or the first 16 of the next tile
+              {
+                const bool last = c0 + rd * 16 + 16 >= R;
+                if (!last)
+                  x_round_load(tile_base + (long long)((c0 + rd * 16 + 16) / 8) * tp_el, tv, xr[(rd + 1) & 1]);
+                else if (i + 2 < 2 * npairs)
+                  x_round_load(next_base, ntv, xr[(rd + 1) & 1]);
+              }
+              if (lane == 0) {
+                const long long w0 = TRACE ? clock64() : 0;
+                tma_store_wait_read<0>();  // this warp's previous bulk store has read its staging slice
+                if (TRACE) t_wait += clock64() - w0;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int g2 = 0; g2 < 2; ++g2) {
+                float fh[8], fl[8], u[8];
+                bf16x8_to_float(xr[rd & 1][g2], fh);
+                bf16x8_to_float(xr[rd & 1][2 + g2], fl);
+                const float4 bA = b2v[(S + c0 + rd * 16 + g2 * 8) / 4], bB = b2v[(S + c0 + rd * 16 + g2 * 8) / 4 + 1];
+                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+                const unsigned* rr = rd < 2 ? r0 : r1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = fmaf((__uint_as_float(rr[(rd & 1) * 16 + g2 * 8 + j]) + fh[j]) + fl[j], rs, bb[j]);
+                uint4 hi, lo;
+                split8(u, hi, lo);
+                if (!tv) hi = lo = make_uint4(0, 0, 0, 0);  // rows past the end of the sequence stay zero (the next layer's padding)
+                sx[(0 * 2 + g2) * 32] = hi;
+                sx[(1 * 2 + g2) * 32] = lo;
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && !(p.variant & (8 | 32))) {
+                tma_store_3d(&tm_xo, smem_u32(sx - lane), 2 * (p.halo + t0 + q * 32), (c0 + rd * 16) / 8, 2 * b);
+                tma_store_commit();
+              }
+            }
+          }
+        }
+      }
+      if (!waited) {
+        mbar_wait_hint(SO_FULL(set), (n >> 1) & 1);
         tc_fence_after();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ACC_EMPTY(set));
-      if ((ew & 3) == 0) WN_TRACE(ew >> 2, n, 2);
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ACC_EMPTY(set));
+      }
+      if ((ew & 3) == 0) WN_TRACE(out_half ? 1 : 0, i, 2);
+      if (TRACE && (ew & 3) == 0 && lane == 0 && blockIdx.x == 0 && i < WN_TRACE_TILES) g_wn_trace[out_half ? 1 : 0][i][3] = t_wait;
+      if (i & 1) {
+        b = nb;
+        pin = npin;
+      }
     }
+    if (lane == 0) tma_store_wait<0>();  // bulk stores of this thread's group complete before the CTA exits
   }
   __syncthreads();
-  if (warp == WN_W_MMA) {
+  if (warp == WN_W_SO) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols)
                  : "memory");
@@ -493,7 +648,7 @@ static int wn_plan(const pwgb_wnstack_desc* d, WnK& p, size_t& smem_bytes) {
   if (R <= 0 || R % KC || G <= 0 || G % 2 || (G / 2) % KC || G % 16 || S <= 0 || S % 16 || A <= 0 || A % 16) return 0;
   const int N2 = S + R;
   const int width = G > N2 ? G : N2;
-  if (width > 256 || N2 % 16 || R % 16) return 0;
+  if (width > 128 || N2 % 16 || R % 16) return 0;  // 4 accumulator sets of <= 128 TMEM columns
   p.B = d->batch;
   p.T = d->t;
   p.R = R;
@@ -504,7 +659,7 @@ static int wn_plan(const pwgb_wnstack_desc* d, WnK& p, size_t& smem_bytes) {
   p.halo = d->halo;
   p.H = G / 2;
   p.D = 1;
-  const int tr = ceil_div(d->t, WN_TT) * WN_TT;
+  const int tr = ceil_div(d->t, 2 * WN_TT) * (2 * WN_TT);  // whole tile pairs
   p.Tp = 2 * d->halo + tr;
   p.Tc = tr;
   p.ngx = R / 8;
@@ -513,29 +668,29 @@ static int wn_plan(const pwgb_wnstack_desc* d, WnK& p, size_t& smem_bytes) {
   p.ncc = (A + KC - 1) / KC;
   p.nsc = p.H / KC;
   p.N2 = N2;
-  p.tiles_per_seq = tr / WN_TT;
-  if ((long long)p.tiles_per_seq * d->batch > 0x7fffffffLL) return 0;
-  p.total_tiles = p.tiles_per_seq * d->batch;
+  p.pairs_per_seq = tr / (2 * WN_TT);
+  if ((long long)p.pairs_per_seq * d->batch > 0x3fffffffLL) return 0;
+  p.total_pairs = p.pairs_per_seq * d->batch;
   p.a_bytes = 8 * WN_BLK;
   p.b_bytes = 2 * (KC / 8) * width * 16;
-  if (G != N2) return 0;  // one weight-stage size and one ring slot size (true for every reference config: S = R = G/2)
-  p.slot_bytes = p.a_bytes + p.b_bytes;
+  if (G != N2) return 0;  // one weight-stage size (true for every reference config: S = R = G/2)
+  p.slot_bytes = 2 * p.a_bytes + p.b_bytes;  // two activation windows (the tiles of a pair) share one weight stage
   p.z_bytes = 2 * (p.H / 8) * WN_BLK;
+  p.wso_bytes = p.nsc * p.b_bytes;  // skip / out weights stay resident in shared memory
   p.set_cols = width;
-  p.nset = 512 / width > 4 ? 4 : 512 / width;
-  int alloc = 32;
-  while (alloc < p.nset * width) alloc <<= 1;
-  p.tmem_cols = alloc;
-  const size_t fixed = (size_t)p.z_bytes + 8 * (2 * WN_MAX_SLOTS + 15) + 16 + 4 * (size_t)(G + N2) + 128;
+  p.nset = 4;  // two tile pairs in flight
+  p.tmem_cols = 512;
+  const size_t fixed = (size_t)p.z_bytes + (size_t)p.wso_bytes + 2 * WN_STAGE_BYTES + 8 * (2 * WN_MAX_SLOTS + 16) + 16 + 4 * (size_t)(G + N2) + 128;
   const size_t budget = 227 * 1024;
-  if (fixed + 3 * (size_t)p.slot_bytes > budget) return 0;
-  int ns = (int)((budget - fixed) / p.slot_bytes);
-  p.nslot = (ns > WN_MAX_SLOTS ? WN_MAX_SLOTS : ns) & ~1;  // two rings (one per MMA issuer) of nslot / 2 slots
+  if (fixed + 2 * (size_t)p.slot_bytes > budget) return 0;
+  const int ns = (int)((budget - fixed) / p.slot_bytes);
+  p.nslot = ns > 4 ? 4 : ns;
   smem_bytes = (size_t)p.nslot * p.slot_bytes + fixed;
   p.idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(G >> 3) << 17) | ((128u >> 4) << 24);
   p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N2 >> 3) << 17) | ((128u >> 4) << 24);
   p.write_x = 1;
   p.skip_init = 0;
+  p.skip_tma = d->t % 4 == 0;
   p.variant = g_wn_variant;
   return 1;
 }
@@ -628,7 +783,9 @@ extern "C" int pwgb_wnstack_layer_forward(const pwgb_wnstack_desc* d, int dilati
   p.skip_init = skips_init != 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wavenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wavenet_fused_kernel<64, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wavenet_fused_kernel<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wavenet_fused_kernel<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("wnstack_layer: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PWGB_CUDA_ERROR;
@@ -642,11 +799,11 @@ extern "C" int pwgb_wnstack_layer_forward(const pwgb_wnstack_desc* d, int dilati
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  const int grid = p.total_pairs < num_sms ? p.total_pairs : num_sms;
   // tensor maps of the packed streams.  A plane ([rows][8 ch] bf16) is contiguous, so it is described as a vector of
   // 8-byte elements (2 per row): dims (2 * rows, 8-channel groups, batch x hi|lo), box (256, 4, 2) = one 16 KB operand
   // window with a 2 KB inner extent
-  CUtensorMap tm_x, tm_c;
+  CUtensorMap tm_x, tm_c, tm_xo, tm_s;
   {
     const unsigned long long dx[3] = {2ull * p.Tp, (unsigned long long)p.ngx, 2ull * p.B};
     const unsigned long long dc[3] = {2ull * p.Tc, (unsigned long long)p.ngc, 2ull * p.B};
@@ -655,8 +812,29 @@ extern "C" int pwgb_wnstack_layer_forward(const pwgb_wnstack_desc* d, int dilati
     if (rc) return rc;
     rc = tma_make(&tm_c, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, 3, cpk, dc, box);
     if (rc) return rc;
+    // stores, one box per epilogue warp (its 32 rows) and 16 channels: no cross-warp synchronisation in the epilogue
+    const unsigned box_o[3] = {64u, 2u, 2u};  // per warp: 32 rows x 16 channels x hi|lo = 2 KB
+    rc = tma_make(&tm_xo, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, 3, p.write_x ? xpk_out : xpk_in, dx, box_o);
+    if (rc) return rc;
+    if (p.skip_tma) {
+      PWGB_CHECK_ARG(!(reinterpret_cast<uintptr_t>(skips) & 15), "wnstack_layer: skips must be 16-byte aligned");
+      const unsigned long long ds[2] = {(unsigned long long)p.T, (unsigned long long)p.B * p.S};
+      const unsigned box_s[2] = {32u, 16u};  // per warp: 32 samples x 16 channels fp32 = 2 KB
+      rc = tma_make(&tm_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, skips, ds, box_s);
+      if (rc) return rc;
+    } else {
+      tm_s = tm_c;  // unused
+    }
   }
-  wavenet_fused_kernel<<<(unsigned)grid, WN_THREADS, bytes, (cudaStream_t)stream>>>(
-      p, tm_x, tm_c, (const uint4*)xpk_in, (const unsigned char*)packed_w, b_conv, b_skip_out, (uint4*)xpk_out, skips);
+#define PWGB_WN_LAUNCH(CR, CS, TR)                                                                         \
+  wavenet_fused_kernel<CR, CS, TR><<<(unsigned)grid, WN_THREADS, bytes, (cudaStream_t)stream>>>(            \
+      p, tm_x, tm_c, tm_xo, tm_s, (const uint4*)xpk_in, (const unsigned char*)packed_w, b_conv, b_skip_out, (uint4*)xpk_out, skips)
+  if (p.R == 64 && p.S == 64 && (p.variant & 64))
+    PWGB_WN_LAUNCH(64, 64, true);  // timeline build (pwgb_debug_set(2, 64))
+  else if (p.R == 64 && p.S == 64)
+    PWGB_WN_LAUNCH(64, 64, false);
+  else
+    PWGB_WN_LAUNCH(0, 0, false);
+#undef PWGB_WN_LAUNCH
   return check_launch("wavenet_fused_kernel");
 }

@@ -40,14 +40,15 @@ with torch.no_grad():
 buf = np.zeros((8, 32, 4), dtype=np.int64)
 n = capi.lib().pwgb_debug_get(2, C.c_void_p(buf.ctypes.data), buf.nbytes)
 assert n == buf.nbytes, n
-t0 = buf[buf > 0].min()
+t0 = buf[:, :, :3][buf[:, :, :3] > 0].min()
 rel = np.where(buf > 0, buf - t0, -1)
-names = ["epi-skip", "epi-x", "gate", "-", "mma0", "mma1", "ld0", "ld1"]
-stamps = {0: ["start", "so_full", "done"], 1: ["start", "so_full", "done"], 2: ["start", "g_full", "z_empty", "done"],
-          4: ["acc_empty", "conv_issued", "z_full", "so_issued"], 5: ["acc_empty", "conv_issued", "z_full", "so_issued"],
-          6: ["start", "conv_loaded", "so_loaded"], 7: ["start", "conv_loaded", "so_loaded"]}
+rel[0:2, :, 3] = buf[0:2, :, 3]  # accumulated clocks, not a stamp
+rel[4:7, :, 2] = buf[4:7, :, 2]
+names = ["epi-skip", "epi-x", "gate", "so-issuer", "conv0", "conv1", "loader", "epi-x-detail"]
+stamps = {0: ["start", "so_full", "done", "store_wait"], 1: ["start", "so_full", "done", "store_wait"], 2: ["start", "g_full", "z_empty", "done"],
+          3: ["start", "z_full", "issued"], 4: ["acc_empty", "conv_issued", "full_wait"], 5: ["acc_empty", "conv_issued", "full_wait"], 6: ["start", "conv_loaded", "empty_wait"], 7: ["ldtm_done", "round0_bar1", "round0_bar2", "round1_bar1"]}
 print(f"variant bits {64 | extra}; d{d} T{T} B{B}; clocks relative to the first stamp")
-for r in (6, 7, 4, 5, 2, 0, 1):
+for r in (6, 4, 5, 2, 3, 0, 1, 7):
     print(f"== {names[r]}: " + ", ".join(stamps[r]))
     for t in range(24):
         row = rel[r, t]
