@@ -65,7 +65,7 @@ struct WnK {
   int nset, set_cols, tmem_cols;
   int write_x, skip_init;
   int skip_tma;          // skips through the staging buffer + TMA reduce (needs T % 4 == 0: 16-byte row pitch)
-  int variant;  // timing experiments only (pwgb_debug_set(2, v)): 1 no activation TMA, 2 no weight copies, 4 no gate math, 8 no epilogue memory traffic, 16 no MMAs, 32 no x' stores, 64 timeline of CTA 0, 128 no skip stores, 256 skips stored instead of reduced
+  int variant;  // timing experiments only (pwgb_debug_set(2, v)): 1 no activation TMA, 2 no weight copies, 4 no gate math, 8 no epilogue memory traffic, 16 no MMAs, 32 no x' stores, 64 timeline of CTA 0, 128 no skip stores, 256 skips stored instead of reduced, 512 no proxy fence in the x' rounds, 1024 no residual loads
   unsigned idesc1, idesc2;
 };
 
@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
         // use -- across tile boundaries too -- so their latency hides under the previous round's arithmetic.
         // running pointer (hi plane, first group of the round to request next); lo plane = + lo_off, next group = + Tp
         auto x_round_load = [&](const uint4* src, bool ok, uint4 (&dst)[4]) {
+          ok = ok && !(p.variant & 1024);
           dst[0] = ok ? ldg16(src) : make_uint4(0, 0, 0, 0);
           dst[1] = ok ? ldg16(src + tp_el) : make_uint4(0, 0, 0, 0);
           dst[2] = ok ? ldg16(src + lo_off) : make_uint4(0, 0, 0, 0);
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
                 sx[(0 * 2 + g2) * 32] = hi;
                 sx[(1 * 2 + g2) * 32] = lo;
               }
-              fence_proxy_async();
+              if (!(p.variant & 512)) fence_proxy_async();
               __syncwarp();
               if (lane == 0 && !(p.variant & (8 | 32))) {
                 tma_store_3d(&tm_xo, smem_u32(sx - lane), 2 * (p.halo + t0 + q * 32), (c0 + rd * 16) / 8, 2 * b);

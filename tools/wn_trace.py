@@ -40,22 +40,21 @@ with torch.no_grad():
 buf = np.zeros((8, 32, 4), dtype=np.int64)
 n = capi.lib().pwgb_debug_get(2, C.c_void_p(buf.ctypes.data), buf.nbytes)
 assert n == buf.nbytes, n
-t0 = buf[:, :, :3][buf[:, :, :3] > 0].min()
-rel = np.where(buf > 0, buf - t0, -1)
-rel[0:2, :, 3] = buf[0:2, :, 3]  # accumulated clocks, not a stamp
-rel[4:7, :, 2] = buf[4:7, :, 2]
-names = ["epi-skip", "epi-x", "gate", "so-issuer", "conv0", "conv1", "loader", "epi-x-detail"]
+big = buf > (1 << 32)  # clock64 stamps; the small entries are accumulated wait cycles
+t0 = buf[big].min()
+rel = np.where(big, buf - t0, np.where(buf > 0, buf, -1))
+names = ["epi-skip", "epi-x", "gate", "so-issuer", "conv0", "conv1", "loader", "-"]
 stamps = {0: ["start", "so_full", "done", "store_wait"], 1: ["start", "so_full", "done", "store_wait"], 2: ["start", "g_full", "z_empty", "done"],
-          3: ["start", "z_full", "issued"], 4: ["acc_empty", "conv_issued", "full_wait"], 5: ["acc_empty", "conv_issued", "full_wait"], 6: ["start", "conv_loaded", "empty_wait"], 7: ["ldtm_done", "round0_bar1", "round0_bar2", "round1_bar1"]}
+          3: ["start", "z_full", "issued"], 4: ["acc_empty", "conv_issued", "full_wait"], 5: ["acc_empty", "conv_issued", "full_wait"], 6: ["start", "conv_loaded", "empty_wait"]}
 print(f"variant bits {64 | extra}; d{d} T{T} B{B}; clocks relative to the first stamp")
-for r in (6, 4, 5, 2, 3, 0, 1, 7):
+for r in (6, 4, 5, 2, 3, 0, 1):
     print(f"== {names[r]}: " + ", ".join(stamps[r]))
     for t in range(24):
         row = rel[r, t]
-        if (row >= 0).any():
+        if (row[:2] >= 0).any():
             print(f"  tile {t:2d}: " + "  ".join(f"{int(v):8d}" for v in row[: len(stamps[r])]))
 # per-tile period (steady state) from the epilogue done stamps
-done = rel[0, :, 2]
-done = done[done > 0]
+done = np.sort(np.concatenate([rel[0, :, 2], rel[1, :, 2]]))
+done = done[done > 0][::2]
 if len(done) > 6:
     print("steady-state period per tile (clocks):", float(np.diff(done[2:]).mean()))
