@@ -400,7 +400,10 @@ def test_pwg_train_step_gradients(dev):
     # tolerance per (loss term, tensor): 1e-3 unless the oracle itself moves more under fp32-rounding-sized
     # perturbations of the weights (weight_g gradients of the 1-channel upsampling convs are <dL/dc, c>/g:
     # one cancelling sum shared by all four layers; the STFT loss goes through sign(log ratio) and 1/x)
-    ref_all, tol, obs = conditioning_tolerances(oracle, sd)
+    # the probe perturbation is the forward accuracy of the tensor-core path (2e-5, TC_TOL): the last layers are
+    # ReLU -> 1x1 conv -> ReLU, and ONE element of the (B, 64, T) skip sum whose sign differs between two correct fp32
+    # evaluations changes every upstream gradient by ~1 / sqrt(B * 64 * T) = 1.6e-3 in relative L2
+    ref_all, tol, obs = conditioning_tolerances(oracle, sd, rel_eps=2e-5)
     y_ref, sc, mag, adv = keep["v"]
     ref_terms = {t: {k: ref_all[t + "/" + k] for k in names} for t in ("stft", "adv", "out")}
 
