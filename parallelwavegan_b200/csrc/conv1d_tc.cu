@@ -1191,41 +1191,108 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
 
   if (warp < 4) {
     unsigned n = 0;
+    // 16-byte loads need 16-byte aligned rows: row pitch and window offset multiples of 4 samples
+    const bool vec_a = p.T_out % 4 == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
+    const bool vec_b = p.T_in % 4 == 0 && p.RX % 4 == 0 && ((long long)k0 * p.D - p.padL) % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     for (int item = split; item < total_items; item += p.nsplit, ++n) {
       const int b = item / p.chunks_per_seq;
       const int t0 = (item - b * p.chunks_per_seq) * WT_TK;
       mbar_wait(EMPTY, (n & 1) ^ 1);
       // gradient tile: row = time, 8 output channels per 16 B
       const float* gb = gy + ((long long)b * p.Cout + co0) * p.T_out;
-      for (int r = tid; r < WT_TK; r += 128) {
-        const int t = t0 + r;
-        const bool ok = t < p.T_out;
-#pragma unroll 4
-        for (int g = 0; g < 16; ++g) {
-          float u[8];
-          const bool cok = ok && (co0 + g * 8 < co_end);  // Cout_g % 8 == 0: whole 8-channel groups are in or out
+      if (vec_a) {
+        // 16-byte loads along time: a task = (8-channel group, 4 consecutive rows); a warp's lanes take consecutive row
+        // quads of one group (512 contiguous bytes per channel).  Two tasks (16 LDG.128) are in flight per thread: the
+        // scalar version kept 16 KB per CTA in flight and paid four DRAM round trips per item.
 #pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = cok ? lrelu(__ldg(gb + (long long)(g * 8 + j) * p.T_out + t), p.g_slope) : 0.f;
-          uint4 hi, lo;
-          split8(u, hi, lo);
-          *reinterpret_cast<uint4*>(a_buf + ((size_t)g * WT_TK + r) * 16) = hi;
-          *reinterpret_cast<uint4*>(a_buf + a_img + ((size_t)g * WT_TK + r) * 16) = lo;
+        for (int it = 0; it < 4; it += 2) {
+          float4 v[2][8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int g = (it + h) * 4 + warp;
+            const int t = t0 + 4 * lane;
+            const bool cok = t < p.T_out && (co0 + g * 8 < co_end);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              v[h][j] = cok ? __ldg(reinterpret_cast<const float4*>(gb + (long long)(g * 8 + j) * p.T_out + t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int g = (it + h) * 4 + warp;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              float u[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float e = rr == 0 ? v[h][j].x : (rr == 1 ? v[h][j].y : (rr == 2 ? v[h][j].z : v[h][j].w));
+                u[j] = lrelu(e, p.g_slope);
+              }
+              uint4 hi, lo;
+              split8(u, hi, lo);
+              const int r = 4 * lane + rr;
+              *reinterpret_cast<uint4*>(a_buf + ((size_t)g * WT_TK + r) * 16) = hi;
+              *reinterpret_cast<uint4*>(a_buf + a_img + ((size_t)g * WT_TK + r) * 16) = lo;
+            }
+          }
+        }
+      } else {
+        for (int r = tid; r < WT_TK; r += 128) {
+          const int t = t0 + r;
+          const bool ok = t < p.T_out;
+#pragma unroll 4
+          for (int g = 0; g < 16; ++g) {
+            float u[8];
+            const bool cok = ok && (co0 + g * 8 < co_end);  // Cout_g % 8 == 0: whole 8-channel groups are in or out
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = cok ? lrelu(__ldg(gb + (long long)(g * 8 + j) * p.T_out + t), p.g_slope) : 0.f;
+            uint4 hi, lo;
+            split8(u, hi, lo);
+            *reinterpret_cast<uint4*>(a_buf + ((size_t)g * WT_TK + r) * 16) = hi;
+            *reinterpret_cast<uint4*>(a_buf + a_img + ((size_t)g * WT_TK + r) * 16) = lo;
+          }
         }
       }
       // activation tile: rows t0 + k0*D - pad ... (+ RX)
       const float* xb = x + ((long long)b * p.Cin + grp * p.Cin_g + ci0) * p.T_in;
-      for (int r = tid; r < p.RX; r += 128) {
-        const long long ts = (long long)t0 + (long long)k0 * p.D - p.padL + r;
-        const bool ok = ts >= 0 && ts < p.T_in;
+      const long long ts0 = (long long)t0 + (long long)k0 * p.D - p.padL;
+      if (vec_b) {
+        for (int task = tid; task < (WT_NC / 8) * (p.RX / 4); task += 128) {
+          const int g = task / (p.RX / 4), rq = task - g * (p.RX / 4);
+          const long long ts = ts0 + 4 * rq;
+          const bool ok = ts >= 0 && ts + 3 < p.T_in;  // T_in % 4 == 0 and ts % 4 == 0: a quad is entirely in or out
+          float4 v[8];
 #pragma unroll
-        for (int g = 0; g < WT_NC / 8; ++g) {
-          float u[8];
+          for (int j = 0; j < 8; ++j)
+            v[j] = ok ? __ldg(reinterpret_cast<const float4*>(xb + (long long)(g * 8 + j) * p.T_in + ts)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) u[j] = ok ? lrelu(__ldg(xb + (long long)(g * 8 + j) * p.T_in + ts), p.x_slope) : 0.f;
-          uint4 hi, lo;
-          split8(u, hi, lo);
-          *reinterpret_cast<uint4*>(b_buf + ((size_t)g * p.RX + r) * 16) = hi;
-          *reinterpret_cast<uint4*>(b_buf + b_img + ((size_t)g * p.RX + r) * 16) = lo;
+          for (int rr = 0; rr < 4; ++rr) {
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float e = rr == 0 ? v[j].x : (rr == 1 ? v[j].y : (rr == 2 ? v[j].z : v[j].w));
+              u[j] = lrelu(e, p.x_slope);
+            }
+            uint4 hi, lo;
+            split8(u, hi, lo);
+            const int r = 4 * rq + rr;
+            *reinterpret_cast<uint4*>(b_buf + ((size_t)g * p.RX + r) * 16) = hi;
+            *reinterpret_cast<uint4*>(b_buf + b_img + ((size_t)g * p.RX + r) * 16) = lo;
+          }
+        }
+      } else {
+        for (int r = tid; r < p.RX; r += 128) {
+          const long long ts = ts0 + r;
+          const bool ok = ts >= 0 && ts < p.T_in;
+#pragma unroll
+          for (int g = 0; g < WT_NC / 8; ++g) {
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = ok ? lrelu(__ldg(xb + (long long)(g * 8 + j) * p.T_in + ts), p.x_slope) : 0.f;
+            uint4 hi, lo;
+            split8(u, hi, lo);
+            *reinterpret_cast<uint4*>(b_buf + ((size_t)g * p.RX + r) * 16) = hi;
+            *reinterpret_cast<uint4*>(b_buf + b_img + ((size_t)g * p.RX + r) * 16) = lo;
+          }
         }
       }
       fence_proxy_async();
@@ -1320,9 +1387,10 @@ static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
   p.ntg = ceil_div(d->kernel, tg);
   const long long items = (long long)p.B * p.chunks_per_seq;
   const long long gxy = (long long)d->groups * ceil_div(cout_g, 128) * (cin_g / WT_NC) * p.ntg;
+  // enough (tile, split) CTAs for two per SM on 148 SMs; a split keeps at least 8 items (1024 time steps) of work
   long long ns = (2 * 296 + gxy - 1) / gxy;
-  if (ns > items) ns = items;
-  if (ns > 64) ns = 64;
+  if (ns > items / 8) ns = items / 8;
+  if (ns > 512) ns = 512;
   if (ns < 1) ns = 1;
   p.nsplit = (int)ns;
   // D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 @ 17, M >> 4 @ 24
