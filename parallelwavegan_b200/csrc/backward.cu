@@ -231,6 +231,20 @@ __global__ void __cluster_dims__(BG_CLUSTER, 1, 1) __launch_bounds__(256)
   cl.sync();  // the partials stay alive until rank 0 has read them
 }
 
+// short rows: one CTA per channel, fixed order
+__global__ void __launch_bounds__(256) bias_grad_small_kernel(const float* __restrict__ g, float* __restrict__ db, int B, int C,
+                                                               long long L, int accumulate) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  double a = 0;
+  for (int b = 0; b < B; ++b) {
+    const float* q = g + ((long long)b * C + c) * L;
+    for (long long i = threadIdx.x; i < L; i += 256) a += q[i];
+  }
+  const double t = block_sum_256(a, red);
+  if (threadIdx.x == 0) db[c] = (accumulate ? db[c] : 0.f) + (float)t;
+}
+
 // gradient of pwgb_reduce_mean_forward: gx = gout[0] * weight / n * f'(x [, y])  (+ optional gy = -gx for L1)
 __global__ void reduce_mean_backward_kernel(int mode, const float* __restrict__ x, const float* __restrict__ y, long long n,
                                             float c, float s, float weight, const float* __restrict__ gout,
@@ -573,6 +587,10 @@ extern "C" int pwgb_act_backward(int mode, const float* g, const float* ref, flo
 extern "C" int pwgb_bias_grad(const float* g, float* db, int batch, int channels, long long len, int accumulate,
                               void* stream) {
   PWGB_CHECK_ARG(g && db && batch >= 0 && channels > 0 && len >= 0, "bias_grad: bad arguments");
+  if ((long long)batch * len < 65536 || channels >= 592) {  // short rows / many channels: one CTA per channel fills the machine
+    bias_grad_small_kernel<<<channels, 256, 0, (cudaStream_t)stream>>>(g, db, batch, channels, len, accumulate);
+    return check_launch("bias_grad_small_kernel");
+  }
   bias_grad_kernel<<<channels * BG_CLUSTER, 256, 0, (cudaStream_t)stream>>>(g, db, batch, channels, len, accumulate);
   return check_launch("bias_grad_kernel");
 }

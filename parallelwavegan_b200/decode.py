@@ -20,12 +20,12 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import capi, sharding
+from . import capi, ops, sharding
 from .capi import PAD_REPLICATE, PAD_ZERO, PwgbError
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ops._stream()
 
 
 class GraphedGenerator:

@@ -16,7 +16,7 @@ import math
 
 import torch
 
-from . import capi
+from . import capi, ops
 from .capi import PwgbError
 
 CHUNK = 8192  # elements per CTA of the multi-tensor kernels
@@ -92,7 +92,7 @@ class _FusedBase(torch.optim.Optimizer):
             if len(self.state[p]) == 0:
                 self._init_state(p)
         L = capi.lib()
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = ops._stream()
         coef = None
         if max_grad_norm is not None and max_grad_norm > 0:
             table, chunks, nch, partial, out2 = self._table(allp)

@@ -39,6 +39,14 @@ def run():
     for _ in range(2):
         step(c, y)
     torch.cuda.synchronize()
+    if len(sys.argv) > 1 and sys.argv[1] == "torchprof":
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_:
+            step(c, y)
+            torch.cuda.synchronize()
+        print(prof_.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+        return
     ops.PROFILE = []
     step(c, y)
     torch.cuda.synchronize()
