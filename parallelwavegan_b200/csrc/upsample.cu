@@ -4,22 +4,50 @@
 
 namespace pwgb {
 
+// Output o = j*s + ph only touches the input frames j-1, j, j+1: y[o] = A[ph] x[j-1] + B[ph] x[j] + C[ph] x[j+1] with the
+// taps pre-summed per phase (A: taps that land in frame j-1, ...).  One thread per input frame writes its s outputs
+// (one 16-byte store per 4): 3 FMAs per output instead of 2s+1 taps with an integer division each (the tap loop ran
+// at 1/12 of the HBM rate: 13 % of the Parallel WaveGAN forward).
 __global__ void upsample_fir_kernel(int rows, int rows_per_batch, int t_in, int s, const float* __restrict__ x,
                                     const float* __restrict__ fir, float* __restrict__ y, long long ybs) {
-  extern __shared__ float f[];
-  for (int i = threadIdx.x; i < 2 * s + 1; i += blockDim.x) f[i] = fir[i];
+  extern __shared__ float coef[];  // [3][s]
+  for (int ph = threadIdx.x; ph < s; ph += blockDim.x) {
+    float a = 0.f, bsum = 0.f, c = 0.f;
+    for (int k = 0; k <= 2 * s; ++k) {
+      const int d = ph + k - s;
+      const float f = fir[k];
+      if (d < 0)
+        a += f;
+      else if (d < s)
+        bsum += f;
+      else
+        c += f;
+    }
+    coef[ph] = a;
+    coef[s + ph] = bsum;
+    coef[2 * s + ph] = c;
+  }
   __syncthreads();
   const int r = blockIdx.y;
   const int t_out = t_in * s;
   const float* xr = x + (long long)r * t_in;
   float* yr = y + (long long)(r / rows_per_batch) * ybs + (long long)(r % rows_per_batch) * t_out;
-  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < t_out; o += gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    for (int k = 0; k <= 2 * s; ++k) {
-      const int i = o + k - s;
-      if (i >= 0 && i < t_out) acc = fmaf(f[k], __ldg(xr + i / s), acc);
+  const bool vec = (s % 4 == 0) && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < t_in; j += gridDim.x * blockDim.x) {
+    const float xm = j > 0 ? __ldg(xr + j - 1) : 0.f, x0 = __ldg(xr + j), xp = j + 1 < t_in ? __ldg(xr + j + 1) : 0.f;
+    float* dst = yr + (long long)j * s;
+    if (vec) {
+      for (int ph = 0; ph < s; ph += 4) {
+        float4 v;
+        v.x = fmaf(coef[2 * s + ph], xp, fmaf(coef[s + ph], x0, coef[ph] * xm));
+        v.y = fmaf(coef[2 * s + ph + 1], xp, fmaf(coef[s + ph + 1], x0, coef[ph + 1] * xm));
+        v.z = fmaf(coef[2 * s + ph + 2], xp, fmaf(coef[s + ph + 2], x0, coef[ph + 2] * xm));
+        v.w = fmaf(coef[2 * s + ph + 3], xp, fmaf(coef[s + ph + 3], x0, coef[ph + 3] * xm));
+        *reinterpret_cast<float4*>(dst + ph) = v;
+      }
+    } else {
+      for (int ph = 0; ph < s; ++ph) dst[ph] = fmaf(coef[2 * s + ph], xp, fmaf(coef[s + ph], x0, coef[ph] * xm));
     }
-    yr[o] = acc;
   }
 }
 
@@ -35,8 +63,8 @@ extern "C" int pwgb_upsample_fir_forward(int rows, int rows_per_batch, int t_in,
   PWGB_UNSUPPORTED_IF(rows > 65535, "upsample_fir: too many rows");
   if (rows == 0) return PWGB_OK;
   const int t_out = t_in * scale;
-  dim3 grid(ceil_div(t_out, 256) < 64 ? ceil_div(t_out, 256) : 64, rows);
-  upsample_fir_kernel<<<grid, 256, (2 * scale + 1) * sizeof(float), (cudaStream_t)stream>>>(
+  dim3 grid(ceil_div(t_in, 256) < 64 ? ceil_div(t_in, 256) : 64, rows);
+  upsample_fir_kernel<<<grid, 256, 3 * scale * sizeof(float), (cudaStream_t)stream>>>(
       rows, rows_per_batch, t_in, scale, x, fir, y, y_batch_stride ? y_batch_stride : (long long)rows_per_batch * t_out);
   return check_launch("upsample_fir_kernel");
 }
