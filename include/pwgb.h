@@ -376,6 +376,16 @@ PWGB_API int pwgb_tade_combine_forward(const float* cg, const float* xn, float* 
                               int scale, void* stream);
 PWGB_API int pwgb_tade_gate_forward(const float* x, const float* residual, float* y, int batch, int channels, long long t,
                            int scale, int softmax, void* stream);
+/* adjoints of the four entry points above (StyleMelGAN generator training, layers/tade_res_block.py:52-160 under autograd):
+ * instance_norm_backward recomputes the row statistics from x; the residual branch of tade_gate is the adjoint of
+ * upsample_nearest (pwgb_upsample_nearest_backward on gy). */
+PWGB_API int pwgb_instance_norm_backward(const float* x, const float* gy, float* gx, long long rows, long long t, float eps,
+                                float pre_slope, void* stream);
+PWGB_API int pwgb_upsample_nearest_backward(const float* gy, float* gx, long long rows, long long t_in, int scale, void* stream);
+PWGB_API int pwgb_tade_combine_backward(const float* cg, const float* xn, const float* gy, float* gcg, float* gxn, int batch,
+                               int channels, long long t_out, int scale, void* stream);
+PWGB_API int pwgb_tade_gate_backward(const float* x, const float* gy, float* gx, int batch, int channels, long long t, int softmax,
+                            void* stream);
 
 #ifdef __cplusplus
 }

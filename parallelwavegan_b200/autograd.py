@@ -366,3 +366,124 @@ class MrStftLossFn(torch.autograd.Function):
             rc = L.pwgb_stft_amplitude_backward(C.byref(d), ops._p(x), ops._p(windows[i]), ops._p(ax), ops._p(dax), ops._p(dx), ops._stream())
             capi.check(rc, "pwgb_stft_amplitude_backward")
         return (dx, None, None, None, None) + (None,) * n_res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# StyleMelGAN generator glue (layers/tade_res_block.py:52-160 under autograd)
+# ---------------------------------------------------------------------------------------------------------------
+class InstanceNormFn(torch.autograd.Function):
+    """InstanceNorm1d (no affine) of LeakyReLU_{pre_slope}(x); the backward recomputes the row statistics from x."""
+
+    @staticmethod
+    def forward(ctx, x, eps, pre_slope):
+        x = x.contiguous()
+        B, Cc, T = x.shape
+        y = torch.empty_like(x)
+        rc = capi.lib().pwgb_instance_norm_forward(ops._p(x), ops._p(y), B * Cc, T, float(eps), float(pre_slope), ops._stream())
+        capi.check(rc, "pwgb_instance_norm_forward")
+        ctx.save_for_backward(x)
+        ctx.eps, ctx.pre_slope = float(eps), float(pre_slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        B, Cc, T = x.shape
+        gx = torch.empty_like(x)
+        rc = capi.lib().pwgb_instance_norm_backward(ops._p(x), ops._p(gy.contiguous()), ops._p(gx), B * Cc, T, ctx.eps, ctx.pre_slope,
+                                                    ops._stream())
+        capi.check(rc, "pwgb_instance_norm_backward")
+        return gx, None, None
+
+
+def _nearest_backward(gy, scale):
+    B, Cc, To = gy.shape
+    gx = torch.empty((B, Cc, To // scale), device=gy.device, dtype=torch.float32)
+    rc = capi.lib().pwgb_upsample_nearest_backward(ops._p(gy.contiguous()), ops._p(gx), B * Cc, To // scale, int(scale), ops._stream())
+    capi.check(rc, "pwgb_upsample_nearest_backward")
+    return gx
+
+
+class UpsampleNearestFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = x.contiguous()
+        B, Cc, T = x.shape
+        y = torch.empty((B, Cc, T * scale), device=x.device, dtype=torch.float32)
+        rc = capi.lib().pwgb_upsample_nearest_forward(ops._p(x), ops._p(y), B * Cc, T, int(scale), ops._stream())
+        capi.check(rc, "pwgb_upsample_nearest_forward")
+        ctx.scale = int(scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _nearest_backward(gy, ctx.scale), None
+
+
+class LeakyReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        rc = capi.lib().pwgb_leaky_relu_forward(ops._p(x), ops._p(y), x.numel(), float(slope), ops._stream())
+        capi.check(rc, "pwgb_leaky_relu_forward")
+        ctx.save_for_backward(y)  # the mask can be read from the output (slope > 0 keeps the sign)
+        ctx.slope = float(slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return ops.act_backward("lrelu", gy.contiguous(), y, slope=ctx.slope), None
+
+
+class TadeCombineFn(torch.autograd.Function):
+    """y = cg[:, :C] * nearest(xn, scale) + cg[:, C:]  (tade_res_block.py:72-74)."""
+
+    @staticmethod
+    def forward(ctx, cg, xn, scale):
+        cg, xn = cg.contiguous(), xn.contiguous()
+        B, C2, T = cg.shape
+        y = torch.empty((B, C2 // 2, T), device=cg.device, dtype=torch.float32)
+        rc = capi.lib().pwgb_tade_combine_forward(ops._p(cg), ops._p(xn), ops._p(y), B, C2 // 2, T, int(scale), ops._stream())
+        capi.check(rc, "pwgb_tade_combine_forward")
+        ctx.save_for_backward(cg, xn)
+        ctx.scale = int(scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        cg, xn = ctx.saved_tensors
+        B, C2, T = cg.shape
+        gcg, gxn = torch.empty_like(cg), torch.empty_like(xn)
+        rc = capi.lib().pwgb_tade_combine_backward(ops._p(cg), ops._p(xn), ops._p(gy.contiguous()), ops._p(gcg), ops._p(gxn), B, C2 // 2, T,
+                                                   ctx.scale, ops._stream())
+        capi.check(rc, "pwgb_tade_combine_backward")
+        return gcg, gxn, None
+
+
+class TadeGateFn(torch.autograd.Function):
+    """y = gate(x[:, :C]) * tanh(x[:, C:]) [+ nearest(residual, scale)]  (tade_res_block.py:150-159)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, scale, softmax):
+        x = x.contiguous()
+        residual = residual.contiguous() if residual is not None else None
+        B, C2, T = x.shape
+        y = torch.empty((B, C2 // 2, T), device=x.device, dtype=torch.float32)
+        rc = capi.lib().pwgb_tade_gate_forward(ops._p(x), ops._p(residual), ops._p(y), B, C2 // 2, T, int(scale), int(softmax), ops._stream())
+        capi.check(rc, "pwgb_tade_gate_forward")
+        ctx.save_for_backward(x)
+        ctx.scale, ctx.softmax, ctx.has_res = int(scale), int(softmax), residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        B, C2, T = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        rc = capi.lib().pwgb_tade_gate_backward(ops._p(x), ops._p(gy), ops._p(gx), B, C2 // 2, T, ctx.softmax, ops._stream())
+        capi.check(rc, "pwgb_tade_gate_backward")
+        gres = _nearest_backward(gy, ctx.scale) if ctx.has_res and ctx.needs_input_grad[1] else None
+        return gx, gres, None, None

@@ -183,6 +183,14 @@ def lib():
     L.pwgb_gate_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
     L.pwgb_gate_backward.restype = C.c_int
     L.pwgb_gate_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_longlong, vp]
+    L.pwgb_instance_norm_backward.restype = C.c_int
+    L.pwgb_instance_norm_backward.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, C.c_float, C.c_float, vp]
+    L.pwgb_upsample_nearest_backward.restype = C.c_int
+    L.pwgb_upsample_nearest_backward.argtypes = [vp, vp, C.c_longlong, C.c_longlong, C.c_int, vp]
+    L.pwgb_tade_combine_backward.restype = C.c_int
+    L.pwgb_tade_combine_backward.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_longlong, C.c_int, vp]
+    L.pwgb_tade_gate_backward.restype = C.c_int
+    L.pwgb_tade_gate_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_longlong, C.c_int, vp]
     L.pwgb_upsample_fir_backward.restype = C.c_int
     L.pwgb_upsample_fir_backward.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_longlong, vp, vp, vp]
     L.pwgb_stft_loss_terms.restype = C.c_int
@@ -223,7 +231,8 @@ EXPORTED_SYMBOLS = [
     "pwgb_conv1d_wgrad_tc_workspace", "pwgb_conv1d_wgrad_tc", "pwgb_act_backward", "pwgb_bias_grad",
     "pwgb_reduce_mean_backward", "pwgb_avg_pool1d_backward", "pwgb_axpby", "pwgb_pad1d_forward", "pwgb_pad1d_backward",
     "pwgb_instance_norm_forward", "pwgb_upsample_nearest_forward", "pwgb_leaky_relu_forward", "pwgb_tade_combine_forward",
-    "pwgb_tade_gate_forward",
+    "pwgb_tade_gate_forward", "pwgb_instance_norm_backward", "pwgb_upsample_nearest_backward", "pwgb_tade_combine_backward",
+    "pwgb_tade_gate_backward",
     "pwgb_stft_amplitude_backward", "pwgb_mel_project_backward", "pwgb_gate_forward", "pwgb_gate_backward",
     "pwgb_upsample_fir_backward", "pwgb_stft_loss_terms", "pwgb_stft_loss_dmag",
 ]

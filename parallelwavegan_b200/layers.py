@@ -439,7 +439,7 @@ class ConvInUpsampleNetwork(torch.nn.Module):
 
 
 # --------------------------------------------------------------------------
-# StyleMelGAN blocks (layers/tade_res_block.py) -- inference only
+# StyleMelGAN blocks (layers/tade_res_block.py)
 # --------------------------------------------------------------------------
 
 

@@ -302,7 +302,7 @@ class MelGANGenerator(_GeneratorBase):
 
 
 class StyleMelGANGenerator(_GeneratorBase):
-    """models/style_melgan.py:22-270 -- inference only (forward / inference under ``torch.no_grad()``)."""
+    """models/style_melgan.py:22-270 (forward / inference; trainable: the TADE glue has adjoint kernels)."""
 
     def __init__(
         self,
@@ -360,13 +360,8 @@ class StyleMelGANGenerator(_GeneratorBase):
                 pre = self.noise_slope
         return ops.leaky_relu(x, self.noise_slope, inplace=True)
 
-    def _check_inference_only(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise PwgbError("StyleMelGANGenerator is inference-only in this build (no backward kernels): use torch.no_grad()")
-
     def forward(self, c, z=None):
         """(B, aux_channels, T) [, (B, in_channels, T_z)] -> (B, out_channels, T * prod(upsample_scales))  (style_melgan.py:140-160)."""
-        self._check_inference_only()
         if z is None:
             z = torch.randn(c.size(0), self.in_channels, 1).to(device=c.device, dtype=c.dtype)
         x = self._noise_path(z)
@@ -392,7 +387,6 @@ class StyleMelGANGenerator(_GeneratorBase):
     def inference(self, c, normalize_before=False, noise=None):
         """(T, aux_channels) -> (T * prod(upsample_scales), out_channels)  (style_melgan.py:226-262); ``noise``
         (1, in_channels, ceil(T / noise_upsample_factor)) may be passed for reproducibility."""
-        self._check_inference_only()
         c = self._prep_inference_input(c, normalize_before)
         n_frames = (c.size(2) - 1) // self.noise_upsample_factor + 1
         if noise is None:

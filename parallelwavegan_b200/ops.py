@@ -594,16 +594,14 @@ def axpby(a, x, b, y):
     return y
 
 
-# ---- StyleMelGAN glue (inference only: these have no adjoint kernels yet) ----
-def _no_grad_only(name, *ts):
-    if _needs_grad(*ts):
-        raise PwgbError(f"{name}: no backward kernel (StyleMelGAN is inference-only in this build); run under torch.no_grad()")
-
-
+# ---- StyleMelGAN glue (forward: raw launches; with gradients: autograd.py Functions over the adjoint kernels) ----
 def instance_norm(x, eps=1e-5, pre_slope=1.0):
     """torch.nn.InstanceNorm1d(C) of (B, C, T), optionally on LeakyReLU(x)."""
     x = _dev(x, "x")
-    _no_grad_only("instance_norm", x)
+    if _needs_grad(x):
+        from . import autograd as ag
+
+        return ag.InstanceNormFn.apply(x, float(eps), float(pre_slope))
     B, Cc, T = x.shape
     y = torch.empty_like(x)
     rc = capi.lib().pwgb_instance_norm_forward(_p(x), _p(y), B * Cc, T, float(eps), float(pre_slope), _stream())
@@ -614,9 +612,12 @@ def instance_norm(x, eps=1e-5, pre_slope=1.0):
 def upsample_nearest(x, scale):
     """torch.nn.Upsample(scale_factor=scale, mode="nearest") of (B, C, T)."""
     x = _dev(x, "x")
-    _no_grad_only("upsample_nearest", x)
     if scale == 1:
         return x
+    if _needs_grad(x):
+        from . import autograd as ag
+
+        return ag.UpsampleNearestFn.apply(x, int(scale))
     B, Cc, T = x.shape
     y = torch.empty(B, Cc, T * scale, device=x.device, dtype=torch.float32)
     rc = capi.lib().pwgb_upsample_nearest_forward(_p(x), _p(y), B * Cc, T, int(scale), _stream())
@@ -626,7 +627,10 @@ def upsample_nearest(x, scale):
 
 def leaky_relu(x, slope, inplace=False):
     x = _dev(x, "x")
-    _no_grad_only("leaky_relu", x)
+    if _needs_grad(x):
+        from . import autograd as ag
+
+        return ag.LeakyReluFn.apply(x, float(slope))
     y = x if inplace else torch.empty_like(x)
     rc = capi.lib().pwgb_leaky_relu_forward(_p(x), _p(y), x.numel(), float(slope), _stream())
     capi.check(rc, "pwgb_leaky_relu_forward")
@@ -637,11 +641,14 @@ def tade_combine(cg, xn, scale):
     """cg (B, 2C, T), xn (B, C, T / scale) -> cg[:, :C] * nearest(xn, scale) + cg[:, C:]."""
     cg = _dev(cg, "cg")
     xn = _dev(xn, "xn")
-    _no_grad_only("tade_combine", cg, xn)
     B, C2, T = cg.shape
     Cc = C2 // 2
     if C2 != 2 * Cc or tuple(xn.shape) != (B, Cc, T // scale) or T % scale:
         raise PwgbError(f"tade_combine: shapes {tuple(cg.shape)} / {tuple(xn.shape)} do not match scale {scale}")
+    if _needs_grad(cg, xn):
+        from . import autograd as ag
+
+        return ag.TadeCombineFn.apply(cg, xn, int(scale))
     y = torch.empty(B, Cc, T, device=cg.device, dtype=torch.float32)
     rc = capi.lib().pwgb_tade_combine_forward(_p(cg), _p(xn), _p(y), B, Cc, T, int(scale), _stream())
     capi.check(rc, "pwgb_tade_combine_forward")
@@ -651,7 +658,6 @@ def tade_combine(cg, xn, scale):
 def tade_gate(x, residual=None, scale=1, gated_function="softmax"):
     """x (B, 2C, T) -> gate(x[:, :C]) * tanh(x[:, C:]) [+ nearest(residual (B, C, T / scale), scale)]."""
     x = _dev(x, "x")
-    _no_grad_only("tade_gate", x, residual)
     if gated_function not in ("softmax", "sigmoid"):
         raise PwgbError(f"tade_gate: gated_function={gated_function!r} is not supported")
     B, C2, T = x.shape
@@ -660,6 +666,10 @@ def tade_gate(x, residual=None, scale=1, gated_function="softmax"):
         residual = _dev(residual, "residual")
         if tuple(residual.shape) != (B, Cc, T // scale) or T % scale:
             raise PwgbError(f"tade_gate: residual shape {tuple(residual.shape)} does not match {(B, Cc, T // scale)}")
+    if _needs_grad(x, residual):
+        from . import autograd as ag
+
+        return ag.TadeGateFn.apply(x, residual, int(scale), int(gated_function == "softmax"))
     y = torch.empty(B, Cc, T, device=x.device, dtype=torch.float32)
     rc = capi.lib().pwgb_tade_gate_forward(_p(x), _p(residual), _p(y), B, Cc, T, int(scale), int(gated_function == "softmax"), _stream())
     capi.check(rc, "pwgb_tade_gate_forward")

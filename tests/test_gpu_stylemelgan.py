@@ -91,11 +91,9 @@ def test_style_melgan_generator_vs_reference(dev, name):
         assert rel_l2(m(c, z).cpu(), g["y"]) < REL_TOL
 
 
-def test_style_melgan_inference_and_grad_guard(dev):
+def test_style_melgan_inference(dev):
     """inference() (style_melgan.py:226-262): noise length ceil(T / 88), conditioning replicate-padded, output cropped."""
     from parallelwavegan_b200 import models
-    from parallelwavegan_b200.capi import PwgbError
-
     meta, _ = load_golden("style_melgan_v1")
     m = models.StyleMelGANGenerator(**json.loads(json.dumps(meta["kwargs"])))
     m.load_state_dict(golden_weights(meta), strict=True)
@@ -111,5 +109,85 @@ def test_style_melgan_inference_and_grad_guard(dev):
     cfg = dict(kw, noise_upsample_negative_slope=0.2)
     ref = ref_ops.style_melgan_generator(golden_effective_weights(meta), cp, noise, cfg)[..., : T * 256]
     assert rel_l2(y.cpu(), ref.squeeze(0).t()) < REL_TOL
-    with pytest.raises(PwgbError):
-        m(synth.randn((1, 80, 88), 7).to(dev))  # grad mode: no backward kernels -> loud failure
+
+
+@pytest.mark.parametrize("scale", [1, 2, 3])
+def test_tade_glue_gradients(dev, scale):
+    """Adjoint kernels of InstanceNorm1d (with / without the fused LeakyReLU), nearest upsampling, the TADE modulation and
+    the softmax / sigmoid gate with residual (layers/tade_res_block.py:52-160) vs torch autograd on the CPU."""
+    from parallelwavegan_b200 import ops
+
+    B, C, T = 2, 24, 50
+    up = lambda t: F.interpolate(t, scale_factor=scale, mode="nearest")
+    for slope in (1.0, 0.2):
+        x = synth.randn((B, C, T), 11) * 2.0 + 0.3
+        w = synth.randn((B, C, T), 12)
+        xr = x.clone().requires_grad_(True)
+        (F.instance_norm(F.leaky_relu(xr, slope) if slope != 1.0 else xr) * w).sum().backward()
+        xd = x.clone().to(dev).requires_grad_(True)
+        (ops.instance_norm(xd, pre_slope=slope) * w.to(dev)).sum().backward()
+        assert rel_l2(xd.grad.cpu(), xr.grad) < 1e-4, slope
+    xn, cg, res = synth.randn((B, C, T), 2), synth.randn((B, 2 * C, T * scale), 3), synth.randn((B, C, T), 4)
+    w = synth.randn((B, C, T * scale), 5)
+    xr, cr = xn.clone().requires_grad_(True), cg.clone().requires_grad_(True)
+    ((cr[:, :C] * up(xr) + cr[:, C:]) * w).sum().backward()
+    xd, cd = xn.clone().to(dev).requires_grad_(True), cg.clone().to(dev).requires_grad_(True)
+    (ops.tade_combine(cd, xd, scale) * w.to(dev)).sum().backward()
+    assert rel_l2(xd.grad.cpu(), xr.grad) < 1e-5 and rel_l2(cd.grad.cpu(), cr.grad) < 1e-5
+    if scale > 1:
+        xr = xn.clone().requires_grad_(True)
+        (up(xr) * w).sum().backward()
+        xd = xn.clone().to(dev).requires_grad_(True)
+        (ops.upsample_nearest(xd, scale) * w.to(dev)).sum().backward()
+        assert rel_l2(xd.grad.cpu(), xr.grad) < 1e-6
+    for fn, gate in (("softmax", lambda t: torch.softmax(t, dim=1)), ("sigmoid", torch.sigmoid)):
+        cr, rr = cg.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        ((gate(cr[:, :C]) * torch.tanh(cr[:, C:]) + up(rr)) * w).sum().backward()
+        cd, rd = cg.clone().to(dev).requires_grad_(True), res.clone().to(dev).requires_grad_(True)
+        (ops.tade_gate(cd, rd, scale, fn) * w.to(dev)).sum().backward()
+        assert rel_l2(cd.grad.cpu(), cr.grad) < 1e-4, fn
+        assert rel_l2(rd.grad.cpu(), rr.grad) < 1e-6, fn
+
+
+def test_style_melgan_generator_gradients(dev):
+    """StyleMelGAN generator training (row a11b): parameter and input gradients of the small golden model through the TADE
+    adjoints, the tcgen05 conv data / weight gradients and the transposed-conv noise path vs torch autograd through the
+    CPU oracle, with the conditioning-aware bound (instance norm + softmax gates amplify fp32 rounding, see the header)."""
+    from helpers import conditioning_tolerances
+    from parallelwavegan_b200 import models
+
+    meta, _ = load_golden("style_melgan_small")
+    kw = json.loads(json.dumps(meta["kwargs"]))
+    m = models.StyleMelGANGenerator(**kw)
+    sd = golden_weights(meta)
+    m.load_state_dict(sd, strict=True)
+    c = synth.randn(meta["c_shape"], meta["c_seed"])
+    z = synth.randn(meta["z_shape"], meta["z_seed"])
+    cfg = dict(kw, noise_upsample_negative_slope=kw["noise_upsample_activation_params"]["negative_slope"])
+    keep = {}
+
+    def oracle(leaves):
+        lf = {k: v.clone().requires_grad_(True) for k, v in leaves.items() if k != "__c"}
+        cr = leaves["__c"].clone().requires_grad_(True)
+        y = ref_ops.style_melgan_generator(ref_ops.fold_weight_norm(lf), cr, z, cfg)
+        keep.setdefault("y", y.detach())
+        keep.setdefault("t", synth.randn(tuple(y.shape), 77))
+        (y * keep["t"]).sum().backward()
+        out = {k: v.grad for k, v in lf.items()}
+        out["__c"] = cr.grad
+        return out
+
+    ref, tol, obs = conditioning_tolerances(oracle, dict(sd, __c=c), rel_eps=2e-5)
+    m = m.to(dev).train()
+    cd = c.to(dev).requires_grad_(True)
+    y = m(cd, z.to(dev))
+    assert rel_l2(y.detach().cpu(), keep["y"]) < REL_TOL
+    (y * keep["t"].to(dev)).sum().backward()
+    bad = []
+    for k, g in [("__c", cd.grad)] + [(k, p.grad) for k, p in m.named_parameters()]:
+        e = rel_l2(g.cpu(), ref[k])
+        if e >= tol[k]:
+            bad.append((k, round(e, 5), round(tol[k], 5), round(obs[k], 6)))
+    print("STYLE-GRAD loose bounds", [(k, round(t, 4)) for k, t in tol.items() if t > 1e-3][:6], "worst",
+          max(rel_l2(p.grad.cpu(), ref[k]) for k, p in m.named_parameters()))
+    assert not bad, bad[:10]
