@@ -339,32 +339,54 @@ __global__ void pad1d_backward_kernel(const float* __restrict__ gxp, float* __re
 }
 
 // WaveNet gate (layers/residual_block.py:128): z[b,h,t] = tanh(g[b,h,t]) * sigmoid(g[b,H+h,t])
+// (B, 2H, T) -> (B, H, T); grid.y = B * H rows, 16-byte accesses along T when the rows are 16-byte aligned
+__device__ __forceinline__ float gate_exact(float a, float s) { return tanhf(a) * sigmoidf_(s); }
 __global__ void gate_forward_kernel(const float* __restrict__ g, float* __restrict__ z, int B, int H, long long T) {
-  const long long n = (long long)B * H * T;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long t = i % T;
-    const long long bh = i / T;
-    const int h = (int)(bh % H);
-    const long long b = bh / H;
-    const float a = g[(b * 2 * H + h) * T + t];
-    const float s = g[(b * 2 * H + H + h) * T + t];
-    z[i] = tanhf(a) * sigmoidf_(s);
+  const long long row = blockIdx.y;
+  const long long b = row / H, h = row - b * H;
+  const float* ga = g + (b * 2 * H + h) * T;
+  const float* gs = ga + (long long)H * T;
+  float* zr = z + row * T;
+  if (T % 4 == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(z)) & 15) == 0) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < T / 4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ga) + i), s = __ldg(reinterpret_cast<const float4*>(gs) + i);
+      reinterpret_cast<float4*>(zr)[i] = make_float4(gate_exact(a.x, s.x), gate_exact(a.y, s.y), gate_exact(a.z, s.z), gate_exact(a.w, s.w));
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < T; i += (long long)gridDim.x * blockDim.x)
+      zr[i] = gate_exact(ga[i], gs[i]);
   }
+}
+__device__ __forceinline__ void gate_grad(float a, float s, float go, float& da, float& ds) {
+  const float ta = tanhf(a), sg = sigmoidf_(s);
+  da = go * sg * (1.f - ta * ta);
+  ds = go * ta * sg * (1.f - sg);
 }
 __global__ void gate_backward_kernel(const float* __restrict__ g, const float* __restrict__ gz, float* __restrict__ gg, int B,
                                      int H, long long T) {
-  const long long n = (long long)B * H * T;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long t = i % T;
-    const long long bh = i / T;
-    const int h = (int)(bh % H);
-    const long long b = bh / H;
-    const long long ia = (b * 2 * H + h) * T + t, is = (b * 2 * H + H + h) * T + t;
-    const float ta = tanhf(g[ia]);
-    const float sg = sigmoidf_(g[is]);
-    const float go = gz[i];
-    gg[ia] = go * sg * (1.f - ta * ta);
-    gg[is] = go * ta * sg * (1.f - sg);
+  const long long row = blockIdx.y;
+  const long long b = row / H, h = row - b * H;
+  const long long oa = (b * 2 * H + h) * T, os = oa + (long long)H * T;
+  const float* gr = gz + row * T;
+  if (T % 4 == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(gz) | reinterpret_cast<uintptr_t>(gg)) & 15) == 0) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < T / 4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(g + oa) + i), s = __ldg(reinterpret_cast<const float4*>(g + os) + i);
+      const float4 go = __ldg(reinterpret_cast<const float4*>(gr) + i);
+      float4 da, ds;
+      gate_grad(a.x, s.x, go.x, da.x, ds.x);
+      gate_grad(a.y, s.y, go.y, da.y, ds.y);
+      gate_grad(a.z, s.z, go.z, da.z, ds.z);
+      gate_grad(a.w, s.w, go.w, da.w, ds.w);
+      reinterpret_cast<float4*>(gg + oa)[i] = da;
+      reinterpret_cast<float4*>(gg + os)[i] = ds;
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < T; i += (long long)gridDim.x * blockDim.x) {
+      float da, ds;
+      gate_grad(g[oa + i], g[os + i], gr[i], da, ds);
+      gg[oa + i] = da;
+      gg[os + i] = ds;
+    }
   }
 }
 
@@ -393,19 +415,20 @@ __global__ void upsample_fir_backward_x_kernel(int t_in, int s, const float* __r
 // the rows; double accumulators per thread and tap, partials combined through distributed shared memory in rank
 // order (deterministic, no workspace).
 constexpr int UF_CLUSTER = 8, UF_MAXT = 17, UF_THREADS = 512;
+template <int MAXT>
 __global__ void __cluster_dims__(UF_CLUSTER, 1, 1) __launch_bounds__(UF_THREADS)
     upsample_fir_backward_f_kernel(int rows, int t_in, int s, const float* __restrict__ x, const float* __restrict__ gy,
                                    float* __restrict__ df, int rows_per_batch, long long gybs) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster();
-  __shared__ double red[UF_THREADS / 32][UF_MAXT];
-  __shared__ double part[UF_MAXT];
+  __shared__ double red[UF_THREADS / 32][MAXT];
+  __shared__ double part[MAXT];
   const int r = (int)cl.block_rank();
   const int t_out = t_in * s, ntap = 2 * s + 1;
   const int row_lo = (int)((long long)rows * r / UF_CLUSTER), row_hi = (int)((long long)rows * (r + 1) / UF_CLUSTER);
-  double acc[UF_MAXT];
+  double acc[MAXT];
 #pragma unroll
-  for (int k = 0; k < UF_MAXT; ++k) acc[k] = 0;
+  for (int k = 0; k < MAXT; ++k) acc[k] = 0;
   for (int row = row_lo; row < row_hi; ++row) {
     const float* gr = gy + (long long)(row / rows_per_batch) * gybs + (long long)(row % rows_per_batch) * t_out;
     const float* xr = x + (long long)row * t_in;
@@ -415,7 +438,7 @@ __global__ void __cluster_dims__(UF_CLUSTER, 1, 1) __launch_bounds__(UF_THREADS)
       const float xm = j > 0 ? xr[j - 1] : 0.f, x0 = xr[j], xp = j + 1 < t_in ? xr[j + 1] : 0.f;
       // tap k reads q = o + k - s = j*s + (ph + k - s); (ph + k - s) in [-s, 2s): index j-1, j or j+1 (out of range -> 0)
 #pragma unroll
-      for (int k = 0; k < UF_MAXT; ++k) {
+      for (int k = 0; k < MAXT; ++k) {
         if (k < ntap) {
           const int d = ph + k - s;
           const float xv = d < 0 ? xm : (d < s ? x0 : xp);
@@ -425,14 +448,14 @@ __global__ void __cluster_dims__(UF_CLUSTER, 1, 1) __launch_bounds__(UF_THREADS)
     }
   }
 #pragma unroll
-  for (int k = 0; k < UF_MAXT; ++k) {
+  for (int k = 0; k < MAXT; ++k) {
     double a = acc[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = a;
   }
   __syncthreads();
-  if (threadIdx.x < UF_MAXT) {
+  if (threadIdx.x < MAXT) {
     double t = 0;
     for (int w = 0; w < UF_THREADS / 32; ++w) t += red[w][threadIdx.x];
     part[threadIdx.x] = t;
@@ -646,7 +669,12 @@ extern "C" int pwgb_gate_forward(const float* g, float* z, int batch, int half_c
   PWGB_CHECK_ARG(g && z && batch >= 0 && half_channels > 0 && t >= 0, "gate_forward: bad arguments");
   const long long n = (long long)batch * half_channels * t;
   if (n == 0) return PWGB_OK;
-  gate_forward_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(g, z, batch, half_channels, t);
+  PWGB_UNSUPPORTED_IF((long long)batch * half_channels > 65535, "gate_forward: too many rows");
+  {
+    const long long per_row = (t + 1023) / 1024;
+    dim3 grid((unsigned)(per_row < 64 ? (per_row < 1 ? 1 : per_row) : 64), (unsigned)(batch * half_channels));
+    gate_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, z, batch, half_channels, t);
+  }
   return check_launch("gate_forward_kernel");
 }
 
@@ -655,7 +683,12 @@ extern "C" int pwgb_gate_backward(const float* g, const float* gz, float* gg, in
   PWGB_CHECK_ARG(g && gz && gg && batch >= 0 && half_channels > 0 && t >= 0, "gate_backward: bad arguments");
   const long long n = (long long)batch * half_channels * t;
   if (n == 0) return PWGB_OK;
-  gate_backward_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(g, gz, gg, batch, half_channels, t);
+  PWGB_UNSUPPORTED_IF((long long)batch * half_channels > 65535, "gate_backward: too many rows");
+  {
+    const long long per_row = (t + 1023) / 1024;
+    dim3 grid((unsigned)(per_row < 64 ? (per_row < 1 ? 1 : per_row) : 64), (unsigned)(batch * half_channels));
+    gate_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, gz, gg, batch, half_channels, t);
+  }
   return check_launch("gate_backward_kernel");
 }
 
@@ -675,7 +708,10 @@ extern "C" int pwgb_upsample_fir_backward(int rows, int rows_per_batch, int t_in
   }
   if (dfir) {
     if (2 * scale + 1 <= UF_MAXT) {
-      upsample_fir_backward_f_kernel<<<UF_CLUSTER, UF_THREADS, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
+      if (2 * scale + 1 <= 9)
+        upsample_fir_backward_f_kernel<9><<<UF_CLUSTER, UF_THREADS, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
+      else
+        upsample_fir_backward_f_kernel<UF_MAXT><<<UF_CLUSTER, UF_THREADS, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
       return check_launch("upsample_fir_backward_f_kernel");
     }
     upsample_fir_backward_f_tap_kernel<<<2 * scale + 1, 256, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
