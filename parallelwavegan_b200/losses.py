@@ -3,6 +3,9 @@
 Forward values are produced by fused sm_100a kernels (``libpwgb.so``): the STFT losses
 never materialise framed / complex / magnitude tensors, the GAN losses are deterministic
 two-stage reductions.  Every loss returns 0-dim CUDA tensors like the reference.
+Backward: the overlap-add of the STFT adjoint (``pwgb_stft_amplitude_backward``) scatters frames with fp32
+atomicAdd, so waveform gradients of the STFT / mel losses differ run to run in the last bits (like cuFFT-based
+torch.stft backward); everything else is fixed-order.
 """
 import numpy as np
 import torch
