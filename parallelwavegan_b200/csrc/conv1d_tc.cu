@@ -1138,7 +1138,7 @@ extern "C" int pwgb_wavenet_layer_forward(const pwgb_wavenet_desc* d, const floa
 // ======================================================================================
 namespace pwgb {
 
-constexpr int WT_NC = 32;    // input channels per CTA (MMA N)
+constexpr int WT_NC = 32;    // input channels per CTA (MMA N); 64 for <= 4 taps (TMEM: taps x NC <= 256 columns)
 constexpr int WT_TK = 128;   // time steps per item (8 MMA k-steps)
 constexpr int WT_TG = 8;     // taps per CTA
 constexpr int WT_THREADS = 160;
@@ -1148,9 +1148,12 @@ struct WtK {
   int G, Cin_g, Cout_g;  // groups: an M tile never straddles two groups (rows beyond the group's channels are zero)
   float x_slope, g_slope;
   int chunks_per_seq, nsplit, RX, ntg, tg;  // tg = taps per CTA (<= WT_TG), ntg = tap groups
+  int nc;                                   // input channels per CTA (32 or 64)
   unsigned idesc;
 };
 
+// NC = input channels per CTA (MMA N): 64 halves the number of CTAs that re-read and re-convert the gradient tile
+template <int NC>
 __global__ void __launch_bounds__(WT_THREADS, 2)
     wgrad_tc_kernel(const WtK p, const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ part) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1158,7 +1161,7 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
   unsigned char* a_buf = smem;
   const int a_img = 16 * WT_TK * 16;
   unsigned char* b_buf = smem + 2 * a_img;
-  const int b_img = (WT_NC / 8) * p.RX * 16;
+  const int b_img = (NC / 8) * p.RX * 16;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(b_buf + 2 * b_img);
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1166,7 +1169,7 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
   const int grp = blockIdx.x / tpg;
   const int co0 = grp * p.Cout_g + (blockIdx.x - grp * tpg) * 128;
   const int co_end = (grp + 1) * p.Cout_g;
-  const int ci0 = (blockIdx.y / p.ntg) * WT_NC;  // within the group
+  const int ci0 = (blockIdx.y / p.ntg) * NC;  // within the group
   const int k0 = (blockIdx.y % p.ntg) * p.tg;
   const int ntap = min(p.tg, p.K - k0);
   const int split = blockIdx.z;
@@ -1256,7 +1259,7 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
       const float* xb = x + ((long long)b * p.Cin + grp * p.Cin_g + ci0) * p.T_in;
       const long long ts0 = (long long)t0 + (long long)k0 * p.D - p.padL;
       if (vec_b) {
-        for (int task = tid; task < (WT_NC / 8) * (p.RX / 4); task += 128) {
+        for (int task = tid; task < (NC / 8) * (p.RX / 4); task += 128) {
           const int g = task / (p.RX / 4), rq = task - g * (p.RX / 4);
           const long long ts = ts0 + 4 * rq;
           const bool ok = ts >= 0 && ts + 3 < p.T_in;  // T_in % 4 == 0 and ts % 4 == 0: a quad is entirely in or out
@@ -1284,7 +1287,7 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
           const long long ts = ts0 + r;
           const bool ok = ts >= 0 && ts < p.T_in;
 #pragma unroll
-          for (int g = 0; g < WT_NC / 8; ++g) {
+          for (int g = 0; g < NC / 8; ++g) {
             float u[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) u[j] = ok ? lrelu(__ldg(xb + (long long)(g * 8 + j) * p.T_in + ts), p.x_slope) : 0.f;
@@ -1298,16 +1301,16 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
       fence_proxy_async();
       mbar_arrive(FULL);
     }
-    // ---- epilogue: lane = output channel, column = tap * WT_NC + ci
+    // ---- epilogue: lane = output channel, column = tap * NC + ci
     mbar_wait(ACC, 0);
     tc_fence_after();
     const int co = co0 + warp * 32 + lane;
     const bool co_ok = co < co_end;
     float* dst = part + (((long long)split * p.Cout + (co_ok ? co : 0)) * p.Cin_g + ci0) * p.K + k0;
     for (int tp = 0; tp < ntap; ++tp) {
-      for (int c16 = 0; c16 < WT_NC; c16 += 16) {
+      for (int c16 = 0; c16 < NC; c16 += 16) {
         unsigned r[16];
-        tc_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(tp * WT_NC + c16), r);
+        tc_ld16(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(tp * NC + c16), r);
         tc_wait_ld();
         if (co_ok) {
 #pragma unroll
@@ -1334,7 +1337,7 @@ __global__ void __launch_bounds__(WT_THREADS, 2)
         for (int tp = 0; tp < ntap; ++tp) {
           const unsigned long long bd = b_hi | (unsigned long long)(lbo + b16 + (unsigned)(tp * p.D + ks * 16));
           const unsigned acc = (n | (unsigned)ks) != 0 ? 1u : 0u;
-          tc_mma_x3_single(tmem_base + (unsigned)(tp * WT_NC), ad, bd, a_sub, b_sub, p.idesc, acc);
+          tc_mma_x3_single(tmem_base + (unsigned)(tp * NC), ad, bd, a_sub, b_sub, p.idesc, acc);
         }
       }
       tc_commit(EMPTY);
@@ -1376,17 +1379,20 @@ static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
   p.x_slope = d->pre_slope;
   p.g_slope = 1.f;
   p.chunks_per_seq = ceil_div(d->t_out, WT_TK);
+  // 64 input channels per CTA when the taps fit the accumulator (taps x 64 <= 256 TMEM columns): the (dominant)
+  // gradient tile is then read and converted once per 64 instead of once per 32 input channels
+  p.nc = (cin_g % 64 == 0 && d->kernel <= 4) ? 64 : WT_NC;
   // taps per CTA: as many as fit (the activation window grows with (taps - 1) * dilation)
   int tg = d->kernel < WT_TG ? d->kernel : WT_TG;
   for (;; tg = (tg + 1) / 2) {
     p.RX = WT_TK + (tg - 1) * d->dilation;
-    if ((size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (WT_NC / 8) * p.RX * 16 + 64 <= 110 * 1024) break;
+    if ((size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (p.nc / 8) * p.RX * 16 + 64 <= 110 * 1024) break;
     if (tg == 1) return 0;
   }
   p.tg = tg;
   p.ntg = ceil_div(d->kernel, tg);
   const long long items = (long long)p.B * p.chunks_per_seq;
-  const long long gxy = (long long)d->groups * ceil_div(cout_g, 128) * (cin_g / WT_NC) * p.ntg;
+  const long long gxy = (long long)d->groups * ceil_div(cout_g, 128) * (cin_g / p.nc) * p.ntg;
   // enough (tile, split) CTAs for two per SM on 148 SMs; a split keeps at least 8 items (1024 time steps) of work
   long long ns = (2 * 296 + gxy - 1) / gxy;
   if (ns > items / 8) ns = items / 8;
@@ -1394,7 +1400,7 @@ static int wt_plan(const pwgb_conv1d_desc* d, WtK& p) {
   if (ns < 1) ns = 1;
   p.nsplit = (int)ns;
   // D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 @ 17, M >> 4 @ 24
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(WT_NC >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(p.nc >> 3) << 17) | ((128u >> 4) << 24);
   return 1;
 }
 
@@ -1426,18 +1432,22 @@ extern "C" int pwgb_conv1d_wgrad_tc(const pwgb_conv1d_desc* d, const float* x, c
     cudaMemsetAsync(dw, 0, n * sizeof(float), st);
     return PWGB_OK;
   }
-  const size_t smem = (size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (WT_NC / 8) * p.RX * 16 + 64;
+  const size_t smem = (size_t)2 * 16 * WT_TK * 16 + (size_t)2 * (p.nc / 8) * p.RX * 16 + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) {
       set_error("conv1d_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PWGB_CUDA_ERROR;
     }
     attr_set = true;
   }
-  dim3 grid(p.G * ceil_div(p.Cout_g, 128), (p.Cin_g / WT_NC) * p.ntg, p.nsplit);
-  wgrad_tc_kernel<<<grid, WT_THREADS, smem, st>>>(p, x, gy, (float*)ws);
+  dim3 grid(p.G * ceil_div(p.Cout_g, 128), (p.Cin_g / p.nc) * p.ntg, p.nsplit);
+  if (p.nc == 64)
+    wgrad_tc_kernel<64><<<grid, WT_THREADS, smem, st>>>(p, x, gy, (float*)ws);
+  else
+    wgrad_tc_kernel<32><<<grid, WT_THREADS, smem, st>>>(p, x, gy, (float*)ws);
   int rc = check_launch("wgrad_tc_kernel");
   if (rc) return rc;
   int blocks = (int)((n + 255) / 256);
