@@ -377,6 +377,34 @@ def test_wavenet_fused_layer_packed(dev, dilation, T, B, skips_init, write_x):
     assert int(planes[:, :512].abs().sum()) == 0 and int(planes[:, 512 + T:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("R,G,S,A", [(32, 64, 32, 80), (96, 128, 32, 64), (32, 128, 96, 80)])
+def test_wavenet_fused_layer_packed_other_channel_counts(dev, R, G, S, A):
+    """The fused layer for channel counts other than the PWG v1 ones (run-time channel loops of the kernel:
+    residual / skip halves wider than one 64-column register block, a conditioning width that is a multiple of 32)."""
+    from parallelwavegan_b200 import layers, ops
+
+    B, T, dilation = 2, 900, 4
+    blk = layers.WaveNetResidualBlock(residual_channels=R, gate_channels=G, skip_channels=S, aux_channels=A, dilation=dilation)
+    sd = synth.synth_state_dict([(k, tuple(v.shape)) for k, v in blk.state_dict().items()], 90 + R, 1.0)
+    blk.load_state_dict(sd)
+    blk = blk.to(dev)
+    x, c, sk0 = synth.randn((B, R, T), 1), synth.randn((B, A, T), 2), synth.randn((B, S, T), 3)
+    xr, sr = ref_ops.wavenet_residual_block({f"b.{k}": v for k, v in sd.items()}, "b", x, c, dilation, 3)
+    assert ops.WnStack.supported(B, T, R, G, S, A, 3, 16)
+    st = ops.WnStack(B, T, R, G, S, A, 3, 16, dev)
+    st.pack_c(c.to(dev))
+    st.pack_x(x.to(dev))
+    skips = sk0.clone().to(dev)
+    with torch.no_grad():
+        packed, bso = ops.wavenet_packed_weights(layers.effective_weight(blk.conv), layers.effective_weight(blk.conv1x1_aux),
+                                                 layers.effective_weight(blk.conv1x1_skip), layers.effective_weight(blk.conv1x1_out),
+                                                 blk.conv1x1_skip.bias, blk.conv1x1_out.bias, A)
+        st.layer(packed, blk.conv.bias, bso, dilation, skips)
+        torch.cuda.synchronize()
+        xo = st.unpack_x().cpu()
+    assert rel_l2(xo, xr) < TC_TOL and rel_l2(skips.cpu(), sk0 + sr) < TC_TOL
+
+
 @pytest.mark.parametrize("update", ["inplace_op", "fused_optimizer", "load_state_dict"])
 def test_pwg_forward_sees_weight_updates(dev, update):
     """Packed operand images are cached per layer, keyed on the LEAF parameters (weight_g / weight_v / bias):
