@@ -236,7 +236,7 @@ def measure_train_step(dev, rank, local_rank, world, dist, steps=3, warmup=2):
             "losses": {k: float(v) for k, v in st.items()}}
 
 
-def measure_pwg_train_step(dev, rank, local_rank, world, dist, steps=2, warmup=1, batch=64):
+def measure_pwg_train_step(dev, rank, local_rank, world, dist, steps=3, warmup=2, batch=64):
     """BASELINE.json configs[2]: Parallel WaveGAN v1 G + D train step (30-layer residual stack,
     MultiResolutionSTFTLoss + adversarial loss, RAdam), per-GPU batch 64 x 25600 samples, DDP when world > 1."""
     from parallelwavegan_b200 import losses, models
