@@ -139,6 +139,23 @@ __global__ void __launch_bounds__(256) conv1d_wgrad_narrow_kernel(const WgK p, c
     base[j] = ok ? to * p.S - p.padL : -(1 << 30);
   }
   float* dst = part + ((long long)blockIdx.y * npairs + q) * p.K;
+  if (p.P == 1 && p.S == 1 && p.t_valid >= p.t_in) {
+    // plain stride-1 conv (the 1 -> C and C -> 1 layers of the generators / discriminators): row = o - pad + k * D,
+    // no period view, no reflect extension -- 32-bit index arithmetic only
+    for (int k = 0; k < p.K; ++k) {
+      float acc = 0.f;
+      const int r0 = o0 + lane - p.padL + k * p.D;
+#pragma unroll
+      for (int j = 0; j < WGN_CHUNK / 32; ++j) {
+        const int row = r0 + 32 * j;
+        if (row >= 0 && row < p.t_in) acc = fmaf(gv[j], lrelu(__ldg(xr + row), p.x_slope), acc);
+      }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+      if (lane == 0) dst[k] = acc;
+    }
+    return;
+  }
   for (int k = 0; k < p.K; ++k) {
     float acc = 0.f;
 #pragma unroll
