@@ -427,61 +427,80 @@ __global__ void upsample_fir_backward_x_kernel(int t_in, int s, const float* __r
     gx[(long long)r * t_in + i] = acc;
   }
 }
-// df[k] = sum_{r,o} gy[r,o] * x[r,(o+k-s)/s]: ONE pass over gy for all 2s+1 taps (the one-CTA-per-tap version read
-// gy 2s+1 times on 2s+1 SMs: 100 ms per call, 40 % of the Parallel WaveGAN training step).  A cluster of 8 CTAs splits
-// the rows; double accumulators per thread and tap, partials combined through distributed shared memory in rank
-// order (deterministic, no workspace).
-constexpr int UF_CLUSTER = 8, UF_MAXT = 17, UF_THREADS = 512;
-template <int MAXT>
+// df[k] = sum_{r,o} gy[r,o] * x[r,(o+k-s)/s]: ONE pass over gy for all 2s+1 taps (the one-CTA-per-tap version read gy
+// 2s+1 times on 2s+1 SMs: 100 ms per call, 40 % of the Parallel WaveGAN training step).  Output o = j*s + ph only meets
+// the input frames j-1, j, j+1, so the kernel accumulates the 3 s sums S[w][ph] = sum gy[j*s+ph] * x[j + w - 1] (three FMAs
+// per element, float within a row, double across rows) and folds them into the taps at the end:
+// df[k] = sum_ph S[w(ph, k)][ph], w = 0 / 1 / 2 for ph + k - s < 0 / < s / >= s.  A cluster of 8 CTAs splits the rows;
+// partials are combined through distributed shared memory in rank order (deterministic, no workspace).
+constexpr int UF_CLUSTER = 8, UF_MAXS = 8, UF_MAXT = 2 * UF_MAXS + 1, UF_THREADS = 512;
+template <int MAXS>
 __global__ void __cluster_dims__(UF_CLUSTER, 1, 1) __launch_bounds__(UF_THREADS)
     upsample_fir_backward_f_kernel(int rows, int t_in, int s, const float* __restrict__ x, const float* __restrict__ gy,
                                    float* __restrict__ df, int rows_per_batch, long long gybs) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster();
-  __shared__ double red[UF_THREADS / 32][MAXT];
-  __shared__ double part[MAXT];
+  __shared__ double red[UF_THREADS / 32][3 * MAXS];
+  __shared__ double part[3 * MAXS];
   const int r = (int)cl.block_rank();
-  const int t_out = t_in * s, ntap = 2 * s + 1;
+  const int t_out = t_in * s;
   const int row_lo = (int)((long long)rows * r / UF_CLUSTER), row_hi = (int)((long long)rows * (r + 1) / UF_CLUSTER);
-  double acc[MAXT];
+  double acc[3][MAXS];
 #pragma unroll
-  for (int k = 0; k < MAXT; ++k) acc[k] = 0;
+  for (int w = 0; w < 3; ++w)
+#pragma unroll
+    for (int ph = 0; ph < MAXS; ++ph) acc[w][ph] = 0;
   for (int row = row_lo; row < row_hi; ++row) {
     const float* gr = gy + (long long)(row / rows_per_batch) * gybs + (long long)(row % rows_per_batch) * t_out;
     const float* xr = x + (long long)row * t_in;
-    for (int o = threadIdx.x; o < t_out; o += UF_THREADS) {
-      const float gv = gr[o];
-      const int j = o / s, ph = o - j * s;
-      const float xm = j > 0 ? xr[j - 1] : 0.f, x0 = xr[j], xp = j + 1 < t_in ? xr[j + 1] : 0.f;
-      // tap k reads q = o + k - s = j*s + (ph + k - s); (ph + k - s) in [-s, 2s): index j-1, j or j+1 (out of range -> 0)
+    float f[3][MAXS];
 #pragma unroll
-      for (int k = 0; k < MAXT; ++k) {
-        if (k < ntap) {
-          const int d = ph + k - s;
-          const float xv = d < 0 ? xm : (d < s ? x0 : xp);
-          acc[k] += (double)gv * (double)xv;
+    for (int w = 0; w < 3; ++w)
+#pragma unroll
+      for (int ph = 0; ph < MAXS; ++ph) f[w][ph] = 0.f;
+    for (int j = threadIdx.x; j < t_in; j += UF_THREADS) {
+      const float xm = j > 0 ? xr[j - 1] : 0.f, x0 = xr[j], xp = j + 1 < t_in ? xr[j + 1] : 0.f;
+      const float* g = gr + (long long)j * s;
+#pragma unroll
+      for (int ph = 0; ph < MAXS; ++ph) {
+        if (ph < s) {
+          const float gv = g[ph];
+          f[0][ph] = fmaf(gv, xm, f[0][ph]);
+          f[1][ph] = fmaf(gv, x0, f[1][ph]);
+          f[2][ph] = fmaf(gv, xp, f[2][ph]);
         }
       }
     }
+#pragma unroll
+    for (int w = 0; w < 3; ++w)
+#pragma unroll
+      for (int ph = 0; ph < MAXS; ++ph) acc[w][ph] += (double)f[w][ph];
   }
 #pragma unroll
-  for (int k = 0; k < MAXT; ++k) {
-    double a = acc[k];
+  for (int w = 0; w < 3; ++w)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = a;
-  }
+    for (int ph = 0; ph < MAXS; ++ph) {
+      double a = acc[w][ph];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][w * MAXS + ph] = a;
+    }
   __syncthreads();
-  if (threadIdx.x < MAXT) {
+  if (threadIdx.x < 3 * MAXS) {
     double t = 0;
     for (int w = 0; w < UF_THREADS / 32; ++w) t += red[w][threadIdx.x];
     part[threadIdx.x] = t;
   }
   cl.sync();
-  if (r == 0 && threadIdx.x < ntap) {
+  if (r == 0 && threadIdx.x <= 2 * s) {
+    const int k = threadIdx.x;
     double tot = 0;
-    for (int k = 0; k < UF_CLUSTER; ++k) tot += cl.map_shared_rank(part, k)[threadIdx.x];
-    df[threadIdx.x] = (float)tot;
+    for (int ph = 0; ph < s; ++ph) {
+      const int d = ph + k - s;
+      const int w = d < 0 ? 0 : (d < s ? 1 : 2);
+      for (int c = 0; c < UF_CLUSTER; ++c) tot += cl.map_shared_rank(part, c)[w * MAXS + ph];
+    }
+    df[k] = (float)tot;
   }
   cl.sync();
 }
@@ -725,10 +744,10 @@ extern "C" int pwgb_upsample_fir_backward(int rows, int rows_per_batch, int t_in
   }
   if (dfir) {
     if (2 * scale + 1 <= UF_MAXT) {
-      if (2 * scale + 1 <= 9)
-        upsample_fir_backward_f_kernel<9><<<UF_CLUSTER, UF_THREADS, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
+      if (scale <= 4)
+        upsample_fir_backward_f_kernel<4><<<UF_CLUSTER, UF_THREADS, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
       else
-        upsample_fir_backward_f_kernel<UF_MAXT><<<UF_CLUSTER, UF_THREADS, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
+        upsample_fir_backward_f_kernel<UF_MAXS><<<UF_CLUSTER, UF_THREADS, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
       return check_launch("upsample_fir_backward_f_kernel");
     }
     upsample_fir_backward_f_tap_kernel<<<2 * scale + 1, 256, 0, st>>>(rows, t_in, scale, x, gy, dfir, rows_per_batch, gybs);
