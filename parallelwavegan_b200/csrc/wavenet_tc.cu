@@ -28,9 +28,10 @@
 //
 // Warp roles (640 threads, one persistent CTA per SM, mbarriers only; setmaxnreg moves registers from the single-warp
 // roles and the gate to the epilogue):
-//   warps 0-7   epilogue: SO (TMEM) -> skips (fp32, read-modify-write) and x' (packed); all global reads of a tile are
-//               requested before its accumulator is waited for
-//   warps 8-15  gate:     G (TMEM) -> registers -> z operand image (smem)
+//   warps 0-7   gate:     G (TMEM) -> registers -> z operand image (smem)
+//   warps 8-15  epilogue: SO (TMEM) -> registers (TMEM set released at once) -> 2 KB staging slice per warp -> bulk tensor
+//               stores: x' packed hi/lo, skips as an fp32 TMA reduce-add performed by the L2 (per-thread read-modify-
+//               write only when T % 4 != 0); the two warp groups swap the skip half and the residual half every tile
 //   warp  16    TMA loader: per stage two tensor-map loads (the pair's activation windows) + one bulk copy of the weight
 //               stage into a ring of 48 KB slots
 //   warps 17-18 conv issuers (elected lane): warp r issues tile r of every pair into TMEM set 2 (pair & 1) + r
