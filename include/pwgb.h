@@ -327,6 +327,8 @@ PWGB_API int pwgb_reduce_mean_backward(int mode, const float* x, const float* y,
 PWGB_API int pwgb_avg_pool1d_backward(const float* gy, float* gx, int rows, int t_in, int kernel, int stride, int padding,
                              int count_include_pad, void* stream);
 PWGB_API int pwgb_axpby(long long n, float a, const float* x, float b, float* y, void* stream);
+/* out = a * sum_k xs[k] (index order); xs: DEVICE array of n pointers to len floats; rows_16b_aligned: every xs[k] is 16-byte aligned */
+PWGB_API int pwgb_scaled_sum(const float* const* xs, int n, float a, float* out, long long len, int rows_16b_aligned, void* stream);
 /* Explicit ReflectionPad1d / ReplicationPad1d (melgan.py:70-72, residual_stack.py:49) of rows x t -> rows x
  * (pad_left + t + pad_right) and its adjoint (gather form, deterministic).  The forward convs fuse the
  * padding into their loaders; the train step materialises it once per layer so the weight / data

@@ -162,6 +162,8 @@ def lib():
     L.pwgb_avg_pool1d_backward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.pwgb_axpby.restype = C.c_int
     L.pwgb_axpby.argtypes = [C.c_longlong, C.c_float, vp, C.c_float, vp, vp]
+    L.pwgb_scaled_sum.restype = C.c_int
+    L.pwgb_scaled_sum.argtypes = [vp, C.c_int, C.c_float, vp, C.c_longlong, C.c_int, vp]
     L.pwgb_instance_norm_forward.restype = C.c_int
     L.pwgb_instance_norm_forward.argtypes = [vp, vp, C.c_longlong, C.c_longlong, C.c_float, C.c_float, vp]
     L.pwgb_upsample_nearest_forward.restype = C.c_int
@@ -229,7 +231,7 @@ EXPORTED_SYMBOLS = [
     "pwgb_mel_project_forward", "pwgb_reduce_mean_forward", "pwgb_avg_pool1d_forward",
     "pwgb_conv1d_wgrad_workspace", "pwgb_conv1d_wgrad", "pwgb_conv1d_wgrad_tc_supported",
     "pwgb_conv1d_wgrad_tc_workspace", "pwgb_conv1d_wgrad_tc", "pwgb_act_backward", "pwgb_bias_grad",
-    "pwgb_reduce_mean_backward", "pwgb_avg_pool1d_backward", "pwgb_axpby", "pwgb_pad1d_forward", "pwgb_pad1d_backward",
+    "pwgb_reduce_mean_backward", "pwgb_avg_pool1d_backward", "pwgb_axpby", "pwgb_scaled_sum", "pwgb_pad1d_forward", "pwgb_pad1d_backward",
     "pwgb_instance_norm_forward", "pwgb_upsample_nearest_forward", "pwgb_leaky_relu_forward", "pwgb_tade_combine_forward",
     "pwgb_tade_gate_forward", "pwgb_instance_norm_backward", "pwgb_upsample_nearest_backward", "pwgb_tade_combine_backward",
     "pwgb_tade_gate_backward",

@@ -315,6 +315,31 @@ __global__ void axpby_kernel(long long n, float a, const float* __restrict__ x, 
     y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
 }
 
+// out = a * (x_0 + x_1 + ... + x_{n-1}) accumulated in index order (the skip sum of the WaveNet stack, the MRF average of
+// HiFi-GAN): every input is read once; `xs` is a device array of n pointers.
+__global__ void scaled_sum_kernel(const float* const* __restrict__ xs, int n, float a, float* __restrict__ out, long long len,
+                                  int vec) {
+  if (vec) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len / 4; i += (long long)gridDim.x * blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < n; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xs[k]) + i);
+        acc.x = fmaf(a, v.x, acc.x);
+        acc.y = fmaf(a, v.y, acc.y);
+        acc.z = fmaf(a, v.z, acc.z);
+        acc.w = fmaf(a, v.w, acc.w);
+      }
+      reinterpret_cast<float4*>(out)[i] = acc;
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
+      float acc = 0.f;
+      for (int k = 0; k < n; ++k) acc = fmaf(a, xs[k][i], acc);
+      out[i] = acc;
+    }
+  }
+}
+
 // Explicit reflect / replicate padding (torch.nn.ReflectionPad1d / ReplicationPad1d in front of the MelGAN
 // convs, melgan.py:70-72, residual_stack.py:49) and its adjoint.  mode: PWGB_PAD_*.
 __device__ __forceinline__ long long pad_src(long long e, long long T, int pl, int mode) {
@@ -677,6 +702,15 @@ extern "C" int pwgb_axpby(long long n, float a, const float* x, float b, float* 
   if (n == 0) return PWGB_OK;
   axpby_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y);
   return check_launch("axpby_kernel");
+}
+
+extern "C" int pwgb_scaled_sum(const float* const* xs, int n, float a, float* out, long long len, int rows_16b_aligned,
+                               void* stream) {
+  PWGB_CHECK_ARG(xs && out && n > 0 && len >= 0, "scaled_sum: bad arguments");
+  if (len == 0) return PWGB_OK;
+  const int vec = rows_16b_aligned && len % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  scaled_sum_kernel<<<grid_for(vec ? len / 4 : len), 256, 0, (cudaStream_t)stream>>>(xs, n, a, out, len, vec);
+  return check_launch("scaled_sum_kernel");
 }
 
 extern "C" int pwgb_pad1d_forward(const float* x, float* xp, long long rows, long long t, int pad_left, int pad_right,
